@@ -1,0 +1,159 @@
+"""Pin the numpy oracle against outputs of the reference itself (tests/golden/*.npz).
+
+CPU only.  The reference ships no tests or golden vectors for this path, so
+these fixtures -- produced by importing /root/reference in the build container -- are the pin.
+"""
+import numpy as np
+import pytest
+
+from oracle import fakequant_oracle as O
+
+INT_BITS = [2, 3, 4, 5, 6, 8]
+GROUPS = [32, 64, 128, 256, -1, -2]
+FORMATS = {"e2m1": (2, 1), "e1m2": (1, 2), "e3m2": (3, 2), "e2m3": (2, 3), "e4m3": (4, 3), "e5m2": (5, 2)}
+
+
+def _nan_equal_bits(a, b, dtype):
+    """bit equality, except that any NaN matches any NaN (payloads are not part of the contract)."""
+    fa, fb = O.from_bits(a, dtype), O.from_bits(b, dtype)
+    both_nan = np.isnan(fa) & np.isnan(fb)
+    return np.array_equal(np.where(both_nan, 0, a), np.where(both_nan, 0, b))
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+@pytest.mark.parametrize("sym", [False, True])
+@pytest.mark.parametrize("bits", INT_BITS)
+def test_int_matches_reference(golden, dtype, sym, bits):
+    g = golden("golden_int")
+    w = g[f"w_{dtype}"]
+    for grp in GROUPS:
+        key = f"{dtype}_b{bits}_{'sym' if sym else 'asym'}_g{grp}"
+        r = O.int_fake_quant(w, dtype, bits, not sym, grp)
+        # module form: weights, scales, zeros (quant_linear.py:885-956)
+        assert _nan_equal_bits(r["out"], g[f"ql_{key}_out"], dtype), key
+        assert _nan_equal_bits(r["scales"], g[f"ql_{key}_scales"], dtype), key
+        if not sym:
+            # sign of a zero zero-point is not observable in the output; compare values
+            assert np.array_equal(O.from_bits(r["zeros"], dtype), O.from_bits(g[f"ql_{key}_zeros"], dtype)), key
+        # function form (quant_funcs.py:4-46) either asserts on NaN or returns the same bits
+        if f"fn_{key}_assert" in g.files:
+            assert r["has_nan"], key
+        else:
+            assert not r["has_nan"], key
+            assert np.array_equal(r["out"], g[f"fn_{key}"]), key
+
+
+def test_int_inplace_same_as_out_of_place(golden):
+    g = golden("golden_int")
+    assert np.array_equal(g["fn_inplace_f16_b4_asym_g128"], g["fn_f16_b4_asym_g128"])
+    assert np.array_equal(g["fn_inplace_mutated_input"], g["fn_f16_b4_asym_g128"])
+
+
+def test_int_output_never_negative_zero(golden):
+    g = golden("golden_int")
+    for k in g.files:
+        if k.startswith("fn_") and not k.endswith("_assert") and "inplace" not in k:
+            assert not (g[k] == 0x8000).any(), k
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+@pytest.mark.parametrize("fmt", list(FORMATS))
+def test_fp_codec_exhaustive(golden, dtype, fmt):
+    """decode(encode(x)) for every 16-bit input, restricted to |x| <= fmax (the codec is only ever
+    fed clamped values: quant_linear.py:747,755) and, for bf16, |x| >= 2^-126 (quirk Q5)."""
+    E, M = FORMATS[fmt]
+    g = golden("golden_fp_tables")
+    bits = np.arange(65536, dtype=np.uint32).astype(np.uint16)
+    x = O.from_bits(bits, dtype)
+    _, _, _, fmax = O.fp_format(E, M)
+    ok = np.isfinite(x) & (np.abs(x) <= fmax)
+    if dtype == "bf16":
+        ok &= (np.abs(x) >= 2.0 ** -126) | (x == 0)
+    code = O.fp_codec_encode(x, E, M, dtype)
+    val = O.to_bits(O.fp_codec_decode(code, E, M), dtype)
+    assert np.array_equal(code[ok], g[f"codec_{dtype}_{fmt}_code"][ok])
+    assert np.array_equal(val[ok], g[f"codec_{dtype}_{fmt}_val"][ok])
+    assert ok.sum() > 20000
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+def test_log2_rounding_margin(dtype):
+    """Quirk Q3 depends on whether log2(x), rounded to the 16-bit dtype, reaches the next integer k.
+    That decision is "log2(x) >= midpoint(pred_D(k), k)".  Show that for every finite positive input
+    the exact log2 is at least 64 fp32 ulps away from that midpoint, so any faithful fp32 log2 (Sleef,
+    glibc, CUDA) -- and the closed-form per-binade thresholds the CUDA kernels use -- agree."""
+    bits = np.arange(1, 0x7C00 if dtype == "f16" else 0x7F80, dtype=np.uint32).astype(np.uint16)
+    x = O.from_bits(bits, dtype).astype(np.float64)
+    x = x[x >= 2.0 ** -126]
+    l = np.log2(x)
+    k = np.floor(l) + 1.0  # the integer just above log2(x)
+    kb = O.to_bits(k.astype(np.float32), dtype).astype(np.int32)
+    # predecessor of k in D (towards -inf): k > 0 -> bits-1 ; k == 0 -> -min_subnormal ; k < 0 -> bits+1
+    pred = O.from_bits(np.where(k > 0, kb - 1, np.where(k == 0, 0x8001, kb + 1)).astype(np.uint16), dtype).astype(np.float64)
+    mid = (pred + k) / 2
+    ulp32 = np.maximum(np.abs(l), 2.0 ** -126) * 2.0 ** -23
+    notpow2 = np.floor(l) != l
+    assert (np.abs(l - mid)[notpow2] > 64 * ulp32[notpow2]).all()
+    # and the oracle's rounding agrees with the midpoint rule
+    l16 = O.rD(l.astype(np.float32), dtype).astype(np.float64)
+    assert np.array_equal((l16 == k)[notpow2], (l > mid)[notpow2])
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+@pytest.mark.parametrize("fmt", list(FORMATS))
+def test_fp_chain_matches_reference(golden, dtype, fmt):
+    E, M = FORMATS[fmt]
+    if dtype == "f16" and E >= 5:
+        with pytest.raises(RuntimeError):
+            O.fp_codec_fake_quant(np.zeros((2, 32), np.uint16), dtype, E, M, True, 32)
+        return
+    g = golden("golden_fp_chain")
+    w = g[f"w_{dtype}"]
+    for sym in (False, True):
+        for grp in (32, 128, -1, -2):
+            key = f"{dtype}_{fmt}_{'sym' if sym else 'asym'}_g{grp}"
+            r = O.fp_codec_fake_quant(w, dtype, E, M, sym, grp)
+            assert _nan_equal_bits(r["out"], g[f"ql_{key}_out"], dtype), key
+            assert np.array_equal(r["scales_half"], g[f"ql_{key}_scales_half"]), key
+            if not sym:
+                assert np.array_equal(O.from_bits(r["zeros_half"], "f16"), O.from_bits(g[f"ql_{key}_zeros_half"], "f16")), key
+
+
+@pytest.mark.parametrize("fmt", ["e2m1", "e1m2", "e3m2", "e2m3", "e4m3"])
+def test_fp_rne_scale_exhaustive(golden, fmt):
+    E, M = FORMATS[fmt]
+    g = golden("golden_fp_tables")
+    bits = np.arange(65536, dtype=np.uint32).astype(np.uint16)
+    x = O.from_bits(bits, "f16")
+    bias = 2 ** (E - 1) - 1
+    mf = (2 - 2 ** (-M)) * 2 ** (2 ** E - 1 - bias)
+    q = O.fp_rne_scale(x, np.float32(1.0), M, bias, mf, -mf, "f16")
+    ok = np.isfinite(x)
+    assert np.array_equal(O.to_bits(q, "f16")[ok], g[f"fpscale_f16_{fmt}"][ok])
+
+
+def test_fp_rne_matches_reference(golden):
+    g = golden("golden_fp_rne")
+    w = g["w_f16"]
+    for grp in (32, 128, 512):
+        r = O.fp_rne_fake_quant(w, 2, 1, grp)
+        assert tuple(g[f"e2m1_g{grp}_shape"]) == r["out"].shape
+        assert _nan_equal_bits(r["out"], g[f"e2m1_g{grp}"], "f16"), grp
+    r = O.fp_rne_fake_quant(w, 2, 1, -1, per_tensor=True)
+    assert tuple(g["e2m1_pt_shape"]) == r["out"].shape
+    assert _nan_equal_bits(r["out"], g["e2m1_pt"], "f16")
+    # the reference's own __main__ smoke input (fp4_quantize_cpu.py:74-80)
+    r = O.fp_rne_fake_quant(g["main_w"], 2, 1, 128)
+    assert np.array_equal(r["out"], g["main_out"])
+
+
+def test_error_contract():
+    w = np.zeros((4, 100), np.uint16)
+    with pytest.raises(AssertionError):
+        O.int_fake_quant(w, "f16", 4, True, 32)  # quant_funcs.py:11
+    with pytest.raises(AssertionError):
+        O.int_fake_quant(np.zeros((4,), np.uint16), "f16", 4, True, -2)  # quant_funcs.py:15
+    with pytest.raises(ValueError):
+        O.int_fake_quant(w, "f16", 4, True, -3)  # quant_linear.py:906
+    with pytest.raises(ValueError):
+        O.fp_rne_fake_quant(w, 2, 1, 32)  # fp4_quantize_cpu.py:55-56
