@@ -1,0 +1,129 @@
+/*
+ * iwq_b200.h -- C ABI of the B200 (sm_100a) weight fake-quant library `libiwq_b200.so`.
+ *
+ * The reference (LiuTielong/Iron_weight_only_quant) has no FFI layer on this path: the path sits
+ * behind Python call signatures and is executed as sequences of ATen eager ops.  Each entry point
+ * below therefore cites the reference *Python* interface whose arithmetic it replaces (file:line
+ * relative to the reference repo); the Python modules in `iron_weight_only_quant_b200/` keep those
+ * signatures and bind these symbols through ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - plain C types only; all data pointers are DEVICE pointers unless the name says `host`;
+ *   - `stream` is a `cudaStream_t` passed as `void*`; work is enqueued on it, nothing synchronises
+ *     unless stated; the caller makes `device` current or passes it explicitly where asked;
+ *   - return value: 0 on success, a negative `IWQ_ERR_*` otherwise; `iwq_last_error()` gives text;
+ *   - weights are row-major contiguous 2-D `[rows, cols]` of fp16 or bf16, `out` may alias `w`
+ *     (the reference overwrites the weight storage in place: quant_linear.py:949).
+ */
+#ifndef IWQ_B200_H_
+#define IWQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IWQ_ABI_VERSION 1
+
+/* storage dtype of weights, scales and zeros */
+enum { IWQ_F16 = 0, IWQ_BF16 = 1 };
+
+/* quantisation scheme */
+enum {
+  IWQ_SCHEME_INT = 0,      /* quant_funcs.py:4-46 == quant_linear.py:885-956 (INT min-max, asym/sym)   */
+  IWQ_SCHEME_FP_CODEC = 1, /* quant_linear.py:724-883 + _float_to_fp :126-163 + _fp_to_float :213-235 */
+  IWQ_SCHEME_FP_RNE = 2    /* fp4_quantize_cpu.py:37-72 (_fp_scale, ideal RNE minifloat, absmax scale) */
+};
+
+/* granularity: `group` > 0 -> contiguous runs of `group` elements along `cols`
+ * (quant_funcs.py:10-12); IWQ_GROUP_PER_TENSOR (-1) -> one range for the matrix (quant_funcs.py:13-14,
+ * quant_linear.py:898-900); IWQ_GROUP_PER_CHANNEL (-2) -> one range per row (quant_linear.py:901-903). */
+enum { IWQ_GROUP_PER_TENSOR = -1, IWQ_GROUP_PER_CHANNEL = -2 };
+
+enum {
+  IWQ_OK = 0,
+  IWQ_ERR_INVALID = -1,     /* bad argument (maps to ValueError)                                        */
+  IWQ_ERR_INDIVISIBLE = -2, /* cols % group != 0 (maps to AssertionError, quant_funcs.py:11)            */
+  IWQ_ERR_UNSUPPORTED = -3, /* combination the kernels do not implement (maps to NotImplementedError)   */
+  IWQ_ERR_CUDA = -4,        /* a CUDA runtime call failed                                               */
+  IWQ_ERR_ALIGN = -5,       /* pointer not 16-byte aligned                                              */
+  IWQ_ERR_FP16_RANGE = -6   /* minifloat max not representable in fp16 (reference raises RuntimeError)  */
+};
+
+/* status bits OR-ed into the optional device status word by the kernels */
+enum {
+  IWQ_STATUS_NAN = 1 /* some segment produced NaN: the condition of `assert torch.isnan(t).sum()==0`
+                        (quant_funcs.py:40); checked lazily by the host */
+};
+
+typedef struct iwq_config {
+  int32_t dtype;     /* IWQ_F16 / IWQ_BF16                                                             */
+  int32_t scheme;    /* IWQ_SCHEME_*                                                                   */
+  int32_t bits;      /* INT: n_bits (1..15).  FP schemes: ignored                                      */
+  int32_t exp_bits;  /* FP schemes: exponent bits E (1..5)                                             */
+  int32_t mant_bits; /* FP schemes: mantissa bits M (0..6)                                             */
+  int32_t symmetric; /* 1: absmax scale, no zero point (zero_point=False); 0: min/max (zero_point=True)*/
+  int32_t group;     /* > 0, IWQ_GROUP_PER_TENSOR, IWQ_GROUP_PER_CHANNEL                               */
+  int32_t variant;   /* kernel variant: 0 = default (TMA bulk-copy staged), 1 = direct global loads    */
+} iwq_config_t;
+
+typedef struct iwq_matrix {
+  const void* w;  /* [rows, cols] input                                                               */
+  void* out;      /* [rows, cols] fake-quantised output; may equal `w`                                */
+  void* scales;   /* optional [G] scales in the weight dtype (G = rows*cols/group | rows | 1)         */
+  void* zeros;    /* optional [G]: INT asym zero points / FP asym mid points, weight dtype            */
+  void* codes;    /* optional [rows, cols] uint8: INT code (two's complement for sym) / minifloat code*/
+  int64_t rows;
+  int64_t cols;
+} iwq_matrix_t;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int iwq_abi_version(void);
+const char* iwq_last_error(void);
+/* bytes of device workspace `iwq_fake_quant_batched` needs for `n` matrices */
+size_t iwq_workspace_bytes(int n);
+
+/* ---- the hot path ----------------------------------------------------------------------------- */
+/* One fused pass over one matrix.  Replaces pseudo_quantize_tensor (quant_funcs.py:4-46), the INT
+ * and FP4/6/8 branches of QuantLinear.quantize_weight (quant_linear.py:724-956) and
+ * quantize_fp16_to_fp4_e1m2 (fp4_quantize_cpu.py:47-72).  `status` (device int32*, may be NULL)
+ * receives IWQ_STATUS_* bits via atomicOr.  Per-tensor granularity runs a min/max pass first and needs
+ * `range_ws` (device, 2 floats); other granularities ignore it. */
+int iwq_fake_quant(const iwq_config_t* cfg, const iwq_matrix_t* m, float* range_ws, int32_t* status, void* stream);
+
+/* The same for `n` matrices sharing one config, in ONE launch per pass (persistent work-list kernel):
+ * replaces the per-module loop of quantize_model (quant_wrapper.py:52-82).  `workspace` is device
+ * memory of at least iwq_workspace_bytes(n). */
+int iwq_fake_quant_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, void* workspace, size_t workspace_bytes,
+                           int32_t* status, void* stream);
+
+/* ---- per-tensor granularity on a matrix that is sharded across GPUs (no reference counterpart;
+ *      SURVEY.md section 8e): range pass, (NCCL MAX all-reduce of `range` by the caller), apply pass.
+ * `range`: device float[2*n] laid out {max_or_absmax, -min} per matrix, so one MAX reduction serves both. */
+int iwq_minmax(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, float* range, void* workspace, size_t workspace_bytes,
+               void* stream);
+int iwq_fake_quant_with_range(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, const float* range, void* workspace,
+                              size_t workspace_bytes, int32_t* status, void* stream);
+
+/* ---- element-wise pieces, exposed for exhaustive parity tests ---------------------------------- */
+/* decode(encode(x)) of the quant_linear minifloat codec on `n` 16-bit values (quant_linear.py:126-163,
+ * :213-235); `codes` optional. flavour = IWQ_SCHEME_FP_CODEC or IWQ_SCHEME_FP_RNE (then: _fp_scale with S=1). */
+int iwq_fp_roundtrip(int dtype, int flavour, int exp_bits, int mant_bits, const void* x, void* y, void* codes, int64_t n, void* stream);
+/* exhaustive device check of the reciprocal+FMA quotient against IEEE division for every (w, s) pair of
+ * the dtype; writes the number of mismatching pairs to *mismatches (device int64*, caller zeroes it). */
+int iwq_selftest_division(int dtype, unsigned long long* mismatches, void* stream);
+
+/* ---- host-buffer pipeline (end-to-end path) ---------------------------------------------------- */
+/* Fake-quantise a matrix that lives in HOST memory (pinned for full speed): chunks are copied to the
+ * device, quantised and copied back on alternating streams so that H2D, kernel and D2H overlap.
+ * `host_out` may equal `host_w`.  Synchronises before returning.  `device` is the CUDA device ordinal.
+ * Only group > 0 and per-channel granularity (chunk boundaries fall on rows). */
+int iwq_fake_quant_host(const iwq_config_t* cfg, const void* host_w, void* host_out, int64_t rows, int64_t cols, int device,
+                        size_t chunk_bytes, int32_t* host_status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IWQ_B200_H_ */

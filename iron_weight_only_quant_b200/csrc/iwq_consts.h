@@ -1,0 +1,132 @@
+// iwq_consts.h -- host-side construction of the launch constants (QuantConsts), including the
+// per-binade minifloat table.  Header-only so that the test-only CPU emulator (tests/host/emulate.cu)
+// builds the same table as the library.
+#pragma once
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+
+#include "iwq_math.cuh"
+
+namespace iwq {
+
+enum { KIND_INT_FAST = 0, KIND_INT_WIDE = 1, KIND_FP = 2, KIND_INT_GENERIC = 3 };
+
+static inline float round_to_dtype(int dtype, float x) { return dtype == IWQ_F16 ? rD<IWQ_F16>(x) : rD<IWQ_BF16>(x); }
+
+// number of D values a in [2^(k-1), 2^k) whose log2, rounded to D, reaches k (quirk Q3):
+// log2(a) > midpoint(pred_D(k), k).  Closed form in double precision; the margin to every decision
+// boundary is > 64 fp32 ulps (tests/test_oracle_golden.py::test_log2_rounding_margin).
+static inline int log2_bump_count(int dtype, int k) {
+  const int MB = dtype == IWQ_F16 ? 10 : 7;
+  if (k == 0) return 0;
+  const double ak = fabs((double)k);
+  int fl = (int)floor(log2(ak));
+  double ulp_below;  // spacing of D just below |k| (k > 0) / just above |k| (k < 0)
+  if (k > 0) {
+    const bool pow2 = ldexp(1.0, fl) == ak;
+    ulp_below = ldexp(1.0, (pow2 ? fl - 1 : fl) - MB);
+  } else {
+    ulp_below = ldexp(1.0, fl - MB);
+  }
+  const double mid = (double)k - ulp_below * 0.5;
+  int cnt = 0;
+  for (int j = 1; j < (1 << MB); ++j) {
+    const double l = (double)k + log2(1.0 - ldexp((double)j, -(MB + 1)));
+    if (l > mid) ++cnt; else break;
+  }
+  return cnt;
+}
+
+static inline int build_quant_consts(const iwq_config_t* cfg, QuantConsts* c, int* kind, std::string* err) {
+  auto fail = [&](int code, const char* msg) { *err = msg; return code; };
+  memset(c, 0, sizeof(*c));
+  const int dt = cfg->dtype;
+  if (dt != IWQ_F16 && dt != IWQ_BF16) return fail(IWQ_ERR_INVALID, "dtype must be IWQ_F16 or IWQ_BF16");
+  c->scheme = cfg->scheme;
+  c->bits = cfg->bits;
+  c->exp_bits = cfg->exp_bits;
+  c->mant_bits = cfg->mant_bits;
+  c->symmetric = cfg->symmetric ? 1 : 0;
+  if (cfg->scheme == IWQ_SCHEME_INT) {
+    const int b = cfg->bits;
+    if (b < 1 || b > 15) return fail(IWQ_ERR_INVALID, "INT bits must be in [1, 15]");
+    if (c->symmetric) {
+      c->max_int = (float)((1 << (b - 1)) - 1);
+      c->min_int = -(float)(1 << (b - 1));
+    } else {
+      c->max_int = (float)((1 << b) - 1);
+      c->min_int = 0.0f;
+    }
+    c->eps = round_to_dtype(dt, 1e-5f);
+    const float span = fmaxf(fabsf(c->min_int), fabsf(c->max_int));
+    if (dt == IWQ_F16) {
+      *kind = span <= 256.0f ? KIND_INT_FAST : KIND_INT_GENERIC;
+    } else {
+      *kind = span <= 64.0f ? KIND_INT_FAST : (span <= 256.0f ? KIND_INT_WIDE : KIND_INT_GENERIC);
+    }
+    if (getenv("IWQ_FORCE_GENERIC")) *kind = KIND_INT_GENERIC;
+    return IWQ_OK;
+  }
+  if (cfg->scheme != IWQ_SCHEME_FP_CODEC && cfg->scheme != IWQ_SCHEME_FP_RNE) return fail(IWQ_ERR_INVALID, "unknown scheme");
+  const bool rne = cfg->scheme == IWQ_SCHEME_FP_RNE;
+  const int E = cfg->exp_bits, M = cfg->mant_bits;
+  if (E < 1 || E > 5 || M < 0 || M > 6 || E + M > 7) return fail(IWQ_ERR_INVALID, "minifloat needs 1<=E<=5, 0<=M<=6, E+M<=7");
+  if (rne && M > 3) return fail(IWQ_ERR_UNSUPPORTED, "FP_RNE flavour is implemented (and verified exhaustively) for M <= 3");
+  if (rne && dt != IWQ_F16) return fail(IWQ_ERR_UNSUPPORTED, "FP_RNE flavour is fp16 only (the reference casts to fp16: fp4_quantize_cpu.py:48-49)");
+  if (rne) c->symmetric = 1;
+  c->flavour_rne = rne ? 1 : 0;
+  const int MB = dt == IWQ_F16 ? 10 : 7, DB = dt == IWQ_F16 ? 15 : 127;
+  const int max_field = dt == IWQ_F16 ? 30 : 254;
+  const int bias = (1 << (E - 1)) - 1, emin = 1 - bias, emax = (1 << E) - 1 - bias;
+  const double fmax = (2.0 - ldexp(1.0, -M)) * ldexp(1.0, emax);
+  if (dt == IWQ_F16 && fmax > 65504.0) return fail(IWQ_ERR_FP16_RANGE, "value cannot be converted to type at::Half without overflow");
+  c->fmax = (float)fmax;
+  c->eps = round_to_dtype(dt, rne ? 1e-8f : 1e-5f);
+  int elo = emin - M - 3;
+  if (elo < 1 - DB) elo = 1 - DB;
+  if (elo > emin - M - 2) return fail(IWQ_ERR_UNSUPPORTED, "minifloat grid too fine for the storage dtype");
+  const int n = emax - elo + 1;
+  if (n > 40) return fail(IWQ_ERR_UNSUPPORTED, "minifloat exponent range too wide");
+  const uint16_t inf_bits = dt == IWQ_F16 ? 0x7C00 : 0x7F80;
+  for (int i = 0; i < n; ++i) {
+    const int e = elo + i;
+    const int ge = e > emin ? e : emin;
+    const int mfield = ge - M + MB + DB;
+    if (mfield < 1 || mfield > max_field) return fail(IWQ_ERR_UNSUPPORTED, "minifloat magic constant not representable in the storage dtype");
+    FpEntry en;
+    en.magic = (uint16_t)((mfield << MB) | (1 << (MB - 1)));
+    if (rne) {
+      en.bound = inf_bits;
+    } else if (e >= emin) {
+      en.bound = (uint16_t)(((e + DB) << MB) | (((1 << M) - 1) << (MB - M)));
+    } else if (M == 0) {
+      en.bound = 0;
+    } else {
+      en.bound = (uint16_t)(((emin - 1 + DB) << MB) | (((1 << (M - 1)) - 1) << (MB - (M - 1))));
+    }
+    en.bump_thr = inf_bits;
+    en.bump_val = 0;
+    const int k = e + 1;
+    if (!rne && k >= emin && k <= emax) {
+      const int cnt = log2_bump_count(dt, k);
+      if (cnt > 0) {
+        en.bump_thr = (uint16_t)(((e + DB) << MB) | ((1 << MB) - cnt));
+        en.bump_val = (uint16_t)((k + DB) << MB);
+      }
+    }
+    c->tbl[i] = en;
+  }
+  c->tbl_base = elo + DB;
+  c->tbl_n = n;
+  c->tiny_bits = (uint16_t)((elo + DB) << MB);
+  c->fmax_bits = (uint16_t)(((emax + DB) << MB) | (((1 << M) - 1) << (MB - M)));
+  *kind = KIND_FP;
+  return IWQ_OK;
+}
+
+
+}  // namespace iwq

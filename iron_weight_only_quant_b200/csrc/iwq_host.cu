@@ -1,0 +1,481 @@
+// iwq_host.cu -- C ABI of libiwq_b200.so (declared in include/iwq_b200.h): argument validation,
+// launch-constant construction (including the per-binade minifloat table), work-list building and
+// kernel dispatch.  No torch types; plain pointers, sizes and a cudaStream_t.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "iwq_consts.h"
+#include "iwq_launch.cuh"
+
+namespace iwq {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+static int fail_cuda(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return IWQ_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tuning knobs (environment, read once): ring depth, CTAs per SM, forced kernel variant
+// ------------------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+struct Knobs {
+  int seg_stages = env_int("IWQ_SEG_STAGES", 6);
+  int seg_ctas = env_int("IWQ_SEG_CTAS", 0);
+  int row_ctas = env_int("IWQ_ROW_CTAS", 0);
+  int row_smem_kb = env_int("IWQ_ROW_SMEM_KB", 0);  // per-CTA ring budget; 0 = automatic
+  int variant = env_int("IWQ_VARIANT", -1);          // -1: use cfg->variant
+};
+static const Knobs& knobs() {
+  static Knobs k;
+  return k;
+}
+
+static int build_consts(const iwq_config_t* cfg, QuantConsts* c, int* kind) {
+  std::string msg;
+  int rc = build_quant_consts(cfg, c, kind, &msg);
+  if (rc) return fail(rc, msg);
+  return IWQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch over (dtype, kind)
+// ------------------------------------------------------------------------------------------------
+static cudaError_t dispatch_seg(int dt, int kind, const LaunchParams& p, bool sym, bool given, int variant, const LaunchTuning& t,
+                                cudaStream_t st) {
+  if (dt == IWQ_F16) {
+    switch (kind) {
+      case KIND_INT_FAST: return launch_seg<IWQ_F16, KIND_INT_FAST>(p, sym, given, variant, t, st);
+      case KIND_FP: return launch_seg<IWQ_F16, KIND_FP>(p, sym, given, variant, t, st);
+      default: return launch_seg<IWQ_F16, KIND_INT_GENERIC>(p, sym, given, variant, t, st);
+    }
+  }
+  switch (kind) {
+    case KIND_INT_FAST: return launch_seg<IWQ_BF16, KIND_INT_FAST>(p, sym, given, variant, t, st);
+    case KIND_INT_WIDE: return launch_seg<IWQ_BF16, KIND_INT_WIDE>(p, sym, given, variant, t, st);
+    case KIND_FP: return launch_seg<IWQ_BF16, KIND_FP>(p, sym, given, variant, t, st);
+    default: return launch_seg<IWQ_BF16, KIND_INT_GENERIC>(p, sym, given, variant, t, st);
+  }
+}
+static cudaError_t dispatch_row(int dt, int kind, const LaunchParams& p, bool sym, int consumers, const LaunchTuning& t, cudaStream_t st) {
+  if (dt == IWQ_F16) {
+    switch (kind) {
+      case KIND_INT_FAST: return launch_row<IWQ_F16, KIND_INT_FAST>(p, sym, consumers, t, st);
+      case KIND_FP: return launch_row<IWQ_F16, KIND_FP>(p, sym, consumers, t, st);
+      default: return launch_row<IWQ_F16, KIND_INT_GENERIC>(p, sym, consumers, t, st);
+    }
+  }
+  switch (kind) {
+    case KIND_INT_FAST: return launch_row<IWQ_BF16, KIND_INT_FAST>(p, sym, consumers, t, st);
+    case KIND_INT_WIDE: return launch_row<IWQ_BF16, KIND_INT_WIDE>(p, sym, consumers, t, st);
+    case KIND_FP: return launch_row<IWQ_BF16, KIND_FP>(p, sym, consumers, t, st);
+    default: return launch_row<IWQ_BF16, KIND_INT_GENERIC>(p, sym, consumers, t, st);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// work-list construction
+// ------------------------------------------------------------------------------------------------
+enum Path { PATH_SEG, PATH_ROW };
+
+struct Plan {
+  Path path;
+  int lps, vpl;            // seg path
+  uint32_t seg_elems;      // elements per segment (group, or cols)
+  uint32_t stage_bytes;    // row path
+  int stages, consumers;   // row path
+};
+
+static bool seg_shape(uint64_t seg_elems, int* lps, int* vpl) {
+  // group = 8 * lps * vpl with lps in {1,2,4,8,16,32}; vpl in {1,2,4} only once lps == 32
+  if (seg_elems < 8 || seg_elems > 1024 || (seg_elems & (seg_elems - 1))) return false;
+  uint64_t vecs = seg_elems / 8;
+  if (vecs <= 32) {
+    *lps = (int)vecs;
+    *vpl = 1;
+  } else {
+    *lps = 32;
+    *vpl = (int)(vecs / 32);
+  }
+  return true;
+}
+
+static int check_matrix(const iwq_matrix_t* m) {
+  if (!m->w || !m->out) return fail(IWQ_ERR_INVALID, "null weight/output pointer");
+  if (m->rows <= 0 || m->cols <= 0) return fail(IWQ_ERR_INVALID, "rows and cols must be positive");
+  if (((uintptr_t)m->w | (uintptr_t)m->out) & 15) return fail(IWQ_ERR_ALIGN, "weight/output pointers must be 16-byte aligned");
+  if ((uint64_t)m->rows * (uint64_t)m->cols * 2 >= (1ull << 45)) return fail(IWQ_ERR_INVALID, "matrix too large");
+  return IWQ_OK;
+}
+
+// decide the kernel path for one (cfg.group, cols); all matrices of a batched call must agree
+static int make_plan(const iwq_config_t* cfg, int64_t cols, Plan* pl) {
+  const int g = cfg->group;
+  uint64_t seg;
+  if (g > 0) {
+    if (cols % g != 0) return fail(IWQ_ERR_INDIVISIBLE, "cols is not divisible by the group size");
+    seg = (uint64_t)g;
+  } else if (g == IWQ_GROUP_PER_CHANNEL) {
+    seg = (uint64_t)cols;
+  } else if (g == IWQ_GROUP_PER_TENSOR) {
+    seg = 0;
+  } else {
+    return fail(IWQ_ERR_INVALID, "Invalid w_group_size");
+  }
+  memset(pl, 0, sizeof(*pl));
+  pl->seg_elems = (uint32_t)seg;
+  if (g == IWQ_GROUP_PER_TENSOR) {
+    pl->path = PATH_SEG;
+    pl->lps = 1;
+    pl->vpl = 1;
+    return IWQ_OK;
+  }
+  if (seg_shape(seg, &pl->lps, &pl->vpl)) {
+    pl->path = PATH_SEG;
+    return IWQ_OK;
+  }
+  if (seg % 8 != 0) return fail(IWQ_ERR_UNSUPPORTED, "segment length must be a multiple of 8 elements (16-byte vectors)");
+  const uint64_t row_bytes = seg * 2;
+  const uint32_t stage = (uint32_t)((row_bytes + 127) & ~127ull);
+  const uint64_t max_ring = 200 * 1024;
+  if (2ull * stage > max_ring) return fail(IWQ_ERR_UNSUPPORTED, "row longer than 51200 elements: not implemented for per-channel granularity");
+  pl->path = PATH_ROW;
+  pl->stage_bytes = stage;
+  const uint64_t vecs = row_bytes / 16;
+  pl->consumers = vecs >= 2048 ? 512 : (vecs >= 384 ? 256 : (vecs >= 96 ? 128 : 64));
+  // ring budget per CTA: aim for >= 3 CTAs per SM on short rows, 2 on long ones
+  uint64_t budget = knobs().row_smem_kb > 0 ? (uint64_t)knobs().row_smem_kb * 1024 : (stage <= 24 * 1024 ? 64 * 1024 : 100 * 1024);
+  int st = (int)(budget / stage);
+  if (st < 2) st = 2;
+  if (st > kMaxStages) st = kMaxStages;
+  pl->stages = st;
+  return IWQ_OK;
+}
+
+static Job make_job(const iwq_matrix_t* m, uint32_t first_unit) {
+  Job j;
+  memset(&j, 0, sizeof(j));
+  j.src = (const uint8_t*)m->w;
+  j.dst = (uint8_t*)m->out;
+  j.scales = (uint8_t*)m->scales;
+  j.zeros = (uint8_t*)m->zeros;
+  j.codes = (uint8_t*)m->codes;
+  j.bytes = (uint64_t)m->rows * (uint64_t)m->cols * 2;
+  j.first_unit = first_unit;
+  j.row_bytes = (uint32_t)(m->cols * 2);
+  return j;
+}
+
+static int effective_variant(const iwq_config_t* cfg) { return knobs().variant >= 0 ? knobs().variant : cfg->variant; }
+
+// Fill LaunchParams for `n` matrices; `jobs_host` receives the table (uploaded by the caller when n > 1).
+static int fill_params(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, const Plan& pl, LaunchParams* p, std::vector<Job>* jobs_host) {
+  jobs_host->clear();
+  uint64_t units = 0;
+  for (int i = 0; i < n; ++i) {
+    int rc = check_matrix(&ms[i]);
+    if (rc) return rc;
+    if (units >= 0xFFFFFFFFull) return fail(IWQ_ERR_INVALID, "too much work for one launch");
+    Job j = make_job(&ms[i], (uint32_t)units);
+    if (pl.path == PATH_SEG) {
+      units += (j.bytes + kTileBytes - 1) / kTileBytes;
+    } else {
+      j.row_bytes = pl.seg_elems * 2;  // a "row" is one segment (per-channel row, or an odd-sized group)
+      units += j.bytes / j.row_bytes;
+    }
+    jobs_host->push_back(j);
+  }
+  if (units >= 0xFFFFFFFFull) return fail(IWQ_ERR_INVALID, "too much work for one launch");
+  p->n_jobs = n;
+  p->total_units = (uint32_t)units;
+  p->single = (*jobs_host)[0];
+  p->jobs = nullptr;
+  p->lps = pl.lps;
+  p->vpl = pl.vpl;
+  p->stage_bytes = pl.stage_bytes;
+  int st = knobs().seg_stages;
+  if (st < 2) st = 2;
+  if (st > kMaxStages) st = kMaxStages;
+  p->n_stages = pl.path == PATH_SEG ? st : pl.stages;
+  return IWQ_OK;
+}
+
+static int upload_jobs(const std::vector<Job>& jobs, void* workspace, size_t ws_bytes, LaunchParams* p, cudaStream_t st) {
+  if (jobs.size() <= 1) return IWQ_OK;
+  const size_t need = jobs.size() * sizeof(Job);
+  if (!workspace || ws_bytes < need) return fail(IWQ_ERR_INVALID, "workspace too small (see iwq_workspace_bytes)");
+  if ((uintptr_t)workspace & 15) return fail(IWQ_ERR_ALIGN, "workspace must be 16-byte aligned");
+  cudaError_t e = cudaMemcpyAsync(workspace, jobs.data(), need, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(job table)");
+  p->jobs = (const Job*)workspace;
+  return IWQ_OK;
+}
+
+static int run_minmax(const iwq_config_t* cfg, const LaunchParams& base, float* range, cudaStream_t st) {
+  LaunchParams p = base;
+  p.ranges_out = range;
+  const int n2 = 2 * p.n_jobs;
+  range_init_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(range, n2);
+  int grid = 0;
+  cudaError_t e;
+  const bool sym = p.qc.symmetric != 0;
+#define IWQ_MM(DT, SYM)                                                                \
+  do {                                                                                 \
+    auto k = minmax_kernel<DT, SYM>;                                                   \
+    e = persistent_grid(k, kConsumers, 0, 0, p.total_units, &grid);                    \
+    if (e == cudaSuccess) {                                                            \
+      k<<<grid, kConsumers, 0, st>>>(p);                                               \
+      e = cudaGetLastError();                                                          \
+    }                                                                                  \
+  } while (0)
+  if (cfg->dtype == IWQ_F16) {
+    if (sym) IWQ_MM(IWQ_F16, true); else IWQ_MM(IWQ_F16, false);
+  } else {
+    if (sym) IWQ_MM(IWQ_BF16, true); else IWQ_MM(IWQ_BF16, false);
+  }
+#undef IWQ_MM
+  if (e != cudaSuccess) return fail_cuda(e, "minmax kernel launch");
+  return IWQ_OK;
+}
+
+static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, void* workspace, size_t ws_bytes, const float* given_range,
+                       float* range_ws, int32_t* status, cudaStream_t st, bool minmax_only) {
+  if (!cfg || !ms || n < 1) return fail(IWQ_ERR_INVALID, "null config/matrices or n < 1");
+  LaunchParams p;
+  memset(&p, 0, sizeof(p));
+  int kind = 0;
+  int rc = build_consts(cfg, &p.qc, &kind);
+  if (rc) return rc;
+  Plan pl;
+  rc = make_plan(cfg, ms[0].cols, &pl);
+  if (rc) return rc;
+  for (int i = 1; i < n; ++i) {
+    Plan pi;
+    rc = make_plan(cfg, ms[i].cols, &pi);
+    if (rc) return rc;
+    if (pi.path != pl.path || pi.lps != pl.lps || pi.vpl != pl.vpl || pi.stage_bytes != pl.stage_bytes)
+      return fail(IWQ_ERR_UNSUPPORTED, "matrices of one batched call must share the segment shape (batch per distinct cols for per-channel)");
+  }
+  std::vector<Job> jobs;
+  rc = fill_params(cfg, ms, n, pl, &p, &jobs);
+  if (rc) return rc;
+  rc = upload_jobs(jobs, workspace, ws_bytes, &p, st);
+  if (rc) return rc;
+  p.status = status;
+  const bool sym = p.qc.symmetric != 0;
+  const bool per_tensor = cfg->group == IWQ_GROUP_PER_TENSOR;
+  LaunchTuning tune;
+  tune.stages = p.n_stages;
+  cudaError_t e;
+  if (per_tensor) {
+    const float* rng = given_range;
+    if (!rng) {
+      if (!range_ws) return fail(IWQ_ERR_INVALID, "per-tensor granularity needs a device range buffer of 2 floats per matrix");
+      rc = run_minmax(cfg, p, range_ws, st);
+      if (rc) return rc;
+      rng = range_ws;
+    }
+    if (minmax_only) return IWQ_OK;
+    p.ranges = rng;
+    tune.ctas_per_sm = knobs().seg_ctas;
+    e = dispatch_seg(cfg->dtype, kind, p, sym, true, effective_variant(cfg), tune, st);
+  } else if (pl.path == PATH_SEG) {
+    tune.ctas_per_sm = knobs().seg_ctas;
+    e = dispatch_seg(cfg->dtype, kind, p, sym, false, effective_variant(cfg), tune, st);
+  } else {
+    tune.ctas_per_sm = knobs().row_ctas;
+    e = dispatch_row(cfg->dtype, kind, p, sym, pl.consumers, tune, st);
+  }
+  if (e != cudaSuccess) return fail_cuda(e, "fake-quant kernel launch");
+  return IWQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer pipeline
+// ------------------------------------------------------------------------------------------------
+struct HostPipe {
+  int device = -1;
+  static constexpr int kBuf = 3;
+  void* buf[kBuf] = {nullptr, nullptr, nullptr};
+  size_t cap = 0;
+  cudaStream_t stream[kBuf] = {nullptr, nullptr, nullptr};
+  int32_t* status = nullptr;
+  int32_t* status_host = nullptr;
+};
+static std::mutex g_pipe_mu;
+static HostPipe g_pipes[16];
+
+static int pipe_prepare(HostPipe* hp, int device, size_t chunk) {
+  cudaError_t e;
+  if (hp->device != device) {
+    hp->device = device;
+    for (int i = 0; i < HostPipe::kBuf; ++i) {
+      e = cudaStreamCreateWithFlags(&hp->stream[i], cudaStreamNonBlocking);
+      if (e != cudaSuccess) return fail_cuda(e, "cudaStreamCreate");
+    }
+    e = cudaMalloc((void**)&hp->status, sizeof(int32_t));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(status)");
+    e = cudaMallocHost((void**)&hp->status_host, sizeof(int32_t));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMallocHost(status)");
+  }
+  if (hp->cap < chunk) {
+    for (int i = 0; i < HostPipe::kBuf; ++i) {
+      if (hp->buf[i]) cudaFree(hp->buf[i]);
+      hp->buf[i] = nullptr;
+    }
+    hp->cap = 0;
+    for (int i = 0; i < HostPipe::kBuf; ++i) {
+      e = cudaMalloc(&hp->buf[i], chunk);
+      if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(staging)");
+    }
+    hp->cap = chunk;
+  }
+  return IWQ_OK;
+}
+
+}  // namespace iwq
+
+using namespace iwq;
+
+extern "C" {
+
+int iwq_abi_version(void) { return IWQ_ABI_VERSION; }
+const char* iwq_last_error(void) { return g_err.c_str(); }
+size_t iwq_workspace_bytes(int n) { return (size_t)(n < 1 ? 1 : n) * sizeof(Job); }
+
+int iwq_fake_quant(const iwq_config_t* cfg, const iwq_matrix_t* m, float* range_ws, int32_t* status, void* stream) {
+  return run_batched(cfg, m, 1, nullptr, 0, nullptr, range_ws, status, (cudaStream_t)stream, false);
+}
+
+int iwq_fake_quant_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, void* workspace, size_t workspace_bytes, int32_t* status,
+                           void* stream) {
+  if (cfg && cfg->group == IWQ_GROUP_PER_TENSOR)
+    return fail(IWQ_ERR_INVALID, "per-tensor granularity: use iwq_minmax + iwq_fake_quant_with_range (or iwq_fake_quant per matrix)");
+  return run_batched(cfg, ms, n, workspace, workspace_bytes, nullptr, nullptr, status, (cudaStream_t)stream, false);
+}
+
+int iwq_minmax(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, float* range, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!cfg || cfg->group != IWQ_GROUP_PER_TENSOR) return fail(IWQ_ERR_INVALID, "iwq_minmax is for per-tensor granularity");
+  if (!range) return fail(IWQ_ERR_INVALID, "null range buffer");
+  return run_batched(cfg, ms, n, workspace, workspace_bytes, nullptr, range, nullptr, (cudaStream_t)stream, true);
+}
+
+int iwq_fake_quant_with_range(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, const float* range, void* workspace,
+                              size_t workspace_bytes, int32_t* status, void* stream) {
+  if (!cfg || cfg->group != IWQ_GROUP_PER_TENSOR) return fail(IWQ_ERR_INVALID, "iwq_fake_quant_with_range is for per-tensor granularity");
+  if (!range) return fail(IWQ_ERR_INVALID, "null range buffer");
+  return run_batched(cfg, ms, n, workspace, workspace_bytes, range, nullptr, status, (cudaStream_t)stream, false);
+}
+
+int iwq_fp_roundtrip(int dtype, int flavour, int exp_bits, int mant_bits, const void* x, void* y, void* codes, int64_t n, void* stream) {
+  iwq_config_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.dtype = dtype;
+  cfg.scheme = flavour;
+  cfg.exp_bits = exp_bits;
+  cfg.mant_bits = mant_bits;
+  cfg.symmetric = 1;
+  cfg.group = 128;
+  QuantConsts qc;
+  int kind = 0;
+  int rc = build_consts(&cfg, &qc, &kind);
+  if (rc) return rc;
+  if (kind != KIND_FP) return fail(IWQ_ERR_INVALID, "flavour must be IWQ_SCHEME_FP_CODEC or IWQ_SCHEME_FP_RNE");
+  if (n <= 0 || (n & 1)) return fail(IWQ_ERR_INVALID, "n must be positive and even");
+  if (((uintptr_t)x | (uintptr_t)y) & 3) return fail(IWQ_ERR_ALIGN, "x and y must be 4-byte aligned");
+  const int64_t pairs = n / 2;
+  int grid = (int)((pairs + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == IWQ_F16)
+    fp_roundtrip_kernel<IWQ_F16><<<grid, 256, 0, st>>>((const uint32_t*)x, (uint32_t*)y, (uint16_t*)codes, pairs, qc);
+  else
+    fp_roundtrip_kernel<IWQ_BF16><<<grid, 256, 0, st>>>((const uint32_t*)x, (uint32_t*)y, (uint16_t*)codes, pairs, qc);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, "fp_roundtrip kernel launch");
+  return IWQ_OK;
+}
+
+int iwq_selftest_division(int dtype, unsigned long long* mismatches, void* stream) {
+  if (!mismatches) return fail(IWQ_ERR_INVALID, "null counter");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == IWQ_F16)
+    division_selftest_kernel<IWQ_F16><<<148 * 4, 256, 0, st>>>(mismatches);
+  else if (dtype == IWQ_BF16)
+    division_selftest_kernel<IWQ_BF16><<<148 * 4, 256, 0, st>>>(mismatches);
+  else
+    return fail(IWQ_ERR_INVALID, "dtype must be IWQ_F16 or IWQ_BF16");
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, "division selftest launch");
+  return IWQ_OK;
+}
+
+int iwq_fake_quant_host(const iwq_config_t* cfg, const void* host_w, void* host_out, int64_t rows, int64_t cols, int device,
+                        size_t chunk_bytes, int32_t* host_status) {
+  if (!cfg || !host_w || !host_out) return fail(IWQ_ERR_INVALID, "null argument");
+  if (cfg->group == IWQ_GROUP_PER_TENSOR) return fail(IWQ_ERR_UNSUPPORTED, "host pipeline: per-tensor granularity needs the whole matrix on the device");
+  if (rows <= 0 || cols <= 0) return fail(IWQ_ERR_INVALID, "rows and cols must be positive");
+  if (device < 0 || device >= 16) return fail(IWQ_ERR_INVALID, "device ordinal out of range");
+  if (cfg->group > 0 && cols % cfg->group != 0) return fail(IWQ_ERR_INDIVISIBLE, "cols is not divisible by the group size");
+  const size_t row_bytes = (size_t)cols * 2;
+  if (chunk_bytes == 0) chunk_bytes = 64ull << 20;
+  int64_t chunk_rows = (int64_t)(chunk_bytes / row_bytes);
+  if (chunk_rows < 1) chunk_rows = 1;
+  // keep chunk starts 16-byte aligned: rows are, as soon as cols % 8 == 0; otherwise align to 8 rows
+  if (row_bytes % 16 != 0) chunk_rows = (chunk_rows + 7) / 8 * 8;
+  if (chunk_rows > rows) chunk_rows = rows;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
+  std::lock_guard<std::mutex> lk(g_pipe_mu);
+  HostPipe* hp = &g_pipes[device];
+  int rc = pipe_prepare(hp, device, (size_t)chunk_rows * row_bytes);
+  if (rc) return rc;
+  e = cudaMemsetAsync(hp->status, 0, sizeof(int32_t), hp->stream[0]);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
+  e = cudaStreamSynchronize(hp->stream[0]);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaStreamSynchronize");
+  int i = 0;
+  for (int64_t r0 = 0; r0 < rows; r0 += chunk_rows, ++i) {
+    const int64_t nr = rows - r0 < chunk_rows ? rows - r0 : chunk_rows;
+    const size_t bytes = (size_t)nr * row_bytes;
+    const int b = i % HostPipe::kBuf;
+    cudaStream_t st = hp->stream[b];
+    e = cudaMemcpyAsync(hp->buf[b], (const uint8_t*)host_w + (size_t)r0 * row_bytes, bytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(H2D)");
+    iwq_matrix_t m;
+    memset(&m, 0, sizeof(m));
+    m.w = hp->buf[b];
+    m.out = hp->buf[b];
+    m.rows = nr;
+    m.cols = cols;
+    rc = run_batched(cfg, &m, 1, nullptr, 0, nullptr, nullptr, hp->status, st, false);
+    if (rc) return rc;
+    e = cudaMemcpyAsync((uint8_t*)host_out + (size_t)r0 * row_bytes, hp->buf[b], bytes, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(D2H)");
+  }
+  for (int b = 0; b < HostPipe::kBuf; ++b) {
+    e = cudaStreamSynchronize(hp->stream[b]);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaStreamSynchronize");
+  }
+  e = cudaMemcpy(hp->status_host, hp->status, sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpy(status)");
+  if (host_status) *host_status = *hp->status_host;
+  return IWQ_OK;
+}
+
+}  // extern "C"

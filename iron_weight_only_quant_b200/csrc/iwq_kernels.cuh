@@ -1,0 +1,692 @@
+// iwq_kernels.cuh -- sm_100a kernels of the weight fake-quant path.
+//
+// Data layout in HBM: every weight matrix is a row-major contiguous array of 16-bit values, so a
+// matrix at per-group granularity is nothing but a flat run of independent `group`-element segments,
+// and at per-channel granularity a flat run of `cols`-element segments.  All kernels are HBM-bound
+// streaming passes (4 algorithmic bytes per element: one 16-bit read, one 16-bit write); none uses
+// tensor cores.
+//
+//   seg_tma_kernel    small segments (group = 8..1024): persistent CTAs, one producer lane streams
+//                     16 KB tiles global->shared with 1-D TMA bulk copies (cp.async.bulk + mbarrier
+//                     complete_tx) through an n-stage ring; 8 consumer warps pull 128-bit vectors from
+//                     shared memory, reduce min/max with warp shuffles inside the lanes of a segment,
+//                     derive scale / zero-point in registers, quantise-dequantise and store 128-bit.
+//   seg_direct_kernel same consumer code fed by plain 128-bit global loads (A/B variant).
+//   row_tma_kernel    long segments (per-channel rows): one row per ring stage (one bulk copy per row),
+//                     two sweeps over the row in shared memory (range, then quantise).
+//   minmax_kernel     per-tensor granularity, pass 1: per-matrix {max|absmax, -min} via ordered atomics.
+//                     Pass 2 is seg_*_kernel<GIVEN=true> reading that range (after an NCCL MAX
+//                     all-reduce when the matrix is sharded across GPUs).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "iwq_consts.h"
+#include "iwq_math.cuh"
+
+namespace iwq {
+
+// ------------------------------------------------------------------------------------------------
+// launch-wide parameter blocks
+// ------------------------------------------------------------------------------------------------
+struct Job {               // one matrix (64 bytes)
+  const uint8_t* src;
+  uint8_t* dst;
+  uint8_t* scales;         // optional, D[G]
+  uint8_t* zeros;          // optional, D[G]
+  uint8_t* codes;          // optional, uint8[rows*cols]
+  uint64_t bytes;          // rows*cols*2
+  uint32_t first_unit;     // first tile (seg kernels) / first row (row kernel) of this job in the launch
+  uint32_t row_bytes;      // cols*2
+  uint64_t pad;
+};
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumers = kConsumerWarps * 32;
+constexpr int kVPT = 4;                                  // 128-bit vectors per thread per tile
+constexpr int kTileBytes = kConsumers * kVPT * 16;       // 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kSmemHeader = 1024;                        // barriers + tile contexts + FP table
+
+struct LaunchParams {
+  const Job* jobs;         // device array (n_jobs > 1) or nullptr -> `single`
+  Job single;
+  int32_t n_jobs;
+  uint32_t total_units;    // tiles or rows over all jobs
+  int32_t n_stages;
+  uint32_t stage_bytes;    // row kernel: bytes reserved per ring stage
+  int32_t lps;             // lanes per segment (1..32)      } group = 8 * lps * vpl elements
+  int32_t vpl;             // vectors per lane per segment   }
+  const float* ranges;     // GIVEN mode: {max|absmax, -min} per job
+  float* ranges_out;       // minmax kernel output
+  int32_t* status;
+  QuantConsts qc;
+};
+
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared::cta bulk copy, completion signalled on `bar` as transaction bytes (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ uint4 lds128(const void* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg128(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg128(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// range of one 128-bit vector, packed as a T2 pair {max|absmax, -min} (both reduce with max)
+// ------------------------------------------------------------------------------------------------
+template <int DT, bool SYM>
+__device__ __forceinline__ uint32_t vec_range(const uint4& v) {
+  using T2 = typename DType<DT>::T2;
+  if (SYM) {
+    T2 a = from_u32<T2>(v.x & 0x7FFF7FFFu), b = from_u32<T2>(v.y & 0x7FFF7FFFu);
+    T2 c = from_u32<T2>(v.z & 0x7FFF7FFFu), d = from_u32<T2>(v.w & 0x7FFF7FFFu);
+    T2 m = __hmax2_nan(__hmax2_nan(a, b), __hmax2_nan(c, d));
+    uint32_t mb = as_u32(m);
+    T2 sw = from_u32<T2>(__byte_perm(mb, mb, 0x1032));
+    return as_u32(__hmax2_nan(m, sw));
+  } else {
+    T2 a = from_u32<T2>(v.x), b = from_u32<T2>(v.y), c = from_u32<T2>(v.z), d = from_u32<T2>(v.w);
+    T2 mx = __hmax2_nan(__hmax2_nan(a, b), __hmax2_nan(c, d));
+    T2 mn = __hmin2_nan(__hmin2_nan(a, b), __hmin2_nan(c, d));
+    uint32_t xb = as_u32(mx), nb = as_u32(mn);
+    mx = __hmax2_nan(mx, from_u32<T2>(__byte_perm(xb, xb, 0x1032)));
+    mn = __hmin2_nan(mn, from_u32<T2>(__byte_perm(nb, nb, 0x1032)));
+    return __byte_perm(as_u32(mx), as_u32(mn) ^ 0x80008000u, 0x5410);  // {max, -min}
+  }
+}
+
+template <int DT>
+__device__ __forceinline__ uint32_t range_max(uint32_t a, uint32_t b) {
+  using T2 = typename DType<DT>::T2;
+  return as_u32(__hmax2_nan(from_u32<T2>(a), from_u32<T2>(b)));
+}
+
+template <int DT>
+__device__ __forceinline__ void range_unpack(uint32_t pk, float* mx, float* mn) {
+  *mx = DType<DT>::to_f32((uint16_t)(pk & 0xFFFFu));
+  *mn = -DType<DT>::to_f32((uint16_t)(pk >> 16));
+}
+
+// ------------------------------------------------------------------------------------------------
+// element stage on 128-bit vectors: Prepared<DT,KIND> holds one segment's parameters in registers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pack_codes(const uint32_t (&cb)[8], uint2* codes8) {
+  codes8->x = cb[0] | (cb[1] << 8) | (cb[2] << 16) | (cb[3] << 24);
+  codes8->y = cb[4] | (cb[5] << 8) | (cb[6] << 16) | (cb[7] << 24);
+}
+
+template <int DT, int KIND>
+struct Prepared;
+
+template <int DT, int KIND>
+struct PreparedInt {  // KIND_INT_FAST / KIND_INT_WIDE
+  using D = DType<DT>;
+  using T2 = typename D::T2;
+  IntFast<DT, KIND == KIND_INT_WIDE> f;
+  float scale, zero;
+  bool bad;
+  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c) {
+    IntQ q = int_segment_params<DT>(mx, mn, c);
+    f.setup(q);
+    scale = q.s;
+    zero = q.z;
+    bad = q.bad;
+  }
+  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts&, const FpEntry*, bool want_codes, uint2* codes8) const {
+    T2 d[4];
+    uint4 o;
+    o.x = f.apply(v.x, &d[0]);
+    o.y = f.apply(v.y, &d[1]);
+    o.z = f.apply(v.z, &d[2]);
+    o.w = f.apply(v.w, &d[3]);
+    if (want_codes) {
+      uint32_t cb[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 a = D::to_f32x2(d[i]);
+        cb[2 * i] = (uint32_t)(int)(a.x + zero) & 0xFFu;  // code = clamp(rint(x), lo, hi) + z
+        cb[2 * i + 1] = (uint32_t)(int)(a.y + zero) & 0xFFu;
+      }
+      pack_codes(cb, codes8);
+    }
+    return o;
+  }
+};
+template <int DT>
+struct Prepared<DT, KIND_INT_FAST> : PreparedInt<DT, KIND_INT_FAST> {};
+template <int DT>
+struct Prepared<DT, KIND_INT_WIDE> : PreparedInt<DT, KIND_INT_WIDE> {};
+
+template <int DT>
+struct Prepared<DT, KIND_INT_GENERIC> {
+  IntQ q;
+  float scale, zero;
+  bool bad;
+  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c) {
+    q = int_segment_params<DT>(mx, mn, c);
+    scale = q.s;
+    zero = q.z;
+    bad = q.bad;
+  }
+  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts& c, const FpEntry*, bool want_codes, uint2* codes8) const {
+    const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+    uint32_t out[4], cb[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float k0, k1;
+      uint32_t lo = int_generic_elem<DT>((uint16_t)(in[i] & 0xFFFFu), q, c, &k0);
+      uint32_t hi = int_generic_elem<DT>((uint16_t)(in[i] >> 16), q, c, &k1);
+      out[i] = lo | (hi << 16);
+      cb[2 * i] = (uint32_t)(int)k0 & 0xFFu;
+      cb[2 * i + 1] = (uint32_t)(int)k1 & 0xFFu;
+    }
+    if (want_codes) pack_codes(cb, codes8);
+    return make_uint4(out[0], out[1], out[2], out[3]);
+  }
+};
+
+template <int DT>
+struct Prepared<DT, KIND_FP> {
+  using T2 = typename DType<DT>::T2;
+  FpTable<DT> f;
+  float scale, zero;
+  bool bad;
+  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c) {
+    FpQ q = fp_segment_params<DT>(mx, mn, c);
+    f.setup(q, c);
+    scale = q.S;
+    zero = q.mid;
+    bad = q.bad;
+  }
+  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts& c, const FpEntry* tbl, bool want_codes, uint2* codes8) const {
+    T2 g[4];
+    uint4 o;
+    o.x = f.apply(v.x, tbl, &g[0]);
+    o.y = f.apply(v.y, tbl, &g[1]);
+    o.z = f.apply(v.z, tbl, &g[2]);
+    o.w = f.apply(v.w, tbl, &g[3]);
+    if (want_codes) {
+      uint32_t cb[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t gb = as_u32(g[i]);
+        cb[2 * i] = fp_code_of<DT>((uint16_t)(gb & 0xFFFFu), c.exp_bits, c.mant_bits);
+        cb[2 * i + 1] = fp_code_of<DT>((uint16_t)(gb >> 16), c.exp_bits, c.mant_bits);
+      }
+      pack_codes(cb, codes8);
+    }
+    return o;
+  }
+};
+
+// per-tile context handed from the producer to the consumers through shared memory
+struct TileCtx {
+  uint8_t* dst;      // output address of the tile's first byte
+  uint8_t* scales;
+  uint8_t* zeros;
+  uint8_t* codes;
+  uint64_t vec0;     // index (in 16-byte vectors, within the matrix) of the tile's first vector
+  uint32_t n_vec;    // valid vectors in the tile
+  float given_mx;    // GIVEN mode
+  float given_mn;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ const Job* job_table(const LaunchParams& p) { return p.n_jobs == 1 ? &p.single : p.jobs; }
+
+// Track the job of `unit`, scanning forward from *cur (units are visited in increasing order).
+// `*jb` is reloaded only when the job changes; *cur == -1 forces the first load.
+__device__ __forceinline__ void advance_job(const LaunchParams& p, uint32_t unit, int* cur, Job* jb) {
+  const Job* jobs = job_table(p);
+  int j = *cur < 0 ? 0 : *cur;
+  while (j + 1 < p.n_jobs && unit >= jobs[j + 1].first_unit) ++j;
+  if (j != *cur) {
+    *cur = j;
+    *jb = jobs[j];
+  }
+}
+
+__device__ __forceinline__ TileCtx make_tile_ctx(const LaunchParams& p, const Job& jb, int job_idx, uint32_t tile, bool given) {
+  TileCtx t;
+  const uint64_t off = (uint64_t)(tile - jb.first_unit) * kTileBytes;
+  const uint64_t left = jb.bytes - off;
+  t.dst = jb.dst + off;
+  t.scales = jb.scales;
+  t.zeros = jb.zeros;
+  t.codes = jb.codes;
+  t.vec0 = off >> 4;
+  t.n_vec = (uint32_t)((left < (uint64_t)kTileBytes ? left : (uint64_t)kTileBytes) >> 4);
+  t.given_mx = 0.f;
+  t.given_mn = 0.f;
+  if (given) {
+    t.given_mx = p.ranges[2 * job_idx];
+    t.given_mn = -p.ranges[2 * job_idx + 1];
+  }
+  t.pad = 0;
+  return t;
+}
+
+// Consumer side of one tile: v[it] is the vector at tile-local index warp*128 + it*32 + lane.
+template <int DT, int KIND, bool SYM, bool GIVEN>
+__device__ __forceinline__ void consume_tile(uint4 (&v)[kVPT], const TileCtx& t, const LaunchParams& p, const FpEntry* tbl, int warp,
+                                             int lane) {
+  const int lps = p.lps, vpl = p.vpl;
+  uint32_t pk[kVPT];
+  if (!GIVEN) {
+#pragma unroll
+    for (int it = 0; it < kVPT; ++it) pk[it] = vec_range<DT, SYM>(v[it]);
+    if (vpl >= 2) {
+      pk[0] = pk[1] = range_max<DT>(pk[0], pk[1]);
+      pk[2] = pk[3] = range_max<DT>(pk[2], pk[3]);
+    }
+    if (vpl >= 4) pk[0] = pk[1] = pk[2] = pk[3] = range_max<DT>(pk[0], pk[2]);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      if (o < lps) {
+#pragma unroll
+        for (int it = 0; it < kVPT; ++it) pk[it] = range_max<DT>(pk[it], __shfl_xor_sync(0xFFFFFFFFu, pk[it], o));
+      }
+    }
+  }
+  const bool want_codes = t.codes != nullptr;
+  bool any_bad = false;
+  Prepared<DT, KIND> prep;
+  if (GIVEN) prep.setup(t.given_mx, t.given_mn, p.qc);
+#pragma unroll
+  for (int it = 0; it < kVPT; ++it) {
+    const uint32_t idx = (uint32_t)warp * (32 * kVPT) + it * 32 + lane;
+    if (!GIVEN && (it & (vpl - 1)) == 0) {  // its of one segment share the parameters
+      float mx, mn;
+      range_unpack<DT>(pk[it], &mx, &mn);
+      prep.setup(mx, mn, p.qc);
+    }
+    uint2 codes8;
+    const uint4 o = prep.apply(v[it], p.qc, tbl, want_codes, &codes8);
+    if (idx < t.n_vec) {
+      stg128(t.dst + (size_t)idx * 16, o);
+      if (want_codes) *reinterpret_cast<uint2*>(t.codes + (t.vec0 + idx) * 8) = codes8;
+      any_bad |= prep.bad;
+      // segment parameters: one lane per segment; per-tensor (GIVEN) has a single segment per matrix
+      const bool owner = GIVEN ? (t.vec0 + idx == 0) : ((lane & (lps - 1)) == 0 && (it & (vpl - 1)) == 0);
+      if (owner) {
+        const uint64_t g = GIVEN ? 0 : (t.vec0 + idx) / (uint32_t)(lps * vpl);
+        if (t.scales) reinterpret_cast<uint16_t*>(t.scales)[g] = DType<DT>::from_f32(prep.scale);
+        if (t.zeros) reinterpret_cast<uint16_t*>(t.zeros)[g] = DType<DT>::from_f32(prep.zero);
+      }
+    }
+  }
+  if (any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
+}
+
+__device__ __forceinline__ void load_fp_table(const LaunchParams& p, FpEntry* s_tbl) {
+  if (threadIdx.x < 40) s_tbl[threadIdx.x] = p.qc.tbl[threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------------
+// seg_tma_kernel: TMA bulk-copy ring -> consumer warps
+// shared memory: [0,64) full barriers | [64,128) empty barriers | [128,640) TileCtx[8] | [640,960) FP table | [1024,...) stages
+// ------------------------------------------------------------------------------------------------
+template <int DT, int KIND, bool SYM, bool GIVEN>
+__global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_constant__ LaunchParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + kMaxStages;
+  TileCtx* ctx = reinterpret_cast<TileCtx*>(smem + 128);
+  FpEntry* s_tbl = reinterpret_cast<FpEntry*>(smem + 640);
+  uint8_t* data = smem + kSmemHeader;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_stages = p.n_stages;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kConsumerWarps);
+    }
+    fence_mbar_init();
+  }
+  if (KIND == KIND_FP) load_fp_table(p, s_tbl);
+  __syncthreads();
+
+  if (warp == kConsumerWarps) {
+    // ---------------- producer: one lane issues the bulk copies ----------------
+    if (lane == 0) {
+      int stage = 0, cur = -1;
+      uint32_t phase = 0;
+      Job jb;
+      for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        advance_job(p, tile, &cur, &jb);
+        const TileCtx t = make_tile_ctx(p, jb, cur, tile, GIVEN);
+        ctx[stage] = t;
+        const uint32_t bytes = t.n_vec * 16u;
+        mbar_arrive_expect_tx(&full[stage], bytes);
+        tma_load_1d(data + (size_t)stage * kTileBytes, jb.src + (t.vec0 << 4), bytes, &full[stage]);
+        if (++stage == n_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ---------------- consumers ----------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+      mbar_wait(&full[stage], phase);
+      const TileCtx t = ctx[stage];
+      const uint8_t* sbase = data + (size_t)stage * kTileBytes + (size_t)warp * (32 * kVPT * 16) + lane * 16;
+      uint4 v[kVPT];
+#pragma unroll
+      for (int it = 0; it < kVPT; ++it) {
+        const uint32_t idx = (uint32_t)warp * (32 * kVPT) + it * 32 + lane;
+        v[it] = (idx < t.n_vec) ? lds128(sbase + it * 512) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);  // data is in registers: hand the stage back early
+      consume_tile<DT, KIND, SYM, GIVEN>(v, t, p, s_tbl, warp, lane);
+      if (++stage == n_stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// seg_direct_kernel: same consumer code, plain 128-bit global loads (no shared-memory staging)
+// ------------------------------------------------------------------------------------------------
+template <int DT, int KIND, bool SYM, bool GIVEN>
+__global__ void __launch_bounds__(kConsumers) seg_direct_kernel(const __grid_constant__ LaunchParams p) {
+  __shared__ FpEntry s_tbl[40];
+  if (KIND == KIND_FP) {
+    load_fp_table(p, s_tbl);
+    __syncthreads();
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int cur = -1;
+  Job jb;
+  for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+    advance_job(p, tile, &cur, &jb);
+    const TileCtx t = make_tile_ctx(p, jb, cur, tile, GIVEN);
+    const uint8_t* gbase = jb.src + (t.vec0 << 4);
+    uint4 v[kVPT];
+#pragma unroll
+    for (int it = 0; it < kVPT; ++it) {
+      const uint32_t idx = (uint32_t)warp * (32 * kVPT) + it * 32 + lane;
+      v[it] = (idx < t.n_vec) ? ldg128(gbase + (size_t)idx * 16) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    consume_tile<DT, KIND, SYM, GIVEN>(v, t, p, s_tbl, warp, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// row_tma_kernel: one row (segment of `row_bytes`) per ring stage; blockDim.x = consumers + 32
+// shared memory header as above, with per-warp partial ranges at [960, 1024) x2 parities (16 warps max)
+// ------------------------------------------------------------------------------------------------
+struct RowCtx {
+  uint8_t* dst;
+  uint8_t* scales;
+  uint8_t* zeros;
+  uint8_t* codes;
+  uint64_t row;       // row index within the matrix
+  uint32_t n_vec;
+  uint32_t pad;
+};
+
+template <int DT, int KIND, bool SYM>
+__global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant__ LaunchParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + kMaxStages;
+  RowCtx* ctx = reinterpret_cast<RowCtx*>(smem + 128);        // 8 x 48 B = 384 B
+  FpEntry* s_tbl = reinterpret_cast<FpEntry*>(smem + 640);    // 320 B
+  uint32_t* partial = reinterpret_cast<uint32_t*>(smem + 960); // [2][16]... 128 B -> spills into the pad before `data`
+  uint8_t* data = smem + kSmemHeader + 128;
+
+  const int n_cons = (int)blockDim.x - 32;
+  const int n_cwarps = n_cons >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_stages = p.n_stages;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], n_cwarps);
+    }
+    fence_mbar_init();
+  }
+  if (KIND == KIND_FP) load_fp_table(p, s_tbl);
+  __syncthreads();
+
+  if (warp == n_cwarps) {
+    if (lane == 0) {
+      int stage = 0, cur = -1;
+      uint32_t phase = 0;
+      Job jb;
+      for (uint32_t row = blockIdx.x; row < p.total_units; row += gridDim.x) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        advance_job(p, row, &cur, &jb);
+        const uint64_t r = row - jb.first_unit;
+        RowCtx t;
+        t.dst = jb.dst + r * jb.row_bytes;
+        t.scales = jb.scales;
+        t.zeros = jb.zeros;
+        t.codes = jb.codes ? jb.codes + r * (jb.row_bytes >> 1) : nullptr;
+        t.row = r;
+        t.n_vec = jb.row_bytes >> 4;
+        t.pad = 0;
+        ctx[stage] = t;
+        mbar_arrive_expect_tx(&full[stage], jb.row_bytes);
+        tma_load_1d(data + (size_t)stage * p.stage_bytes, jb.src + r * jb.row_bytes, jb.row_bytes, &full[stage]);
+        if (++stage == n_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    int stage = 0;
+    uint32_t phase = 0, par = 0;
+    const int tid = threadIdx.x;
+    for (uint32_t row = blockIdx.x; row < p.total_units; row += gridDim.x) {
+      mbar_wait(&full[stage], phase);
+      const RowCtx t = ctx[stage];
+      const uint8_t* sdata = data + (size_t)stage * p.stage_bytes;
+      // sweep 1: range of the row
+      uint32_t pk = SYM ? 0u : 0xFC00FC00u;  // {0,0} for absmax; {-inf,-inf} otherwise (bf16: see below)
+      if (!SYM && DT == IWQ_BF16) pk = 0xFF80FF80u;
+      for (uint32_t i = tid; i < t.n_vec; i += n_cons) pk = range_max<DT>(pk, vec_range<DT, SYM>(lds128(sdata + (size_t)i * 16)));
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) pk = range_max<DT>(pk, __shfl_xor_sync(0xFFFFFFFFu, pk, o));
+      if (lane == 0) partial[par * 16 + warp] = pk;
+      asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory");
+      uint32_t all = partial[par * 16];
+      for (int w = 1; w < n_cwarps; ++w) all = range_max<DT>(all, partial[par * 16 + w]);
+      par ^= 1u;
+      float mx, mn;
+      range_unpack<DT>(all, &mx, &mn);
+      // sweep 2: quantise from shared memory, store to global
+      const bool want_codes = t.codes != nullptr;
+      Prepared<DT, KIND> prep;
+      prep.setup(mx, mn, p.qc);
+      for (uint32_t i = tid; i < t.n_vec; i += n_cons) {
+        uint2 codes8;
+        const uint4 o = prep.apply(lds128(sdata + (size_t)i * 16), p.qc, s_tbl, want_codes, &codes8);
+        stg128(t.dst + (size_t)i * 16, o);
+        if (want_codes) *reinterpret_cast<uint2*>(t.codes + (size_t)i * 8) = codes8;
+      }
+      if (tid == 0) {
+        if (t.scales) reinterpret_cast<uint16_t*>(t.scales)[t.row] = DType<DT>::from_f32(prep.scale);
+        if (t.zeros) reinterpret_cast<uint16_t*>(t.zeros)[t.row] = DType<DT>::from_f32(prep.zero);
+        if (prep.bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == n_stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-tensor granularity, pass 1
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v != v) {
+    atomicMax(reinterpret_cast<int*>(addr), 0x7FFFFFFF);  // NaN dominates (positive NaN is the largest int pattern)
+  } else if (v >= 0.0f) {
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  } else {
+    atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+  }
+}
+
+static __global__ void range_init_kernel(float* ranges, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ranges[i] = -INFINITY;
+}
+
+template <int DT, bool SYM>
+__global__ void __launch_bounds__(kConsumers) minmax_kernel(const __grid_constant__ LaunchParams p) {
+  __shared__ uint32_t s_part[kConsumerWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ident = SYM ? 0u : (DT == IWQ_F16 ? 0xFC00FC00u : 0xFF80FF80u);
+  int cur = -1, acc_job = -1;
+  uint32_t acc = ident;
+  Job jb;
+
+  auto flush = [&](int job) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) acc = range_max<DT>(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t all = s_part[0];
+      for (int w = 1; w < kConsumerWarps; ++w) all = range_max<DT>(all, s_part[w]);
+      float mx, mn;
+      range_unpack<DT>(all, &mx, &mn);
+      atomic_max_float(&p.ranges_out[2 * job], mx);
+      if (!SYM) atomic_max_float(&p.ranges_out[2 * job + 1], -mn);
+    }
+    __syncthreads();
+    acc = ident;
+  };
+
+  for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+    advance_job(p, tile, &cur, &jb);
+    if (cur != acc_job) {
+      if (acc_job >= 0) flush(acc_job);  // block-uniform: every thread sees the same tile sequence
+      acc_job = cur;
+    }
+    const TileCtx t = make_tile_ctx(p, jb, cur, tile, false);
+    const uint8_t* gbase = jb.src + (t.vec0 << 4);
+    uint4 v[kVPT];
+#pragma unroll
+    for (int it = 0; it < kVPT; ++it) {
+      const uint32_t idx = (uint32_t)warp * (32 * kVPT) + it * 32 + lane;
+      // out-of-range lanes re-read vector 0 of the tile: harmless for a max/min
+      v[it] = ldg128(gbase + (size_t)(idx < t.n_vec ? idx : 0u) * 16);
+    }
+#pragma unroll
+    for (int it = 0; it < kVPT; ++it) acc = range_max<DT>(acc, vec_range<DT, SYM>(v[it]));
+  }
+  if (acc_job >= 0) flush(acc_job);
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise test kernels (exhaustive parity checks)
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void fp_roundtrip_kernel(const uint32_t* __restrict__ x, uint32_t* __restrict__ y, uint16_t* __restrict__ codes, int64_t n_pairs,
+                                    const __grid_constant__ QuantConsts qc) {
+  __shared__ FpEntry s_tbl[40];
+  if (threadIdx.x < 40) s_tbl[threadIdx.x] = qc.tbl[threadIdx.x];
+  __syncthreads();
+  using T2 = typename DType<DT>::T2;
+  FpQ q;
+  q.S = 1.0f;
+  q.r = 1.0f;
+  q.mid = 0.f;
+  q.mid_h = 0.f;
+  q.bad = false;
+  q.slow_div = false;
+  FpTable<DT> f;
+  f.setup(q, qc);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_pairs; i += (int64_t)gridDim.x * blockDim.x) {
+    T2 v = f.grid(from_u32<T2>(x[i]), s_tbl);
+    uint32_t vb = as_u32(v);
+    y[i] = vb;
+    if (codes) {
+      uint32_t c0 = fp_code_of<DT>((uint16_t)(vb & 0xFFFFu), qc.exp_bits, qc.mant_bits);
+      uint32_t c1 = fp_code_of<DT>((uint16_t)(vb >> 16), qc.exp_bits, qc.mant_bits);
+      codes[i] = (uint16_t)(c0 | (c1 << 8));
+    }
+  }
+}
+
+// every (w, s): rD(fast_quot) vs rD(IEEE w/s); blockIdx.x enumerates s, threads sweep w
+template <int DT>
+__global__ void division_selftest_kernel(unsigned long long* mismatches) {
+  const uint32_t top = DT == IWQ_F16 ? 0x7C00u : 0x7F80u;
+  unsigned long long bad = 0;
+  for (uint32_t sb = 1 + blockIdx.x; sb < top; sb += gridDim.x) {
+    const float s = DType<DT>::to_f32((uint16_t)sb);
+    const float r = ieee_rcp(s);
+    if (DT == IWQ_BF16 && !(s > 1e-30f && s < 1e30f)) continue;
+    for (uint32_t wb = threadIdx.x; wb < top; wb += blockDim.x) {
+      const float w = DType<DT>::to_f32((uint16_t)wb);
+      const float want = ieee_div(w, s);
+      if (DT == IWQ_BF16 && !(fabsf(want) < 1e37f && (fabsf(want) > 1e-30f || want == 0.f))) continue;
+      const uint16_t a = DType<DT>::from_f32(want);
+      const uint16_t b = DType<DT>::from_f32(fast_quot(w, s, r));
+      bad += (a != b);
+    }
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+}  // namespace iwq

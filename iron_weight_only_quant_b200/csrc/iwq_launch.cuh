@@ -1,0 +1,115 @@
+// iwq_launch.cuh -- typed launch wrappers.  Each (dtype, kind) pair is explicitly instantiated in its
+// own translation unit (iwq_inst_*.cu) so the library builds in parallel; iwq_host.cu only sees the
+// declarations below.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "iwq_kernels.cuh"
+
+namespace iwq {
+
+struct LaunchTuning {
+  int stages;        // ring depth of the TMA kernels (2..8)
+  int ctas_per_sm;   // 0 = as many as fit
+};
+
+// grid size for a persistent kernel: resident CTAs per SM (occupancy API) x SM count, cached
+template <class Kernel>
+inline cudaError_t persistent_grid(Kernel kernel, int threads, size_t smem, int cap_per_sm, uint32_t total_units, int* grid_out) {
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, int, size_t, int>, std::pair<int, int>> cache;  // -> (occ, sms)
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  auto key = std::make_tuple(reinterpret_cast<const void*>(kernel), threads, smem, dev);
+  std::pair<int, int> v;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+      // opt in to the full 227 KB once per kernel (a later, smaller value would lower the limit again)
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return e;
+      int occ = 0, sms = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+      if (e != cudaSuccess) return e;
+      e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (e != cudaSuccess) return e;
+      if (occ < 1) return cudaErrorLaunchOutOfResources;
+      v = std::make_pair(occ, sms);
+      cache[key] = v;
+    } else {
+      v = it->second;
+    }
+  }
+  int occ = v.first;
+  if (cap_per_sm > 0 && occ > cap_per_sm) occ = cap_per_sm;
+  long long g = (long long)occ * v.second;
+  if (g > (long long)total_units) g = total_units;
+  if (g < 1) g = 1;
+  *grid_out = (int)g;
+  return cudaSuccess;
+}
+
+template <int DT, int KIND>
+cudaError_t launch_seg(const LaunchParams& p, bool sym, bool given, int variant, const LaunchTuning& tune, cudaStream_t st);
+
+template <int DT, int KIND>
+cudaError_t launch_row(const LaunchParams& p, bool sym, int consumers, const LaunchTuning& tune, cudaStream_t st);
+
+#ifdef IWQ_INSTANTIATE
+
+template <int DT, int KIND, bool SYM, bool GIVEN>
+static cudaError_t launch_seg_one(LaunchParams p, int variant, const LaunchTuning& tune, cudaStream_t st) {
+  int grid = 0;
+  if (variant == 1) {
+    auto k = seg_direct_kernel<DT, KIND, SYM, GIVEN>;
+    cudaError_t e = persistent_grid(k, kConsumers, 0, tune.ctas_per_sm, p.total_units, &grid);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kConsumers, 0, st>>>(p);
+  } else {
+    auto k = seg_tma_kernel<DT, KIND, SYM, GIVEN>;
+    const size_t smem = kSmemHeader + (size_t)p.n_stages * kTileBytes;
+    cudaError_t e = persistent_grid(k, kConsumers + 32, smem, tune.ctas_per_sm, p.total_units, &grid);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kConsumers + 32, smem, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+template <int DT, int KIND>
+cudaError_t launch_seg(const LaunchParams& p, bool sym, bool given, int variant, const LaunchTuning& tune, cudaStream_t st) {
+  if (sym) {
+    return given ? launch_seg_one<DT, KIND, true, true>(p, variant, tune, st) : launch_seg_one<DT, KIND, true, false>(p, variant, tune, st);
+  }
+  return given ? launch_seg_one<DT, KIND, false, true>(p, variant, tune, st) : launch_seg_one<DT, KIND, false, false>(p, variant, tune, st);
+}
+
+template <int DT, int KIND, bool SYM>
+static cudaError_t launch_row_one(LaunchParams p, int consumers, const LaunchTuning& tune, cudaStream_t st) {
+  auto k = row_tma_kernel<DT, KIND, SYM>;
+  const size_t smem = kSmemHeader + 128 + (size_t)p.n_stages * p.stage_bytes;
+  int grid = 0;
+  cudaError_t e = persistent_grid(k, consumers + 32, smem, tune.ctas_per_sm, p.total_units, &grid);
+  if (e != cudaSuccess) return e;
+  k<<<grid, consumers + 32, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int DT, int KIND>
+cudaError_t launch_row(const LaunchParams& p, bool sym, int consumers, const LaunchTuning& tune, cudaStream_t st) {
+  return sym ? launch_row_one<DT, KIND, true>(p, consumers, tune, st) : launch_row_one<DT, KIND, false>(p, consumers, tune, st);
+}
+
+#define IWQ_INSTANTIATE_KIND(DT, KIND)                                                                                       \
+  template cudaError_t launch_seg<DT, KIND>(const LaunchParams&, bool, bool, int, const LaunchTuning&, cudaStream_t);       \
+  template cudaError_t launch_row<DT, KIND>(const LaunchParams&, bool, int, const LaunchTuning&, cudaStream_t);
+
+#endif  // IWQ_INSTANTIATE
+
+}  // namespace iwq

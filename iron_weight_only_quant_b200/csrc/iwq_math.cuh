@@ -1,0 +1,425 @@
+// iwq_math.cuh -- per-segment parameter computation and per-element transforms of the fake-quant
+// path, written so that every intermediate is rounded exactly where the reference's eager ATen ops
+// round it ("fp32 compute, round to the storage dtype after every op").
+//
+// Everything here is __host__ __device__: the CUDA kernels (iwq_kernels.cuh) are the product; the
+// host instantiation exists ONLY so that tests/host/emulate.cu can run the very same functions on
+// the CPU build box (no GPU there) against the golden vectors before GPU time is spent.  The Python
+// package never calls the host instantiation.
+//
+// Reference citations are file:line in LiuTielong/Iron_weight_only_quant.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/iwq_b200.h"
+
+#define IWQ_HD __host__ __device__ __forceinline__
+
+namespace iwq {
+
+// ------------------------------------------------------------------------------------------------
+// storage dtype traits
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+struct DType;
+
+IWQ_HD uint32_t f32_bits(float f) {
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; return c.u;
+#endif
+}
+IWQ_HD float bits_f32(uint32_t u) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+
+template <>
+struct DType<IWQ_F16> {
+  using T = __half;
+  using T2 = __half2;
+  static constexpr int kMantBits = 10;
+  static constexpr int kExpBias = 15;
+  static constexpr uint32_t kInfBits = 0x7C00u;
+  static IWQ_HD float to_f32(uint16_t b) { return __half2float(__ushort_as_half(b)); }
+  static IWQ_HD uint16_t from_f32(float f) { return __half_as_ushort(__float2half_rn(f)); }
+  static IWQ_HD T2 from_f32x2(float lo, float hi) { return __floats2half2_rn(lo, hi); }
+  static IWQ_HD float2 to_f32x2(T2 v) { return __half22float2(v); }
+  static IWQ_HD T2 bcast(uint16_t b) { return __half2half2(__ushort_as_half(b)); }
+};
+
+template <>
+struct DType<IWQ_BF16> {
+  using T = __nv_bfloat16;
+  using T2 = __nv_bfloat162;
+  static constexpr int kMantBits = 7;
+  static constexpr int kExpBias = 127;
+  static constexpr uint32_t kInfBits = 0x7F80u;
+  static IWQ_HD float to_f32(uint16_t b) { return bits_f32((uint32_t)b << 16); }
+  static IWQ_HD uint16_t from_f32(float f) { return __bfloat16_as_ushort(__float2bfloat16_rn(f)); }
+  static IWQ_HD T2 from_f32x2(float lo, float hi) { return __floats2bfloat162_rn(lo, hi); }
+  static IWQ_HD float2 to_f32x2(T2 v) {
+    // exact and one ALU op per element: a bf16 is the top half of an fp32
+    uint32_t u = *reinterpret_cast<uint32_t*>(&v);
+    return make_float2(bits_f32(u << 16), bits_f32(u & 0xFFFF0000u));
+  }
+  static IWQ_HD T2 bcast(uint16_t b) { return __bfloat162bfloat162(__ushort_as_bfloat16(b)); }
+};
+
+template <class T2>
+IWQ_HD uint32_t as_u32(T2 v) {
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <class T2>
+IWQ_HD T2 from_u32(uint32_t u) {
+  return *reinterpret_cast<T2*>(&u);
+}
+
+// round an fp32 value to the storage dtype and come back (the reference's per-op rounding)
+template <int DT>
+IWQ_HD float rD(float x) {
+  return DType<DT>::to_f32(DType<DT>::from_f32(x));
+}
+
+// torch.clamp semantics: NaN propagates
+IWQ_HD float clamp_min_nan(float x, float lo) { return (x != x) ? x : fmaxf(x, lo); }
+IWQ_HD float clamp_nan(float x, float lo, float hi) { return (x != x) ? x : fminf(fmaxf(x, lo), hi); }
+
+IWQ_HD float ieee_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fdiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
+IWQ_HD float ieee_rcp(float a) {
+#ifdef __CUDA_ARCH__
+  return __frcp_rn(a);
+#else
+  return 1.0f / a;
+#endif
+}
+IWQ_HD float fma_rn(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+  return __fmaf_rn(a, b, c);
+#else
+  return fmaf(a, b, c);
+#endif
+}
+
+// half2 / bfloat162 fused multiply-add with a zero addend.  On the device this is one HFMA2; the
+// host emulation multiplies in fp32 (exact: 11x11 / 8x8 bit significands) and rounds once.
+template <int DT>
+IWQ_HD typename DType<DT>::T2 mul_add_zero(typename DType<DT>::T2 a, typename DType<DT>::T2 b) {
+  using T2 = typename DType<DT>::T2;
+#ifdef __CUDA_ARCH__
+  return __hfma2(a, b, from_u32<T2>(0u));
+#else
+  float2 x = DType<DT>::to_f32x2(a), y = DType<DT>::to_f32x2(b);
+  return DType<DT>::from_f32x2(x.x * y.x + 0.0f, x.y * y.y + 0.0f);
+#endif
+}
+
+// quotient w/s for 16-bit w, s, such that rounding it to D equals rD(fl32(w / s)).
+// r = fl32(1/s);  t = w*r;  e = fma(-s, t, w);  q = fma(r, e, t).
+// Proven for every (w, s) pair of both dtypes by tests/host/div_check.c (CPU, exhaustive) and by
+// iwq_selftest_division on the device.  Three FMA-pipe ops instead of an IEEE division (8-10).
+IWQ_HD float fast_quot(float w, float s, float r) {
+  float t = w * r;
+  float e = fma_rn(-s, t, w);
+  return fma_rn(r, e, t);
+}
+
+template <int DT>
+IWQ_HD typename DType<DT>::T2 fast_quot2(typename DType<DT>::T2 w2, float s, float r) {
+  float2 w = DType<DT>::to_f32x2(w2);
+#ifdef __CUDA_ARCH__
+  // packed fp32x2 FMA (sm_100a FFMA2): one issue slot for both elements
+  const float2 rr = make_float2(r, r), ns = make_float2(-s, -s);
+  float2 t = __fmul2_rn(w, rr);
+  float2 e = __ffma2_rn(ns, t, w);
+  float2 q = __ffma2_rn(rr, e, t);
+  return DType<DT>::from_f32x2(q.x, q.y);
+#else
+  return DType<DT>::from_f32x2(fast_quot(w.x, s, r), fast_quot(w.y, s, r));
+#endif
+}
+
+template <int DT>
+IWQ_HD typename DType<DT>::T2 ieee_quot2(typename DType<DT>::T2 w2, float s) {
+  float2 w = DType<DT>::to_f32x2(w2);
+  return DType<DT>::from_f32x2(ieee_div(w.x, s), ieee_div(w.y, s));
+}
+
+// ------------------------------------------------------------------------------------------------
+// configuration constants shared by all segments of a launch (built on the host: iwq_host.cu)
+// ------------------------------------------------------------------------------------------------
+struct FpEntry {      // one per binade of the clamped magnitude |n|
+  uint16_t magic;     // 1.5 * 2^(grid_exp + mantissa_bits(D)): (a + magic) - magic == RNE onto the grid
+  uint16_t bound;     // largest value of the binade the codec may return (no carry, quirk Q2); +inf for RNE flavour
+  uint16_t bump_thr;  // a >= bump_thr: half-precision log2 rounds up to the next integer (quirk Q3) ...
+  uint16_t bump_val;  // ... and the result is 2^(e+1)
+};
+
+struct QuantConsts {
+  int32_t scheme, bits, exp_bits, mant_bits, symmetric, flavour_rne;
+  float min_int, max_int;  // INT: clamp bounds (quant_funcs.py:19-20, :26-27)
+  float eps;               // rD(1e-5) (quant_funcs.py:21,25) or rD(1e-8) (fp4_quantize_cpu.py:68)
+  float fmax;              // FP: largest minifloat magnitude (quant_linear.py:741 / fp4_quantize_cpu.py:64)
+  uint16_t fmax_bits;      // fmax as D bits
+  uint16_t tiny_bits;      // D bits of 2^(emin - M - 3): magnitudes are clamped up to it before the table lookup
+  int32_t tbl_base;        // biased D exponent of table entry 0
+  int32_t tbl_n;
+  FpEntry tbl[40];
+};
+
+// ------------------------------------------------------------------------------------------------
+// INT min-max: per-segment parameters        (quant_funcs.py:16-29, quant_linear.py:909-922)
+// ------------------------------------------------------------------------------------------------
+struct IntQ {
+  float s;         // scale, a D value
+  float r;         // fl32(1/s)
+  float z;         // zero point (integer valued), 0 for symmetric
+  float lo, hi;    // min_int - z, max_int - z: clamp(rint(x)+z, min, max) - z == clamp(rint(x), lo, hi)
+  bool bad;        // !(0 < s < inf): the segment yields NaN (quant_funcs.py:40 assert condition)
+  bool slow_div;   // bf16 only: |w|/s can overflow fp32, use IEEE division for this segment
+};
+
+// mx = max (asym) or absmax (sym); mn = min (asym), ignored for sym.  D values held in fp32.
+template <int DT>
+IWQ_HD IntQ int_segment_params(float mx, float mn, const QuantConsts& c) {
+  IntQ q;
+  if (c.symmetric) {
+    float d = rD<DT>(clamp_min_nan(mx, c.eps));           // absmax.clamp(min=1e-5)            :25
+    q.s = rD<DT>(ieee_div(d, c.max_int));                 // / max_int                          :28
+    q.z = 0.0f;                                           // zeros = 0                          :29
+  } else {
+    float d = rD<DT>(mx - mn);                            // max_val - min_val                  :21
+    d = rD<DT>(clamp_min_nan(d, c.eps));                  // .clamp(min=1e-5)                   :21
+    q.s = rD<DT>(ieee_div(d, c.max_int));                 // / max_int                          :21
+    float zq = rD<DT>(ieee_div(mn, q.s));                 // min_val / scales                   :22
+    q.z = clamp_nan(-rintf(zq), c.min_int, c.max_int);    // (-round(.)).clamp_(min_int,max_int):22
+  }
+  q.r = ieee_rcp(q.s);
+  q.lo = c.min_int - q.z;
+  q.hi = c.max_int - q.z;
+  q.bad = !(q.s > 0.0f && q.s < INFINITY);
+  q.slow_div = false;
+  if (DT == IWQ_BF16) {
+    float big = fmaxf(fabsf(mx), c.symmetric ? 0.0f : fabsf(mn));
+    q.slow_div = !(big * q.r < 1e37f);
+  }
+  return q;
+}
+
+// Packed element stage for the fast INT path.
+//   x  = rD(w / s)                                  one F2FP pack after the fp32 quotient
+//   r  = rint(x)                                    (x + K) - K in D arithmetic, K = 1.5 * 2^mantissa_bits
+//   d  = clamp(r, lo, hi)          == clamp(r + z, min_int, max_int) - z   (all values are small integers)
+//   out= fma(d, s, +0)             == rD(d * s), and turns -0 into +0 exactly like "(-0.0) + zeros" does
+// Valid when |lo|,|hi| <= 512 (fp16) / 64 (bf16); kWide extends bf16 to 256 via the |x|+128 trick.
+template <int DT, bool kWide>
+struct IntFast {
+  using D = DType<DT>;
+  using T2 = typename D::T2;
+  T2 lo2, hi2, s2;
+  float s, r;
+  bool slow_div;
+
+  IWQ_HD void setup(const IntQ& q) {
+    lo2 = D::from_f32x2(q.lo, q.lo);
+    hi2 = D::from_f32x2(q.hi, q.hi);
+    s2 = D::from_f32x2(q.s, q.s);
+    s = q.s;
+    r = q.r;
+    slow_div = q.slow_div;
+  }
+
+  IWQ_HD T2 rint2(T2 x) const {
+    if (DT == IWQ_F16) {
+      const T2 K = D::bcast(0x6600);  // 1536.0
+      return __hsub2(__hadd2(x, K), K);
+    } else if (!kWide) {
+      const T2 K = D::bcast(0x4340);  // 192.0
+      return __hsub2(__hadd2(x, K), K);
+    } else {
+      // bf16, |range| up to 256: |x| < 128 -> (|x| + 128) - 128 rounds to integer (spacing 1 in
+      // [128,256)); |x| >= 128 is already an integer.  Sign restored by OR (rint is odd).
+      const T2 K = D::bcast(0x4300);  // 128.0
+      uint32_t xb = as_u32(x);
+      uint32_t ab = xb & 0x7FFF7FFFu;
+      T2 a = from_u32<T2>(ab);
+      T2 ra = __hsub2(__hadd2(a, K), K);
+      uint32_t big = __hge2_mask(a, K);  // also false for NaN -> ra (NaN) is kept
+      uint32_t rb = (as_u32(ra) & ~big) | (ab & big);
+      return from_u32<T2>(rb | (xb & 0x80008000u));
+    }
+  }
+
+  // returns the dequantised pair; *d2 receives clamp(rint(x), lo, hi) (for code emission)
+  IWQ_HD uint32_t apply(uint32_t w2, T2* d2) const {
+    T2 w = from_u32<T2>(w2);
+    T2 x = slow_div ? ieee_quot2<DT>(w, s) : fast_quot2<DT>(w, s, r);
+    T2 q = rint2(x);
+    q = __hmin2_nan(__hmax2_nan(q, lo2), hi2);
+    *d2 = q;
+    return as_u32(mul_add_zero<DT>(q, s2));
+  }
+};
+
+// Reference-order scalar element stage: any bit width, any magnitude (quant_funcs.py:36-38).
+template <int DT>
+IWQ_HD uint16_t int_generic_elem(uint16_t wb, const IntQ& q, const QuantConsts& c, float* code) {
+  float w = DType<DT>::to_f32(wb);
+  float x = rD<DT>(ieee_div(w, q.s));        // tensor / scales
+  x = rintf(x);                              // torch.round
+  x = rD<DT>(x + q.z);                       // + zeros
+  x = clamp_nan(x, c.min_int, c.max_int);    // torch.clamp
+  *code = x;
+  float o = rD<DT>(x - q.z);                 // - zeros
+  o = rD<DT>(o * q.s);                       // * scales
+  return DType<DT>::from_f32(o);
+}
+
+// ------------------------------------------------------------------------------------------------
+// minifloat: per-segment parameters
+//   codec flavour: quant_linear.py:744-755 ; RNE flavour: fp4_quantize_cpu.py:67-69
+// ------------------------------------------------------------------------------------------------
+struct FpQ {
+  float S;        // scale (D value)
+  float r;        // fl32(1/S)
+  float mid;      // asym mid point (D value), 0 for sym
+  float mid_h;    // rD(fp16(mid)): what is added back (quirk Q1: `self.zeros` is a .half() copy)
+  bool bad;       // !(0 < S < inf)
+  bool slow_div;
+};
+
+template <int DT>
+IWQ_HD FpQ fp_segment_params(float mx, float mn, const QuantConsts& c) {
+  FpQ q;
+  q.mid = 0.0f;
+  q.mid_h = 0.0f;
+  if (c.flavour_rne) {
+    float d = rD<DT>(clamp_min_nan(mx, c.eps));                    // absmax.clamp(min=1e-8)   fp4_quantize_cpu.py:68
+    q.S = rD<DT>(ieee_div(d, c.fmax));                             // / max_float              :69
+  } else if (c.symmetric) {
+    float d = rD<DT>(clamp_min_nan(mx, c.eps));                    // absmax.clamp(min=1e-5)   quant_linear.py:744
+    q.S = rD<DT>(clamp_min_nan(rD<DT>(ieee_div(d, c.fmax)), c.eps));  // (/ fmax).clamp(1e-5)  :745
+  } else {
+    q.mid = rD<DT>(rD<DT>(mx + mn) * 0.5f);                        // (max + min) * 0.5        :751
+    float span = rD<DT>(rD<DT>(mx - mn) * 0.5f);                   // (max - min) * 0.5        :752
+    span = rD<DT>(clamp_min_nan(span, c.eps));                     // .clamp(min=1e-5)         :752
+    q.S = rD<DT>(clamp_min_nan(rD<DT>(ieee_div(span, c.fmax)), c.eps));  //                    :753
+    q.mid_h = rD<DT>(DType<IWQ_F16>::to_f32(DType<IWQ_F16>::from_f32(q.mid)));  // zeros.half().to(D) :765,:776
+  }
+  q.r = ieee_rcp(q.S);
+  q.bad = !(q.S > 0.0f && q.S < INFINITY);
+  float big = fmaxf(fabsf(mx), fabsf(mn)) * 2.0f;
+  q.slow_div = q.bad || !(big * q.r < 1e37f);
+  return q;
+}
+
+// Packed element stage for both minifloat flavours.
+//   n   = clamp(rD([w - mid] / S), +-fmax)                                         quant_linear.py:747,755
+//   a   = max(|n|, tiny)            tiny = 2^(emin-M-3) quantises to 0 like everything below it
+//   per-binade constants from the table (indexed by the D exponent field of a)
+//   v   = min((a + magic) - magic, bound)     RNE onto the binade's grid, mantissa overflow does not
+//                                             carry (quirk Q2, :148-149); subnormal grid below emin (:152-154)
+//   v   = a >= bump_thr ? bump_val : v        half-precision log2 rounding (quirk Q3, :139)
+//   sign: codec -> (n < 0), so a negative input that flushes to zero gives -0.0 (quirk Q4, :130,:234)
+//         RNE   -> sign bit of n (rint(-0.0/sc)*sc = -0.0, fp4_quantize_cpu.py:42-43)
+//   out = rD(v * S) [+ mid_h]                                                      :774-777
+template <int DT>
+struct FpTable {
+  using D = DType<DT>;
+  using T2 = typename D::T2;
+  T2 S2, mid2, midh2, fmax2, tiny2;
+  float S, r;
+  bool asym, rne, slow_div;
+  int tbl_off;  // entry index = exponent_field - tbl_base
+
+  IWQ_HD void setup(const FpQ& q, const QuantConsts& c) {
+    S2 = D::from_f32x2(q.S, q.S);
+    mid2 = D::from_f32x2(q.mid, q.mid);
+    midh2 = D::from_f32x2(q.mid_h, q.mid_h);
+    fmax2 = D::bcast(c.fmax_bits);
+    tiny2 = D::bcast(c.tiny_bits);
+    S = q.S;
+    r = q.r;
+    asym = !c.symmetric && !c.flavour_rne;
+    rne = c.flavour_rne != 0;
+    slow_div = q.slow_div;
+    tbl_off = c.tbl_base;
+  }
+
+  // quantise an already-normalised pair n2 (D values) onto the minifloat grid; sign handled here
+  IWQ_HD T2 grid(T2 n2, const FpEntry* tbl) const {
+    constexpr int MB = D::kMantBits;
+    const uint32_t nb = as_u32(n2);
+    T2 a = from_u32<T2>(nb & 0x7FFF7FFFu);
+    a = __hmin2(a, fmax2);   // clamp(+-fmax); a NaN becomes fmax here and is restored by the * S below
+    a = __hmax2(a, tiny2);
+    const uint32_t ab = as_u32(a);
+    const uint32_t i0 = ((ab >> MB) & ((1u << (15 - MB)) - 1u)) - tbl_off;
+    const uint32_t i1 = (ab >> (16 + MB)) - tbl_off;
+    const uint2 e0 = *reinterpret_cast<const uint2*>(tbl + i0);
+    const uint2 e1 = *reinterpret_cast<const uint2*>(tbl + i1);
+    const uint32_t magic = (e0.x & 0xFFFFu) | (e1.x << 16);
+    const uint32_t bound = (e0.x >> 16) | (e1.x & 0xFFFF0000u);
+    const uint32_t thr = (e0.y & 0xFFFFu) | (e1.y << 16);
+    const uint32_t bval = (e0.y >> 16) | (e1.y & 0xFFFF0000u);
+    T2 v = __hsub2(__hadd2(a, from_u32<T2>(magic)), from_u32<T2>(magic));
+    v = __hmin2(v, from_u32<T2>(bound));
+    const uint32_t bump = __hge2_mask(a, from_u32<T2>(thr));
+    uint32_t vb = (as_u32(v) & ~bump) | (bval & bump);
+    const uint32_t sgn = rne ? (nb & 0x80008000u) : (__hlt2_mask(n2, from_u32<T2>(0u)) & 0x80008000u);
+    return from_u32<T2>(vb | sgn);
+  }
+
+  IWQ_HD uint32_t apply(uint32_t w2, const FpEntry* tbl, T2* v2) const {
+    T2 w = from_u32<T2>(w2);
+    if (asym) w = __hsub2(w, mid2);                                   // weight - zeros            :755
+    T2 n = slow_div ? ieee_quot2<DT>(w, S) : fast_quot2<DT>(w, S, r); // / scales
+    T2 v = grid(n, tbl);
+    // a NaN quotient (only possible when S is 0/inf/NaN, i.e. slow_div) must stay NaN: grid() clamped it
+    if (slow_div) v = from_u32<T2>(as_u32(v) | __hneu2_mask(n, n));
+    *v2 = v;
+    T2 o = __hmul2(v, S2);                                            // decoded.to(D) * scales    :774
+    if (asym) o = __hadd2(o, midh2);                                  // + zeros.half().to(D)      :776
+    return as_u32(o);
+  }
+};
+
+// minifloat code of a grid value (for optional code emission): sign | exponent field | mantissa,
+// zero -> 0 unless the sign survived (quirk Q4).                     quant_linear.py:156-161
+template <int DT>
+IWQ_HD uint8_t fp_code_of(uint16_t vbits, int E, int M) {
+  float v = DType<DT>::to_f32(vbits);
+  uint32_t sign = (vbits >> 15) & 1u;
+  float a = fabsf(v);
+  int bias = (1 << (E - 1)) - 1;
+  int emin = 1 - bias;
+  uint32_t ef = 0, mf = 0;
+  if (a > 0.0f) {
+    int e;
+    float m = frexpf(a, &e);  // a = m * 2^e, m in [0.5, 1)
+    e -= 1;                   // a = (2m) * 2^e, 2m in [1, 2)
+    if (e < emin) {
+      mf = (uint32_t)(a * exp2f((float)(M - emin)));
+    } else {
+      ef = (uint32_t)(e + bias);
+      mf = (uint32_t)((2.0f * m - 1.0f) * (float)(1 << M));
+    }
+  }
+  return (uint8_t)((sign << (E + M)) | (ef << M) | mf);
+}
+
+}  // namespace iwq

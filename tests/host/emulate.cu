@@ -1,0 +1,127 @@
+// TEST-ONLY CPU emulator: runs the *host instantiation* of the product's per-segment / per-element
+// math (iron_weight_only_quant_b200/csrc/iwq_math.cuh, iwq_consts.h) over whole matrices so that the
+// arithmetic (clamp fusion, magic-number rounding, reciprocal+FMA quotient, minifloat table) can be
+// checked against the reference's golden vectors on the GPU-less build box.  The product never loads
+// this library; it is built and used by tests/test_host_emulation.py only.
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../iron_weight_only_quant_b200/csrc/iwq_consts.h"
+
+using namespace iwq;
+
+template <int DT>
+static void seg_range(const uint16_t* w, int64_t n, bool sym, float* mx, float* mn) {
+  float a = sym ? 0.0f : -INFINITY, b = INFINITY;
+  bool nan = false;
+  for (int64_t i = 0; i < n; ++i) {
+    float v = DType<DT>::to_f32(w[i]);
+    if (v != v) nan = true;
+    if (sym) {
+      a = fmaxf(a, fabsf(v));
+    } else {
+      a = fmaxf(a, v);
+      b = fminf(b, v);
+    }
+  }
+  if (nan) a = b = NAN;
+  *mx = a;
+  *mn = b;
+}
+
+template <int DT>
+static int run(const iwq_config_t* cfg, const QuantConsts& c, int kind, const uint16_t* w, uint16_t* out, uint16_t* scales, uint16_t* zeros,
+               int64_t rows, int64_t cols) {
+  using T2 = typename DType<DT>::T2;
+  const int64_t total = rows * cols;
+  int64_t seg = cfg->group > 0 ? cfg->group : (cfg->group == IWQ_GROUP_PER_TENSOR ? total : cols);
+  if (cfg->group > 0 && cols % cfg->group) return IWQ_ERR_INDIVISIBLE;
+  if (seg % 2) return IWQ_ERR_UNSUPPORTED;
+  const bool sym = c.symmetric != 0;
+  for (int64_t s0 = 0, g = 0; s0 < total; s0 += seg, ++g) {
+    float mx, mn;
+    seg_range<DT>(w + s0, seg, sym, &mx, &mn);
+    float sc = 0, zp = 0;
+    if (kind == KIND_FP) {
+      FpQ q = fp_segment_params<DT>(mx, mn, c);
+      FpTable<DT> f;
+      f.setup(q, c);
+      for (int64_t i = 0; i < seg; i += 2) {
+        uint32_t w2 = (uint32_t)w[s0 + i] | ((uint32_t)w[s0 + i + 1] << 16);
+        T2 v;
+        uint32_t o = f.apply(w2, c.tbl, &v);
+        out[s0 + i] = (uint16_t)(o & 0xFFFF);
+        out[s0 + i + 1] = (uint16_t)(o >> 16);
+      }
+      sc = q.S;
+      zp = q.mid;
+    } else {
+      IntQ q = int_segment_params<DT>(mx, mn, c);
+      if (kind == KIND_INT_GENERIC) {
+        for (int64_t i = 0; i < seg; ++i) {
+          float code;
+          out[s0 + i] = int_generic_elem<DT>(w[s0 + i], q, c, &code);
+        }
+      } else {
+        IntFast<DT, false> fn;
+        IntFast<DT, true> fw;
+        fn.setup(q);
+        fw.setup(q);
+        for (int64_t i = 0; i < seg; i += 2) {
+          uint32_t w2 = (uint32_t)w[s0 + i] | ((uint32_t)w[s0 + i + 1] << 16);
+          T2 d;
+          uint32_t o = kind == KIND_INT_WIDE ? fw.apply(w2, &d) : fn.apply(w2, &d);
+          out[s0 + i] = (uint16_t)(o & 0xFFFF);
+          out[s0 + i + 1] = (uint16_t)(o >> 16);
+        }
+      }
+      sc = q.s;
+      zp = q.z;
+    }
+    if (scales) scales[g] = DType<DT>::from_f32(sc);
+    if (zeros) zeros[g] = DType<DT>::from_f32(zp);
+  }
+  return 0;
+}
+
+extern "C" int emu_fake_quant(const iwq_config_t* cfg, const uint16_t* w, uint16_t* out, uint16_t* scales, uint16_t* zeros, int64_t rows,
+                              int64_t cols, int force_kind) {
+  QuantConsts c;
+  int kind = 0;
+  std::string err;
+  int rc = build_quant_consts(cfg, &c, &kind, &err);
+  if (rc) return rc;
+  if (force_kind >= 0) kind = force_kind;
+  return cfg->dtype == IWQ_F16 ? run<IWQ_F16>(cfg, c, kind, w, out, scales, zeros, rows, cols)
+                               : run<IWQ_BF16>(cfg, c, kind, w, out, scales, zeros, rows, cols);
+}
+
+template <int DT>
+static void roundtrip(const QuantConsts& c, const uint16_t* x, uint16_t* y, int64_t n) {
+  using T2 = typename DType<DT>::T2;
+  FpQ q;
+  q.S = 1.0f; q.r = 1.0f; q.mid = 0.f; q.mid_h = 0.f; q.bad = false; q.slow_div = false;
+  FpTable<DT> f;
+  f.setup(q, c);
+  for (int64_t i = 0; i < n; i += 2) {
+    uint32_t x2 = (uint32_t)x[i] | ((uint32_t)x[i + 1] << 16);
+    uint32_t o = as_u32(f.grid(from_u32<T2>(x2), c.tbl));
+    y[i] = (uint16_t)(o & 0xFFFF);
+    y[i + 1] = (uint16_t)(o >> 16);
+  }
+}
+
+extern "C" int emu_fp_roundtrip(int dtype, int flavour, int E, int M, const uint16_t* x, uint16_t* y, int64_t n) {
+  iwq_config_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.dtype = dtype; cfg.scheme = flavour; cfg.exp_bits = E; cfg.mant_bits = M; cfg.symmetric = 1; cfg.group = 128;
+  QuantConsts c;
+  int kind = 0;
+  std::string err;
+  int rc = build_quant_consts(&cfg, &c, &kind, &err);
+  if (rc) return rc;
+  if (dtype == IWQ_F16) roundtrip<IWQ_F16>(c, x, y, n); else roundtrip<IWQ_BF16>(c, x, y, n);
+  return 0;
+}

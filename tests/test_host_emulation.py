@@ -1,0 +1,164 @@
+"""CPU check of the product's device math (host instantiation of csrc/iwq_math.cuh + iwq_consts.h).
+
+The build box has no GPU, so before GPU time is spent the same `__host__ __device__` functions the CUDA
+kernels call are compiled for the host into a TEST-ONLY shared library (tests/host/emulate.cu) and run
+against the reference's golden vectors.  This is not a fallback: the package never loads it.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "host", "emulate.cu")
+NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+F16, BF16 = 0, 1
+SCHEME_INT, SCHEME_FP_CODEC, SCHEME_FP_RNE = 0, 1, 2
+KIND_INT_FAST, KIND_INT_WIDE, KIND_FP, KIND_INT_GENERIC = 0, 1, 2, 3
+FORMATS = {"e2m1": (2, 1), "e1m2": (1, 2), "e3m2": (3, 2), "e2m3": (2, 3), "e4m3": (4, 3), "e5m2": (5, 2)}
+
+
+class Cfg(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("dtype", "scheme", "bits", "exp_bits", "mant_bits", "symmetric", "group", "variant")]
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    if not os.path.exists(NVCC):
+        pytest.skip("nvcc not available")
+    out = str(tmp_path_factory.mktemp("emu") / "libiwq_emulate.so")
+    cmd = [NVCC, "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a", SRC, "-o", out]
+    subprocess.run(cmd, check=True, capture_output=True)
+    lib = ctypes.CDLL(out)
+    lib.emu_fake_quant.restype = ctypes.c_int
+    lib.emu_fp_roundtrip.restype = ctypes.c_int
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def run_emu(lib, w, dtype, scheme, group, bits=4, E=0, M=0, sym=False, force_kind=-1):
+    cfg = Cfg(dtype=dtype, scheme=scheme, bits=bits, exp_bits=E, mant_bits=M, symmetric=int(sym), group=group, variant=0)
+    w = np.ascontiguousarray(w, dtype=np.uint16)
+    rows, cols = w.shape
+    G = rows * cols // group if group > 0 else (1 if group == -1 else rows)
+    out = np.empty_like(w)
+    scales = np.empty(G, np.uint16)
+    zeros = np.empty(G, np.uint16)
+    rc = lib.emu_fake_quant(ctypes.byref(cfg), _ptr(w), _ptr(out), _ptr(scales), _ptr(zeros), ctypes.c_int64(rows), ctypes.c_int64(cols), force_kind)
+    assert rc == 0, rc
+    return out, scales, zeros
+
+
+def _is_nan(bits, dt):
+    if dt == "f16":
+        return (bits & 0x7FFF) > 0x7C00
+    return (bits & 0x7FFF) > 0x7F80
+
+
+def assert_bits_equal(a, b, dt, msg=""):
+    na, nb = _is_nan(a, dt), _is_nan(b, dt)
+    assert np.array_equal(na, nb), msg
+    assert np.array_equal(np.where(na, 0, a), np.where(nb, 0, b)), msg
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("sym", [False, True])
+@pytest.mark.parametrize("bits", [2, 3, 4, 5, 6, 8])
+def test_int_fast_math_matches_reference(emu, golden, dt, sym, bits):
+    g = golden("golden_int")
+    w = g[f"w_{dt}"]
+    for grp in (32, 64, 128, 256, -1, -2):
+        key = f"{dt}_b{bits}_{'sym' if sym else 'asym'}_g{grp}"
+        out, scales, zeros = run_emu(emu, w, F16 if dt == "f16" else BF16, SCHEME_INT, grp, bits=bits, sym=sym)
+        assert_bits_equal(out, g[f"ql_{key}_out"], dt, key)
+        assert_bits_equal(scales, g[f"ql_{key}_scales"], dt, key)
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_int_generic_math_matches_reference(emu, golden, dt):
+    g = golden("golden_int")
+    w = g[f"w_{dt}"]
+    for bits in (3, 4, 8):
+        for sym in (False, True):
+            key = f"{dt}_b{bits}_{'sym' if sym else 'asym'}_g128"
+            out, _, _ = run_emu(emu, w, F16 if dt == "f16" else BF16, SCHEME_INT, 128, bits=bits, sym=sym, force_kind=KIND_INT_GENERIC)
+            assert_bits_equal(out, g[f"ql_{key}_out"], dt, key)
+
+
+def test_bf16_wide_path_matches_fast_and_reference(emu, golden):
+    g = golden("golden_int")
+    w = g["w_bf16"]
+    for bits in (4, 6, 8):
+        for sym in (False, True):
+            key = f"bf16_b{bits}_{'sym' if sym else 'asym'}_g64"
+            out, _, _ = run_emu(emu, w, BF16, SCHEME_INT, 64, bits=bits, sym=sym, force_kind=KIND_INT_WIDE)
+            assert_bits_equal(out, g[f"ql_{key}_out"], "bf16", key)
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("fmt", list(FORMATS))
+def test_fp_codec_table_exhaustive(emu, golden, dt, fmt):
+    E, M = FORMATS[fmt]
+    if dt == "f16" and E >= 5:
+        return
+    g = golden("golden_fp_tables")
+    bits = np.arange(65536, dtype=np.uint32).astype(np.uint16)
+    y = np.empty_like(bits)
+    rc = emu.emu_fp_roundtrip(F16 if dt == "f16" else BF16, SCHEME_FP_CODEC, E, M, _ptr(bits), _ptr(y), ctypes.c_int64(65536))
+    assert rc == 0
+    from oracle import fakequant_oracle as O
+
+    x = O.from_bits(bits, dt)
+    fmax = O.fp_format(E, M)[3]
+    ok = np.isfinite(x) & (np.abs(x) <= fmax)
+    if dt == "bf16":
+        ok &= (np.abs(x) >= 2.0 ** -126) | (x == 0)
+    want = g[f"codec_{dt}_{fmt}_val"]
+    bad = ok & (y != want)
+    assert not bad.any(), [(hex(b), hex(a), hex(c)) for b, a, c in zip(bits[bad][:8], y[bad][:8], want[bad][:8])]
+
+
+@pytest.mark.parametrize("fmt", ["e2m1", "e1m2", "e3m2", "e2m3", "e4m3"])
+def test_fp_rne_table_exhaustive(emu, golden, fmt):
+    E, M = FORMATS[fmt]
+    g = golden("golden_fp_tables")
+    bits = np.arange(65536, dtype=np.uint32).astype(np.uint16)
+    y = np.empty_like(bits)
+    rc = emu.emu_fp_roundtrip(F16, SCHEME_FP_RNE, E, M, _ptr(bits), _ptr(y), ctypes.c_int64(65536))
+    assert rc == 0
+    ok = (bits & 0x7FFF) < 0x7C00
+    want = g[f"fpscale_f16_{fmt}"]
+    bad = ok & (y != want)
+    assert not bad.any(), [(hex(b), hex(a), hex(c)) for b, a, c in zip(bits[bad][:8], y[bad][:8], want[bad][:8])]
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("fmt", list(FORMATS))
+def test_fp_chain_math_matches_reference(emu, golden, dt, fmt):
+    E, M = FORMATS[fmt]
+    if dt == "f16" and E >= 5:
+        return
+    g = golden("golden_fp_chain")
+    w = g[f"w_{dt}"]
+    for sym in (False, True):
+        for grp in (32, 128, -1, -2):
+            key = f"{dt}_{fmt}_{'sym' if sym else 'asym'}_g{grp}"
+            out, scales, zeros = run_emu(emu, w, F16 if dt == "f16" else BF16, SCHEME_FP_CODEC, grp, E=E, M=M, sym=sym)
+            assert_bits_equal(out, g[f"ql_{key}_out"], dt, key)
+
+
+def test_fp_rne_chain_matches_reference(emu, golden):
+    g = golden("golden_fp_rne")
+    w = g["w_f16"]
+    for grp in (32, 128, 512):
+        out, _, _ = run_emu(emu, w, F16, SCHEME_FP_RNE, grp, E=2, M=1, sym=True)
+        assert_bits_equal(out.reshape(-1, grp), g[f"e2m1_g{grp}"], "f16", str(grp))
+    out, _, _ = run_emu(emu, w, F16, SCHEME_FP_RNE, -1, E=2, M=1, sym=True)
+    assert_bits_equal(out.reshape(1, -1), g["e2m1_pt"], "f16", "pt")

@@ -1,0 +1,182 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/iwq_b200.h declares, the
+product path refuses to run without a GPU (no CPU fallback), layer partitioning, and the N>1 range
+exchange over gloo (world size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+
+    ge.build()
+    from iron_weight_only_quant_b200 import _lib
+
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "iwq_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(iwq_[a-z_0-9]+)\s*\(", hdr))
+    assert {"iwq_fake_quant", "iwq_fake_quant_batched", "iwq_minmax", "iwq_fake_quant_with_range", "iwq_fake_quant_host"} <= declared
+    L = ctypes.CDLL(built.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert set(built.EXPORTS) == declared
+    assert L.iwq_abi_version() == 1
+    L.iwq_workspace_bytes.restype = ctypes.c_size_t
+    assert L.iwq_workspace_bytes(10) == 640
+
+
+def test_argument_validation_without_gpu(built):
+    """Validation happens before any CUDA call, so it is testable here: error codes map to the
+    exception classes the reference raises."""
+    L = built.lib()
+    cfg = built.make_config(torch.float16, built.SCHEME_INT, 128, bits=4)
+    m = built.Matrix(w=0, out=0, scales=None, zeros=None, codes=None, rows=4, cols=128)
+    rc = L.iwq_fake_quant(ctypes.byref(cfg), ctypes.byref(m), None, None, None)
+    with pytest.raises(ValueError):
+        built.check(rc)  # null pointers
+    m = built.Matrix(w=4096, out=4096, scales=None, zeros=None, codes=None, rows=4, cols=100)
+    with pytest.raises(AssertionError):
+        built.check(L.iwq_fake_quant(ctypes.byref(cfg), ctypes.byref(m), None, None, None))  # 100 % 128
+    cfg = built.make_config(torch.float16, built.SCHEME_INT, -3, bits=4)
+    m = built.Matrix(w=4096, out=4096, scales=None, zeros=None, codes=None, rows=4, cols=128)
+    with pytest.raises(ValueError):
+        built.check(L.iwq_fake_quant(ctypes.byref(cfg), ctypes.byref(m), None, None, None))  # Invalid w_group_size
+    cfg = built.make_config(torch.float16, built.SCHEME_FP_CODEC, 128, exp_bits=5, mant_bits=2)
+    with pytest.raises(RuntimeError):
+        built.check(L.iwq_fake_quant(ctypes.byref(cfg), ctypes.byref(m), None, None, None))  # E5M2 on fp16
+    cfg = built.make_config(torch.float16, built.SCHEME_INT, 128, bits=4)
+    m = built.Matrix(w=4100, out=4100, scales=None, zeros=None, codes=None, rows=4, cols=128)
+    with pytest.raises(RuntimeError):
+        built.check(L.iwq_fake_quant(ctypes.byref(cfg), ctypes.byref(m), None, None, None))  # misaligned
+    with pytest.raises(TypeError):
+        built.make_config(torch.float32, built.SCHEME_INT, 128, bits=4)
+
+
+def test_no_cpu_fallback(built):
+    from iron_weight_only_quant_b200 import fp4_quantize_cpu, quant_funcs, quant_linear
+
+    w = torch.zeros(4, 128, dtype=torch.float16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        quant_funcs.pseudo_quantize_tensor(w, n_bits=4, q_group_size=128)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fp4_quantize_cpu.quantize_fp16_to_fp4_e1m2(w)
+    lin = torch.nn.Linear(128, 4, bias=False).half()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        quant_linear.QuantLinear.from_linear(lin)
+    # nothing in the package imports the oracle
+    pkg = os.path.join(ROOT, "iron_weight_only_quant_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, fn)).read(), fn
+
+
+def test_signatures_match_reference(built):
+    """Names, positional order and defaults of the reference's public functions."""
+    import inspect
+
+    from iron_weight_only_quant_b200 import fp4_quantize_cpu, quant_funcs, quant_linear, quant_wrapper
+
+    def sig(f):
+        return [(p.name, p.default) for p in inspect.signature(f).parameters.values()]
+
+    E = inspect.Parameter.empty
+    assert sig(quant_funcs.pseudo_quantize_tensor) == [("tensor", E), ("n_bits", 8), ("zero_point", True), ("q_group_size", -1), ("per_tensor", False), ("inplace", False)]
+    assert sig(quant_funcs.quantize_weight_per_channel_absmax) == [("w", E), ("n_bits", 8)]
+    assert sig(quant_funcs.quantize_activation_per_token_absmax) == [("t", E), ("n_bits", 8)]
+    assert sig(fp4_quantize_cpu.quantize_fp16_to_fp4_e1m2) == [("tensor", E), ("group_size", 128), ("per_tensor", False), ("return_scales", False)]
+    assert [n for n, _ in sig(fp4_quantize_cpu._fp_scale)] == ["tensor", "S", "M", "bias", "max_float", "min_float"]
+    assert sig(quant_wrapper.quantize_model) == [("model", E), ("args", E), ("quant_mix_gate", False)]
+    fl = sig(quant_linear.QuantLinear.from_linear)
+    assert fl[:8] == [("linear_layer", E), ("w_bit", 4), ("w_group_size", 128), ("symmetric", False), ("mode", 0), ("weight_format", "int"), ("approximate", False), ("quant_dim", 0)]
+    assert [n for n, _ in fl[8:]] == ["fp8_hi_align_start", "fp8_hi_align_exp_field", "fp8_tail_pad_bits", "double_approximate", "fp6_hi_align_start", "fp6_hi_align_exp_field", "fp6_tail_pad_bits", "fp4_hi_align_start", "fp4_hi_align_exp_field", "fp4_tail_pad_bits"]
+    init = sig(quant_linear.QuantLinear.__init__)
+    assert init[1:11] == [("in_features", E), ("out_features", E), ("bias", True), ("w_bit", 4), ("w_group_size", 128), ("symmetric", True), ("mode", 0), ("weight_format", "int"), ("approximate", False), ("quant_dim", 0)]
+    ql = quant_linear.QuantLinear(16, 8)
+    assert set(dict(ql.named_buffers()).keys()) == {"quantized"}  # the others are registered as None
+    for b in ("scales", "zeros", "weight_fp4", "weight_fp6", "weight_fp8", "weight_bfp_mantissa", "weight_bfp_exponent"):
+        assert hasattr(ql, b) and getattr(ql, b) is None
+    assert ql.weight.shape == (8, 16) and ql.bias.shape == (8,)
+    quant_linear.configure_fp_formats(fp4_exp_bits=1, fp4_mantissa_bits=2)
+    assert (quant_linear.FP4_EXP_BITS, quant_linear.FP4_MANTISSA_BITS, quant_linear.FP4_EXP_BIAS) == (1, 2, 0)
+    quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
+    assert quant_linear.fp_format_of("fp8") == (4, 3)
+
+
+def test_layer_partition(built):
+    from iron_weight_only_quant_b200 import shapes
+
+    m = shapes.MODELS["llama-2-70b"]
+    assert m.total_weights() == 68_451_041_280 and len(m.matrices(range(m.n_layers))) == 560
+    assert shapes.MODELS["llama-2-7b"].total_weights() == 6_476_005_376
+    assert shapes.MODELS["opt-6.7b"].total_weights() == 6_442_450_944
+    assert shapes.MODELS["opt-125m"].total_weights() == 84_934_656
+    for n, ws in [(80, 8), (80, 3), (32, 5), (12, 8), (3, 8)]:
+        blocks = [shapes.partition_layers(n, ws, r) for r in range(ws)]
+        assert [x for b in blocks for x in b] == list(range(n))  # contiguous, disjoint, complete
+        assert max(len(b) for b in blocks) - min(len(b) for b in blocks) <= 1
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["IWQ_ROOT"])
+from iron_weight_only_quant_b200 import shapes, sharded
+from oracle import fakequant_oracle as O
+
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{os.environ['IWQ_PORT']}", rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+g = torch.Generator().manual_seed(7)
+mats = [(torch.randn(96, 256, generator=g) * (0.02 * (i + 1))).half() for i in range(5)]
+# this rank's row block of every matrix, its local {max, -min}
+rng = torch.empty(10, dtype=torch.float32)
+for i, w in enumerate(mats):
+    rows = shapes.split_rows(96, 2, rank)
+    shard = w[rows.start:rows.stop]
+    b = shard.contiguous().view(torch.int16).numpy().view(np.uint16)
+    mx, mn, _ = O.minmax_of(b, "f16")
+    rng[2 * i], rng[2 * i + 1] = float(mx), float(-mn)
+sharded.allreduce_ranges(rng)
+for i, w in enumerate(mats):
+    assert rng[2 * i].item() == w.float().max().item() and -rng[2 * i + 1].item() == w.float().min().item(), i
+# every rank now derives the same (scale, zero): quantising its shard with the global range equals the
+# matching rows of the unsharded result
+for i, w in enumerate(mats):
+    full = O.int_fake_quant(w.view(torch.int16).numpy().view(np.uint16), "f16", 4, True, -1)
+    s, z = O.int_ranges_to_qparams(np.float32(rng[2 * i].item()), np.float32(-rng[2 * i + 1].item()), 4, True, "f16")
+    rows = shapes.split_rows(96, 2, rank)
+    shard = O.from_bits(w[rows.start:rows.stop].contiguous().view(torch.int16).numpy().view(np.uint16), "f16")
+    out, _ = O.int_apply(shard, s, z, 4, True, "f16")
+    assert np.array_equal(O.to_bits(out, "f16"), full["out"][rows.start:rows.stop]), i
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_range_allreduce_world_size_2_gloo(built, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = 29500 + (os.getpid() % 1000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), IWQ_PORT=str(port), IWQ_ROOT=ROOT)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o

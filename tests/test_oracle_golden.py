@@ -157,3 +157,25 @@ def test_error_contract():
         O.int_fake_quant(w, "f16", 4, True, -3)  # quant_linear.py:906
     with pytest.raises(ValueError):
         O.fp_rne_fake_quant(w, 2, 1, 32)  # fp4_quantize_cpu.py:55-56
+
+
+def test_torch_cpu_port_matches_reference(golden):
+    """The eager-torch port that bench.py times as the CPU baseline gives the reference's bits."""
+    import torch
+
+    from oracle import torch_cpu_port as P
+
+    g = golden("golden_int")
+    for dtype, tdt in (("f16", torch.float16), ("bf16", torch.bfloat16)):
+        w = torch.from_numpy(g[f"w_{dtype}"].view(np.int16).copy()).view(tdt)
+        for bits, sym, grp in [(4, False, 128), (4, True, 64), (8, False, -2), (3, True, 32)]:
+            key = f"{dtype}_b{bits}_{'sym' if sym else 'asym'}_g{grp}"
+            o = P.int_fake_quant(w, bits, not sym, grp)
+            assert np.array_equal(o.view(torch.int16).numpy().view(np.uint16), g[f"fn_{key}"]), key
+    g = golden("golden_fp_chain")
+    w = torch.from_numpy(g["w_f16"].view(np.int16).copy()).view(torch.float16)
+    for fmt, (E, M) in (("e2m1", (2, 1)), ("e4m3", (4, 3))):
+        for sym in (False, True):
+            key = f"f16_{fmt}_{'sym' if sym else 'asym'}_g128"
+            o = P.fp_codec_fake_quant(w, E, M, sym, 128)
+            assert _nan_equal_bits(o.view(torch.int16).numpy().view(np.uint16), g[f"ql_{key}_out"], "f16"), key
