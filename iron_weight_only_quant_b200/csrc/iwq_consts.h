@@ -69,6 +69,8 @@ static inline int build_quant_consts(const iwq_config_t* cfg, QuantConsts* c, in
       *kind = span <= 64.0f ? KIND_INT_FAST : (span <= 256.0f ? KIND_INT_WIDE : KIND_INT_GENERIC);
     }
     if (getenv("IWQ_FORCE_GENERIC")) *kind = KIND_INT_GENERIC;
+    // max_int is a value of the 16-bit dtype on the packed paths (<= 255): exact reciprocal-multiply division
+    c->inv_div = (*kind == KIND_INT_GENERIC) ? 0.0f : 1.0f / c->max_int;
     return IWQ_OK;
   }
   if (cfg->scheme != IWQ_SCHEME_FP_CODEC && cfg->scheme != IWQ_SCHEME_FP_RNE) return fail(IWQ_ERR_INVALID, "unknown scheme");
@@ -85,6 +87,7 @@ static inline int build_quant_consts(const iwq_config_t* cfg, QuantConsts* c, in
   const double fmax = (2.0 - ldexp(1.0, -M)) * ldexp(1.0, emax);
   if (dt == IWQ_F16 && fmax > 65504.0) return fail(IWQ_ERR_FP16_RANGE, "value cannot be converted to type at::Half without overflow");
   c->fmax = (float)fmax;
+  c->inv_div = 1.0f / c->fmax;  // fmax = (2 - 2^-M) * 2^emax has <= 7 significant bits: a value of either dtype
   c->eps = round_to_dtype(dt, rne ? 1e-8f : 1e-5f);
   int elo = emin - M - 3;
   if (elo < 1 - DB) elo = 1 - DB;

@@ -282,6 +282,15 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
   LaunchTuning tune;
   tune.stages = p.n_stages;
   cudaError_t e;
+  // kernel variant: 0 = seg4 (TMA in + TMA out, 4 vectors per lane; needs group >= 32), 1 = direct global
+  // loads/stores, 2 = TMA in + register stores (one vector per lane-iteration; also serves group 8 / 16)
+  int variant = effective_variant(cfg);
+  if (variant < 0 || variant > 2) variant = 0;
+  if (variant == 0 && !per_tensor && pl.path == PATH_SEG && pl.seg_elems < 32) variant = 2;
+  if (variant == 0 && pl.path == PATH_SEG) {
+    p.lps = per_tensor ? 1 : (int)(pl.seg_elems / 32);
+    p.vpl = 1;
+  }
   if (per_tensor) {
     const float* rng = given_range;
     if (!rng) {
@@ -293,10 +302,10 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
     if (minmax_only) return IWQ_OK;
     p.ranges = rng;
     tune.ctas_per_sm = knobs().seg_ctas;
-    e = dispatch_seg(cfg->dtype, kind, p, sym, true, effective_variant(cfg), tune, st);
+    e = dispatch_seg(cfg->dtype, kind, p, sym, true, variant, tune, st);
   } else if (pl.path == PATH_SEG) {
     tune.ctas_per_sm = knobs().seg_ctas;
-    e = dispatch_seg(cfg->dtype, kind, p, sym, false, effective_variant(cfg), tune, st);
+    e = dispatch_seg(cfg->dtype, kind, p, sym, false, variant, tune, st);
   } else {
     tune.ctas_per_sm = knobs().row_ctas;
     e = dispatch_row(cfg->dtype, kind, p, sym, pl.consumers, tune, st);

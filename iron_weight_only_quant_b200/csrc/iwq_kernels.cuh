@@ -100,6 +100,22 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                : "memory");
 }
 
+// shared::cta -> global bulk store (SASS: UBLKCP), tracked by the thread's bulk async-group
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (TMA) before a bulk store reads them
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void sts128(void* p, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ uint4 lds128(const void* p) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
@@ -433,6 +449,133 @@ __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_c
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// seg4_tma_kernel (default for group >= 32 and for the per-tensor apply pass)
+//
+//   global --TMA bulk load--> shared stage --LDS.128--> registers --STS.128--> same stage --TMA bulk store--> global
+//
+// Each lane owns FOUR consecutive 16-byte vectors (32 elements) of its warp's 2 KB slice of the tile, so a
+// segment of `group` elements is held by group/32 lanes: the min/max reduction needs log2(group/32) shuffle
+// rounds and the scale / zero-point arithmetic is done once per 32 elements instead of once per 8.
+// Lane L touches its vectors in the rotated order (k + L/2) mod 4, which makes every LDS.128 / STS.128
+// quarter-warp hit 8 distinct 16-byte bank groups (conflict-free) although lanes are 64 bytes apart.
+// Results go back into the lane's own 64 bytes of the stage; one elected lane per warp issues a 2 KB bulk
+// store, and hands the stage back to the producer once the PREVIOUS tile's store has finished reading
+// shared memory (cp.async.bulk.wait_group.read 1), so the store latency is never exposed.
+// No per-element global store instructions, no per-vector address arithmetic.
+// ------------------------------------------------------------------------------------------------
+template <int DT, int KIND, bool SYM, bool GIVEN>
+__global__ void __launch_bounds__(kConsumers + 32) seg4_tma_kernel(const __grid_constant__ LaunchParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + kMaxStages;
+  TileCtx* ctx = reinterpret_cast<TileCtx*>(smem + 128);
+  FpEntry* s_tbl = reinterpret_cast<FpEntry*>(smem + 640);
+  uint8_t* data = smem + kSmemHeader;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_stages = p.n_stages;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kConsumerWarps);
+    }
+    fence_mbar_init();
+  }
+  if (KIND == KIND_FP) load_fp_table(p, s_tbl);
+  __syncthreads();
+
+  if (warp == kConsumerWarps) {
+    if (lane == 0) {
+      int stage = 0, cur = -1;
+      uint32_t phase = 0;
+      Job jb;
+      for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        advance_job(p, tile, &cur, &jb);
+        const TileCtx t = make_tile_ctx(p, jb, cur, tile, GIVEN);
+        ctx[stage] = t;
+        const uint32_t bytes = t.n_vec * 16u;
+        mbar_arrive_expect_tx(&full[stage], bytes);
+        tma_load_1d(data + (size_t)stage * kTileBytes, jb.src + (t.vec0 << 4), bytes, &full[stage]);
+        if (++stage == n_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const int lps = p.lps;                      // lanes per segment = group / 32 (1..32); unused when GIVEN
+  const uint32_t lane_vec = (uint32_t)warp * 128u + (uint32_t)lane * 4u;  // first vector of this lane in the tile
+  const uint32_t rot = (uint32_t)lane >> 1;
+  int stage = 0, prev_stage = -1;
+  uint32_t phase = 0;
+  for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+    mbar_wait(&full[stage], phase);
+    const TileCtx t = ctx[stage];
+    uint8_t* lbase = data + (size_t)stage * kTileBytes + (size_t)lane_vec * 16;
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t j = (k + rot) & 3u;
+      v[k] = (lane_vec + j < t.n_vec) ? lds128(lbase + j * 16) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    Prepared<DT, KIND> prep;
+    if (GIVEN) {
+      prep.setup(t.given_mx, t.given_mn, p.qc);
+    } else {
+      uint32_t pk = range_max<DT>(range_max<DT>(vec_range<DT, SYM>(v[0]), vec_range<DT, SYM>(v[1])),
+                                  range_max<DT>(vec_range<DT, SYM>(v[2]), vec_range<DT, SYM>(v[3])));
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        if (o < lps) pk = range_max<DT>(pk, __shfl_xor_sync(0xFFFFFFFFu, pk, o));
+      }
+      float mx, mn;
+      range_unpack<DT>(pk, &mx, &mn);
+      prep.setup(mx, mn, p.qc);
+    }
+    const bool want_codes = t.codes != nullptr;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t j = (k + rot) & 3u;
+      uint2 codes8;
+      const uint4 o = prep.apply(v[k], p.qc, s_tbl, want_codes, &codes8);
+      sts128(lbase + j * 16, o);
+      if (want_codes && lane_vec + j < t.n_vec) *reinterpret_cast<uint2*>(t.codes + (t.vec0 + lane_vec + j) * 8) = codes8;
+    }
+    if (lane_vec < t.n_vec) {
+      const bool owner = GIVEN ? (t.vec0 + lane_vec == 0) : ((lane & (lps - 1)) == 0);
+      if (owner) {
+        const uint64_t g = GIVEN ? 0 : (t.vec0 + lane_vec) / (uint32_t)(4 * lps);
+        if (t.scales) reinterpret_cast<uint16_t*>(t.scales)[g] = DType<DT>::from_f32(prep.scale);
+        if (t.zeros) reinterpret_cast<uint16_t*>(t.zeros)[g] = DType<DT>::from_f32(prep.zero);
+      }
+      if (prep.bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t w0 = (uint32_t)warp * 128u;
+      if (w0 < t.n_vec) {
+        const uint32_t nv = t.n_vec - w0 < 128u ? t.n_vec - w0 : 128u;
+        tma_store_1d(t.dst + (size_t)w0 * 16, data + (size_t)stage * kTileBytes + (size_t)w0 * 16, nv * 16u);
+      }
+      tma_store_commit();
+      tma_store_wait_read<1>();                       // the previous tile's store no longer reads its stage
+      if (prev_stage >= 0) mbar_arrive(&empty[prev_stage]);
+    }
+    prev_stage = stage;
+    if (++stage == n_stages) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+  if (lane == 0) tma_store_wait_all();  // all bulk stores complete (and visible) before the CTA retires
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -32,9 +32,12 @@ inline cudaError_t persistent_grid(Kernel kernel, int threads, size_t smem, int 
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
     if (it == cache.end()) {
-      // opt in to the full 227 KB once per kernel (a later, smaller value would lower the limit again)
-      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) return e;
+      // kernels with a dynamic ring opt in to the full 227 KB once (a later, smaller value would lower the
+      // limit again); kernels without dynamic shared memory must not be touched (static smem + 227 KB > limit)
+      if (smem > 0) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+      }
       int occ = 0, sms = 0;
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
       if (e != cudaSuccess) return e;
@@ -72,6 +75,12 @@ static cudaError_t launch_seg_one(LaunchParams p, int variant, const LaunchTunin
     cudaError_t e = persistent_grid(k, kConsumers, 0, tune.ctas_per_sm, p.total_units, &grid);
     if (e != cudaSuccess) return e;
     k<<<grid, kConsumers, 0, st>>>(p);
+  } else if (variant == 0) {
+    auto k = seg4_tma_kernel<DT, KIND, SYM, GIVEN>;
+    const size_t smem = kSmemHeader + (size_t)p.n_stages * kTileBytes;
+    cudaError_t e = persistent_grid(k, kConsumers + 32, smem, tune.ctas_per_sm, p.total_units, &grid);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kConsumers + 32, smem, st>>>(p);
   } else {
     auto k = seg_tma_kernel<DT, KIND, SYM, GIVEN>;
     const size_t smem = kSmemHeader + (size_t)p.n_stages * kTileBytes;

@@ -89,9 +89,26 @@ IWQ_HD float rD(float x) {
   return DType<DT>::to_f32(DType<DT>::from_f32(x));
 }
 
-// torch.clamp semantics: NaN propagates
-IWQ_HD float clamp_min_nan(float x, float lo) { return (x != x) ? x : fmaxf(x, lo); }
-IWQ_HD float clamp_nan(float x, float lo, float hi) { return (x != x) ? x : fminf(fmaxf(x, lo), hi); }
+// torch.clamp semantics: NaN propagates (one FMNMX.NAN each on the device)
+IWQ_HD float clamp_min_nan(float x, float lo) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(lo));
+  return r;
+#else
+  return (x != x) ? x : fmaxf(x, lo);
+#endif
+}
+IWQ_HD float clamp_nan(float x, float lo, float hi) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(lo));
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(r), "f"(hi));
+  return r;
+#else
+  return (x != x) ? x : fminf(fmaxf(x, lo), hi);
+#endif
+}
 
 IWQ_HD float ieee_div(float a, float b) {
 #ifdef __CUDA_ARCH__
@@ -172,6 +189,7 @@ struct FpEntry {      // one per binade of the clamped magnitude |n|
 struct QuantConsts {
   int32_t scheme, bits, exp_bits, mant_bits, symmetric, flavour_rne;
   float min_int, max_int;  // INT: clamp bounds (quant_funcs.py:19-20, :26-27)
+  float inv_div;           // fl32(1 / max_int) resp. fl32(1 / fmax), or 0: the divisor is not a 16-bit value -> IEEE division
   float eps;               // rD(1e-5) (quant_funcs.py:21,25) or rD(1e-8) (fp4_quantize_cpu.py:68)
   float fmax;              // FP: largest minifloat magnitude (quant_linear.py:741 / fp4_quantize_cpu.py:64)
   uint16_t fmax_bits;      // fmax as D bits
@@ -193,30 +211,40 @@ struct IntQ {
   bool slow_div;   // bf16 only: |w|/s can overflow fp32, use IEEE division for this segment
 };
 
+// x / c for a launch-constant divisor c (max_int or fmax).  When c is itself a value of the 16-bit dtype
+// the reciprocal+FMA quotient is exact after rounding to D (same proof as fast_quot); otherwise IEEE.
+IWQ_HD float div_const(float x, float c, float inv_c) {
+  // (an infinite or NaN numerator takes the IEEE path so that inf / c stays inf)
+  return (inv_c != 0.0f && fabsf(x) < INFINITY) ? fast_quot(x, c, inv_c) : ieee_div(x, c);
+}
+
 // mx = max (asym) or absmax (sym); mn = min (asym), ignored for sym.  D values held in fp32.
 template <int DT>
 IWQ_HD IntQ int_segment_params(float mx, float mn, const QuantConsts& c) {
   IntQ q;
+  float d;
   if (c.symmetric) {
-    float d = rD<DT>(clamp_min_nan(mx, c.eps));           // absmax.clamp(min=1e-5)            :25
-    q.s = rD<DT>(ieee_div(d, c.max_int));                 // / max_int                          :28
-    q.z = 0.0f;                                           // zeros = 0                          :29
+    d = rD<DT>(clamp_min_nan(mx, c.eps));                 // absmax.clamp(min=1e-5)            :25
   } else {
-    float d = rD<DT>(mx - mn);                            // max_val - min_val                  :21
+    d = rD<DT>(mx - mn);                                  // max_val - min_val                  :21
     d = rD<DT>(clamp_min_nan(d, c.eps));                  // .clamp(min=1e-5)                   :21
-    q.s = rD<DT>(ieee_div(d, c.max_int));                 // / max_int                          :21
-    float zq = rD<DT>(ieee_div(mn, q.s));                 // min_val / scales                   :22
-    q.z = clamp_nan(-rintf(zq), c.min_int, c.max_int);    // (-round(.)).clamp_(min_int,max_int):22
   }
+  q.s = rD<DT>(div_const(d, c.max_int, c.inv_div));       // / max_int                          :21 / :28
   q.r = ieee_rcp(q.s);
-  q.lo = c.min_int - q.z;
-  q.hi = c.max_int - q.z;
   q.bad = !(q.s > 0.0f && q.s < INFINITY);
   q.slow_div = false;
   if (DT == IWQ_BF16) {
     float big = fmaxf(fabsf(mx), c.symmetric ? 0.0f : fabsf(mn));
     q.slow_div = !(big * q.r < 1e37f);
   }
+  if (c.symmetric) {
+    q.z = 0.0f;                                           // zeros = 0                          :29
+  } else {
+    float zq = rD<DT>((q.slow_div || c.inv_div == 0.0f) ? ieee_div(mn, q.s) : fast_quot(mn, q.s, q.r));  // min_val / scales  :22
+    q.z = clamp_nan(-rintf(zq), c.min_int, c.max_int);    // (-round(.)).clamp_(min_int,max_int):22
+  }
+  q.lo = c.min_int - q.z;
+  q.hi = c.max_int - q.z;
   return q;
 }
 
@@ -309,15 +337,15 @@ IWQ_HD FpQ fp_segment_params(float mx, float mn, const QuantConsts& c) {
   q.mid_h = 0.0f;
   if (c.flavour_rne) {
     float d = rD<DT>(clamp_min_nan(mx, c.eps));                    // absmax.clamp(min=1e-8)   fp4_quantize_cpu.py:68
-    q.S = rD<DT>(ieee_div(d, c.fmax));                             // / max_float              :69
+    q.S = rD<DT>(div_const(d, c.fmax, c.inv_div));                // / max_float              :69
   } else if (c.symmetric) {
     float d = rD<DT>(clamp_min_nan(mx, c.eps));                    // absmax.clamp(min=1e-5)   quant_linear.py:744
-    q.S = rD<DT>(clamp_min_nan(rD<DT>(ieee_div(d, c.fmax)), c.eps));  // (/ fmax).clamp(1e-5)  :745
+    q.S = rD<DT>(clamp_min_nan(rD<DT>(div_const(d, c.fmax, c.inv_div)), c.eps));  // (/ fmax).clamp(1e-5)  :745
   } else {
     q.mid = rD<DT>(rD<DT>(mx + mn) * 0.5f);                        // (max + min) * 0.5        :751
     float span = rD<DT>(rD<DT>(mx - mn) * 0.5f);                   // (max - min) * 0.5        :752
     span = rD<DT>(clamp_min_nan(span, c.eps));                     // .clamp(min=1e-5)         :752
-    q.S = rD<DT>(clamp_min_nan(rD<DT>(ieee_div(span, c.fmax)), c.eps));  //                    :753
+    q.S = rD<DT>(clamp_min_nan(rD<DT>(div_const(span, c.fmax, c.inv_div)), c.eps));  //          :753
     q.mid_h = rD<DT>(DType<IWQ_F16>::to_f32(DType<IWQ_F16>::from_f32(q.mid)));  // zeros.half().to(D) :765,:776
   }
   q.r = ieee_rcp(q.S);

@@ -203,9 +203,10 @@ def run_int(w, nb, sym, grp, variant=0, want_codes=True):
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_int_vs_oracle_all_outputs(dt, variant):
-    """output, scales, zero points AND integer codes, both kernel variants (TMA-staged / direct loads)."""
+    """output, scales, zero points AND integer codes, all kernel variants (0: TMA in + TMA out, 4 vectors per
+    lane; 1: direct global loads/stores; 2: TMA in + register stores)."""
     w = seeded(512, 2048, dt, 11)
     wb = bits(w)
     wd = w.to(DEV)
@@ -430,9 +431,10 @@ def test_full_size_properties(shape):
     w = (torch.randn(rows, cols, generator=g, device=DEV) * 0.02).half()
     cfg = dict(n_bits=4, zero_point=True, q_group_size=128)
     out = quant_funcs.pseudo_quantize_tensor(w, **cfg)
-    # (1) TMA-staged and direct-load variants agree bit for bit; in-place equals out-of-place
-    o2, _, _, _ = run_int(w, 4, False, 128, variant=1, want_codes=False)
-    assert torch.equal(out.view(torch.int16), o2.view(torch.int16))
+    # (1) the three kernel variants agree bit for bit; in-place equals out-of-place
+    for v in (1, 2):
+        o2, _, _, _ = run_int(w, 4, False, 128, variant=v, want_codes=False)
+        assert torch.equal(out.view(torch.int16), o2.view(torch.int16)), v
     t = w.clone()
     quant_funcs.pseudo_quantize_tensor(t, inplace=True, **cfg)
     assert torch.equal(out.view(torch.int16), t.view(torch.int16))
