@@ -260,13 +260,16 @@ def run_ours(args):
                 _lib.check(rc)
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    if args.skip_e2e:
+        e2e_steps, e2e_s = 0, float("inf")
+    else:
         e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -281,10 +284,10 @@ def run_ours(args):
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("seg_tma_kernel_bytes_per_launch")
+                traffic = json.load(open(tp)).get("bench_kernel_dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        cb = cpu_sample(steps=40, warmup=1, seconds_cap=15.0) if world == 1 else None
+        cb = cpu_sample(steps=40, warmup=1, seconds_cap=15.0) if (world == 1 and not args.skip_cpu) else None
         line = {
             "metric": METRIC,
             "value": value,
@@ -309,7 +312,7 @@ def run_ours(args):
             "pct_of_8TBps": 100.0 * value / (8000.0 * world),
             "weights_per_s": n_weights * world / (ms_per_step * 1e-3),
             "llama2_70b_full_model_ms": ms_per_step * (8.0 / world),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel": "seg_tma_kernel<f16,INT_FAST,asym>", "bytes_per_launch": nbytes, "kernel_ms": kernel_ms},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel": "seg4_tma_kernel<f16,INT_FAST,asym>", "bytes_per_launch": nbytes, "kernel_ms": kernel_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_weights * 2, "d2h_bytes_per_step": n_weights * 2, "steps": e2e_steps, "api": "iwq_fake_quant_host (pinned host buffers, 3-deep H2D/kernel/D2H ring)"},
             "gpu_launches": args.steps,
             "clocks": clocks,
@@ -331,6 +334,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-chunk-mb", type=int, default=64)
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave out the host-buffer leg")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: leave out the CPU baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -800,7 +800,7 @@ __global__ void fp_roundtrip_kernel(const uint32_t* __restrict__ x, uint32_t* __
   FpTable<DT> f;
   f.setup(q, qc);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_pairs; i += (int64_t)gridDim.x * blockDim.x) {
-    T2 v = f.grid(from_u32<T2>(x[i]), s_tbl);
+    T2 v = f.grid(from_u32<T2>(x[i]), x[i], s_tbl);
     uint32_t vb = as_u32(v);
     y[i] = vb;
     if (codes) {

@@ -388,8 +388,10 @@ struct FpTable {
     tbl_off = c.tbl_base;
   }
 
-  // quantise an already-normalised pair n2 (D values) onto the minifloat grid; sign handled here
-  IWQ_HD T2 grid(T2 n2, const FpEntry* tbl) const {
+  // quantise an already-normalised pair n2 (D values) onto the minifloat grid; sign handled here.
+  // `sign_src`: bits whose sign the RNE flavour keeps -- the un-normalised input, because the
+  // reciprocal+FMA quotient turns -0.0 into +0.0 (the scale is never negative, so sign(w) == sign(w/S))
+  IWQ_HD T2 grid(T2 n2, uint32_t sign_src, const FpEntry* tbl) const {
     constexpr int MB = D::kMantBits;
     const uint32_t nb = as_u32(n2);
     T2 a = from_u32<T2>(nb & 0x7FFF7FFFu);
@@ -408,7 +410,7 @@ struct FpTable {
     v = __hmin2(v, from_u32<T2>(bound));
     const uint32_t bump = __hge2_mask(a, from_u32<T2>(thr));
     uint32_t vb = (as_u32(v) & ~bump) | (bval & bump);
-    const uint32_t sgn = rne ? (nb & 0x80008000u) : (__hlt2_mask(n2, from_u32<T2>(0u)) & 0x80008000u);
+    const uint32_t sgn = rne ? (sign_src & 0x80008000u) : (__hlt2_mask(n2, from_u32<T2>(0u)) & 0x80008000u);
     return from_u32<T2>(vb | sgn);
   }
 
@@ -416,7 +418,7 @@ struct FpTable {
     T2 w = from_u32<T2>(w2);
     if (asym) w = __hsub2(w, mid2);                                   // weight - zeros            :755
     T2 n = slow_div ? ieee_quot2<DT>(w, S) : fast_quot2<DT>(w, S, r); // / scales
-    T2 v = grid(n, tbl);
+    T2 v = grid(n, w2, tbl);
     // a NaN quotient (only possible when S is 0/inf/NaN, i.e. slow_div) must stay NaN: grid() clamped it
     if (slow_div) v = from_u32<T2>(as_u32(v) | __hneu2_mask(n, n));
     *v2 = v;

@@ -28,7 +28,7 @@ static void seg_range(const uint16_t* w, int64_t n, bool sym, float* mx, float* 
   }
   if (nan) a = b = NAN;
   *mx = a;
-  *mn = b;
+  *mn = sym ? -a : b;  // the kernels unpack {absmax, -absmax} for symmetric ranges
 }
 
 template <int DT>
@@ -107,7 +107,7 @@ static void roundtrip(const QuantConsts& c, const uint16_t* x, uint16_t* y, int6
   f.setup(q, c);
   for (int64_t i = 0; i < n; i += 2) {
     uint32_t x2 = (uint32_t)x[i] | ((uint32_t)x[i + 1] << 16);
-    uint32_t o = as_u32(f.grid(from_u32<T2>(x2), c.tbl));
+    uint32_t o = as_u32(f.grid(from_u32<T2>(x2), x2, c.tbl));
     y[i] = (uint16_t)(o & 0xFFFF);
     y[i + 1] = (uint16_t)(o >> 16);
   }
