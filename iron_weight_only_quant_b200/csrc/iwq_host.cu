@@ -35,7 +35,7 @@ static int env_int(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 struct Knobs {
-  int seg_stages = env_int("IWQ_SEG_STAGES", 6);
+  int seg_stages = env_int("IWQ_SEG_STAGES", 3);
   int seg_ctas = env_int("IWQ_SEG_CTAS", 0);
   int row_ctas = env_int("IWQ_ROW_CTAS", 0);
   int row_smem_kb = env_int("IWQ_ROW_SMEM_KB", 0);  // per-CTA ring budget; 0 = automatic

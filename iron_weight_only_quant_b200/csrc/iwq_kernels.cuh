@@ -80,12 +80,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint
+// expires) instead of burning issue slots in a software spin (ncu showed ~30 spins per tile without it)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
@@ -184,8 +186,8 @@ struct PreparedInt {  // KIND_INT_FAST / KIND_INT_WIDE
   IntFast<DT, KIND == KIND_INT_WIDE> f;
   float scale, zero;
   bool bad;
-  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c) {
-    IntQ q = int_segment_params<DT>(mx, mn, c);
+  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c, bool sym) {
+    IntQ q = int_segment_params<DT>(mx, mn, c, sym);
     f.setup(q);
     scale = q.s;
     zero = q.z;
@@ -221,8 +223,8 @@ struct Prepared<DT, KIND_INT_GENERIC> {
   IntQ q;
   float scale, zero;
   bool bad;
-  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c) {
-    q = int_segment_params<DT>(mx, mn, c);
+  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c, bool sym) {
+    q = int_segment_params<DT>(mx, mn, c, sym);
     scale = q.s;
     zero = q.z;
     bad = q.bad;
@@ -250,7 +252,7 @@ struct Prepared<DT, KIND_FP> {
   FpTable<DT> f;
   float scale, zero;
   bool bad;
-  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c) {
+  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c, bool /*sym*/) {
     FpQ q = fp_segment_params<DT>(mx, mn, c);
     f.setup(q, c);
     scale = q.S;
@@ -350,14 +352,14 @@ __device__ __forceinline__ void consume_tile(uint4 (&v)[kVPT], const TileCtx& t,
   const bool want_codes = t.codes != nullptr;
   bool any_bad = false;
   Prepared<DT, KIND> prep;
-  if (GIVEN) prep.setup(t.given_mx, t.given_mn, p.qc);
+  if (GIVEN) prep.setup(t.given_mx, t.given_mn, p.qc, SYM);
 #pragma unroll
   for (int it = 0; it < kVPT; ++it) {
     const uint32_t idx = (uint32_t)warp * (32 * kVPT) + it * 32 + lane;
     if (!GIVEN && (it & (vpl - 1)) == 0) {  // its of one segment share the parameters
       float mx, mn;
       range_unpack<DT>(pk[it], &mx, &mn);
-      prep.setup(mx, mn, p.qc);
+      prep.setup(mx, mn, p.qc, SYM);
     }
     uint2 codes8;
     const uint4 o = prep.apply(v[it], p.qc, tbl, want_codes, &codes8);
@@ -466,6 +468,51 @@ __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_c
 // shared memory (cp.async.bulk.wait_group.read 1), so the store latency is never exposed.
 // No per-element global store instructions, no per-vector address arithmetic.
 // ------------------------------------------------------------------------------------------------
+// One lane's share of a tile in seg4_tma_kernel: four vectors through registers, results back to the stage.
+// FAST = full 16 KB tile and no code emission: no per-vector predicates at all.
+template <int DT, int KIND, bool SYM, bool GIVEN, bool FAST>
+__device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParams& p, const FpEntry* s_tbl, uint8_t* lbase, uint32_t lane_vec,
+                                             uint32_t rot, int lane, int lps) {
+  uint4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t j = (k + rot) & 3u;
+    v[k] = (FAST || lane_vec + j < t.n_vec) ? lds128(lbase + j * 16) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  Prepared<DT, KIND> prep;
+  if (GIVEN) {
+    prep.setup(t.given_mx, t.given_mn, p.qc, SYM);
+  } else {
+    uint32_t pk = range_max<DT>(range_max<DT>(vec_range<DT, SYM>(v[0]), vec_range<DT, SYM>(v[1])),
+                                range_max<DT>(vec_range<DT, SYM>(v[2]), vec_range<DT, SYM>(v[3])));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      if (o < lps) pk = range_max<DT>(pk, __shfl_xor_sync(0xFFFFFFFFu, pk, o));
+    }
+    float mx, mn;
+    range_unpack<DT>(pk, &mx, &mn);
+    prep.setup(mx, mn, p.qc, SYM);
+  }
+  const bool want_codes = !FAST && t.codes != nullptr;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t j = (k + rot) & 3u;
+    uint2 codes8;
+    const uint4 o = prep.apply(v[k], p.qc, s_tbl, want_codes, &codes8);
+    sts128(lbase + j * 16, o);
+    if (want_codes && lane_vec + j < t.n_vec) *reinterpret_cast<uint2*>(t.codes + (t.vec0 + lane_vec + j) * 8) = codes8;
+  }
+  if (FAST || lane_vec < t.n_vec) {
+    const bool owner = GIVEN ? (t.vec0 + lane_vec == 0) : ((lane & (lps - 1)) == 0);
+    if (owner) {
+      const uint64_t g = GIVEN ? 0 : (t.vec0 + lane_vec) / (uint32_t)(4 * lps);
+      if (t.scales) reinterpret_cast<uint16_t*>(t.scales)[g] = DType<DT>::from_f32(prep.scale);
+      if (t.zeros) reinterpret_cast<uint16_t*>(t.zeros)[g] = DType<DT>::from_f32(prep.zero);
+    }
+    if (prep.bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
+  }
+}
+
 template <int DT, int KIND, bool SYM, bool GIVEN>
 __global__ void __launch_bounds__(kConsumers + 32) seg4_tma_kernel(const __grid_constant__ LaunchParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -519,44 +566,10 @@ __global__ void __launch_bounds__(kConsumers + 32) seg4_tma_kernel(const __grid_
     mbar_wait(&full[stage], phase);
     const TileCtx t = ctx[stage];
     uint8_t* lbase = data + (size_t)stage * kTileBytes + (size_t)lane_vec * 16;
-    uint4 v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t j = (k + rot) & 3u;
-      v[k] = (lane_vec + j < t.n_vec) ? lds128(lbase + j * 16) : make_uint4(0u, 0u, 0u, 0u);
-    }
-    Prepared<DT, KIND> prep;
-    if (GIVEN) {
-      prep.setup(t.given_mx, t.given_mn, p.qc);
-    } else {
-      uint32_t pk = range_max<DT>(range_max<DT>(vec_range<DT, SYM>(v[0]), vec_range<DT, SYM>(v[1])),
-                                  range_max<DT>(vec_range<DT, SYM>(v[2]), vec_range<DT, SYM>(v[3])));
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        if (o < lps) pk = range_max<DT>(pk, __shfl_xor_sync(0xFFFFFFFFu, pk, o));
-      }
-      float mx, mn;
-      range_unpack<DT>(pk, &mx, &mn);
-      prep.setup(mx, mn, p.qc);
-    }
-    const bool want_codes = t.codes != nullptr;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t j = (k + rot) & 3u;
-      uint2 codes8;
-      const uint4 o = prep.apply(v[k], p.qc, s_tbl, want_codes, &codes8);
-      sts128(lbase + j * 16, o);
-      if (want_codes && lane_vec + j < t.n_vec) *reinterpret_cast<uint2*>(t.codes + (t.vec0 + lane_vec + j) * 8) = codes8;
-    }
-    if (lane_vec < t.n_vec) {
-      const bool owner = GIVEN ? (t.vec0 + lane_vec == 0) : ((lane & (lps - 1)) == 0);
-      if (owner) {
-        const uint64_t g = GIVEN ? 0 : (t.vec0 + lane_vec) / (uint32_t)(4 * lps);
-        if (t.scales) reinterpret_cast<uint16_t*>(t.scales)[g] = DType<DT>::from_f32(prep.scale);
-        if (t.zeros) reinterpret_cast<uint16_t*>(t.zeros)[g] = DType<DT>::from_f32(prep.zero);
-      }
-      if (prep.bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
-    }
+    if (t.n_vec == (uint32_t)(kTileBytes / 16) && t.codes == nullptr)
+      seg4_consume<DT, KIND, SYM, GIVEN, true>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps);
+    else
+      seg4_consume<DT, KIND, SYM, GIVEN, false>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps);
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -693,7 +706,7 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
       // sweep 2: quantise from shared memory, store to global
       const bool want_codes = t.codes != nullptr;
       Prepared<DT, KIND> prep;
-      prep.setup(mx, mn, p.qc);
+      prep.setup(mx, mn, p.qc, SYM);
       for (uint32_t i = tid; i < t.n_vec; i += n_cons) {
         uint2 codes8;
         const uint4 o = prep.apply(lds128(sdata + (size_t)i * 16), p.qc, s_tbl, want_codes, &codes8);

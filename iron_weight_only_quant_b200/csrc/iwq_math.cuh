@@ -219,11 +219,12 @@ IWQ_HD float div_const(float x, float c, float inv_c) {
 }
 
 // mx = max (asym) or absmax (sym); mn = min (asym), ignored for sym.  D values held in fp32.
+// `sym` duplicates c.symmetric so that kernels can pass their template constant (the branch folds away).
 template <int DT>
-IWQ_HD IntQ int_segment_params(float mx, float mn, const QuantConsts& c) {
+IWQ_HD IntQ int_segment_params(float mx, float mn, const QuantConsts& c, bool sym) {
   IntQ q;
   float d;
-  if (c.symmetric) {
+  if (sym) {
     d = rD<DT>(clamp_min_nan(mx, c.eps));                 // absmax.clamp(min=1e-5)            :25
   } else {
     d = rD<DT>(mx - mn);                                  // max_val - min_val                  :21
@@ -234,10 +235,10 @@ IWQ_HD IntQ int_segment_params(float mx, float mn, const QuantConsts& c) {
   q.bad = !(q.s > 0.0f && q.s < INFINITY);
   q.slow_div = false;
   if (DT == IWQ_BF16) {
-    float big = fmaxf(fabsf(mx), c.symmetric ? 0.0f : fabsf(mn));
+    float big = fmaxf(fabsf(mx), sym ? 0.0f : fabsf(mn));
     q.slow_div = !(big * q.r < 1e37f);
   }
-  if (c.symmetric) {
+  if (sym) {
     q.z = 0.0f;                                           // zeros = 0                          :29
   } else {
     float zq = rD<DT>((q.slow_div || c.inv_div == 0.0f) ? ieee_div(mn, q.s) : fast_quot(mn, q.s, q.r));  // min_val / scales  :22

@@ -58,7 +58,7 @@ static int run(const iwq_config_t* cfg, const QuantConsts& c, int kind, const ui
       sc = q.S;
       zp = q.mid;
     } else {
-      IntQ q = int_segment_params<DT>(mx, mn, c);
+      IntQ q = int_segment_params<DT>(mx, mn, c, sym);
       if (kind == KIND_INT_GENERIC) {
         for (int64_t i = 0; i < seg; ++i) {
           float code;
