@@ -333,7 +333,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-chunk-mb", type=int, default=64)
+    ap.add_argument("--e2e-chunk-mb", type=int, default=32)
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave out the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: leave out the CPU baseline leg")
     args = ap.parse_args()
