@@ -126,7 +126,13 @@ static inline int build_quant_consts(const iwq_config_t* cfg, QuantConsts* c, in
   c->tbl_base = elo + DB;
   c->tbl_n = n;
   c->tiny_bits = (uint16_t)((elo + DB) << MB);
+  {
+    int llo = emin - M - 1;  // 2^(emin-M-1) is half the smallest step: it and everything below rounds to 0
+    if (llo + DB < 1) llo = 1 - DB;
+    c->lut_lo_bits = (uint16_t)((llo + DB) << MB);
+  }
   c->fmax_bits = (uint16_t)(((emax + DB) << MB) | (((1 << M) - 1) << (MB - M)));
+  c->lut_n = (uint32_t)c->fmax_bits - (uint32_t)c->lut_lo_bits + 1u;
   *kind = KIND_FP;
   return IWQ_OK;
 }

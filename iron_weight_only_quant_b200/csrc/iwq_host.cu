@@ -7,8 +7,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "iwq_consts.h"
@@ -50,6 +52,43 @@ static int build_consts(const iwq_config_t* cfg, QuantConsts* c, int* kind) {
   std::string msg;
   int rc = build_quant_consts(cfg, c, kind, &msg);
   if (rc) return fail(rc, msg);
+  return IWQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// minifloat LUT cache: one small device buffer per (device, dtype, E, M, flavour), built on first use
+// ------------------------------------------------------------------------------------------------
+static std::mutex g_lut_mu;
+static std::map<std::tuple<int, int, int, int, int>, uint16_t*> g_luts;
+
+static int get_fp_lut(const iwq_config_t* cfg, const QuantConsts& qc, cudaStream_t st, const uint16_t** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
+  auto key = std::make_tuple(dev, cfg->dtype, cfg->exp_bits, cfg->mant_bits, qc.flavour_rne);
+  std::lock_guard<std::mutex> lk(g_lut_mu);
+  auto it = g_luts.find(key);
+  if (it != g_luts.end()) {
+    *out = it->second;
+    return IWQ_OK;
+  }
+  uint16_t* buf = nullptr;
+  const size_t bytes = ((size_t)qc.lut_n * 2 + 1023) & ~(size_t)1023;
+  e = cudaMalloc((void**)&buf, bytes);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(minifloat LUT)");
+  const int grid = (int)((qc.lut_n + 255) / 256);
+  if (cfg->dtype == IWQ_F16)
+    fp_lut_kernel<IWQ_F16><<<grid, 256, 0, st>>>(buf, qc);
+  else
+    fp_lut_kernel<IWQ_BF16><<<grid, 256, 0, st>>>(buf, qc);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // one-time: later calls may come on any stream
+  if (e != cudaSuccess) {
+    cudaFree(buf);
+    return fail_cuda(e, "minifloat LUT build");
+  }
+  g_luts[key] = buf;
+  *out = buf;
   return IWQ_OK;
 }
 
@@ -124,7 +163,7 @@ static int check_matrix(const iwq_matrix_t* m) {
 }
 
 // decide the kernel path for one (cfg.group, cols); all matrices of a batched call must agree
-static int make_plan(const iwq_config_t* cfg, int64_t cols, Plan* pl) {
+static int make_plan(const iwq_config_t* cfg, int64_t cols, uint32_t lut_bytes, Plan* pl) {
   const int g = cfg->group;
   uint64_t seg;
   if (g > 0) {
@@ -152,7 +191,7 @@ static int make_plan(const iwq_config_t* cfg, int64_t cols, Plan* pl) {
   if (seg % 8 != 0) return fail(IWQ_ERR_UNSUPPORTED, "segment length must be a multiple of 8 elements (16-byte vectors)");
   const uint64_t row_bytes = seg * 2;
   const uint32_t stage = (uint32_t)((row_bytes + 127) & ~127ull);
-  const uint64_t max_ring = 200 * 1024;
+  const uint64_t max_ring = 200 * 1024 - (uint64_t)lut_bytes;
   if (2ull * stage > max_ring) return fail(IWQ_ERR_UNSUPPORTED, "row longer than 51200 elements: not implemented for per-channel granularity");
   pl->path = PATH_ROW;
   pl->stage_bytes = stage;
@@ -160,6 +199,7 @@ static int make_plan(const iwq_config_t* cfg, int64_t cols, Plan* pl) {
   pl->consumers = vecs >= 2048 ? 512 : (vecs >= 384 ? 256 : (vecs >= 96 ? 128 : 64));
   // ring budget per CTA: aim for >= 3 CTAs per SM on short rows, 2 on long ones
   uint64_t budget = knobs().row_smem_kb > 0 ? (uint64_t)knobs().row_smem_kb * 1024 : (stage <= 24 * 1024 ? 64 * 1024 : 100 * 1024);
+  if (budget > max_ring) budget = max_ring;
   int st = (int)(budget / stage);
   if (st < 2) st = 2;
   if (st > kMaxStages) st = kMaxStages;
@@ -261,12 +301,17 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
   int kind = 0;
   int rc = build_consts(cfg, &p.qc, &kind);
   if (rc) return rc;
+  if (kind == KIND_FP) {
+    rc = get_fp_lut(cfg, p.qc, st, &p.lut);
+    if (rc) return rc;
+    p.lut_smem_bytes = (uint32_t)(((size_t)p.qc.lut_n * 2 + 1023) & ~(size_t)1023);
+  }
   Plan pl;
-  rc = make_plan(cfg, ms[0].cols, &pl);
+  rc = make_plan(cfg, ms[0].cols, p.lut_smem_bytes, &pl);
   if (rc) return rc;
   for (int i = 1; i < n; ++i) {
     Plan pi;
-    rc = make_plan(cfg, ms[i].cols, &pi);
+    rc = make_plan(cfg, ms[i].cols, p.lut_smem_bytes, &pi);
     if (rc) return rc;
     if (pi.path != pl.path || pi.lps != pl.lps || pi.vpl != pl.vpl || pi.stage_bytes != pl.stage_bytes)
       return fail(IWQ_ERR_UNSUPPORTED, "matrices of one batched call must share the segment shape (batch per distinct cols for per-channel)");

@@ -60,6 +60,9 @@ struct LaunchParams {
   const float* ranges;     // GIVEN mode: {max|absmax, -min} per job
   float* ranges_out;       // minmax kernel output
   int32_t* status;
+  const uint16_t* lut;     // KIND_FP: device LUT (qc.lut_n entries), copied into shared memory by every CTA
+  uint32_t lut_smem_bytes; // bytes reserved for it in front of the ring (multiple of 1024; 0 for INT kinds)
+  uint32_t pad0;
   QuantConsts qc;
 };
 
@@ -193,7 +196,7 @@ struct PreparedInt {  // KIND_INT_FAST / KIND_INT_WIDE
     zero = q.z;
     bad = q.bad;
   }
-  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts&, const FpEntry*, bool want_codes, uint2* codes8) const {
+  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts&, const uint16_t*, bool want_codes, uint2* codes8) const {
     T2 d[4];
     uint4 o;
     o.x = f.apply(v.x, &d[0]);
@@ -229,7 +232,7 @@ struct Prepared<DT, KIND_INT_GENERIC> {
     zero = q.z;
     bad = q.bad;
   }
-  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts& c, const FpEntry*, bool want_codes, uint2* codes8) const {
+  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts& c, const uint16_t*, bool want_codes, uint2* codes8) const {
     const uint32_t in[4] = {v.x, v.y, v.z, v.w};
     uint32_t out[4], cb[8];
 #pragma unroll
@@ -259,7 +262,7 @@ struct Prepared<DT, KIND_FP> {
     zero = q.mid;
     bad = q.bad;
   }
-  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts& c, const FpEntry* tbl, bool want_codes, uint2* codes8) const {
+  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts& c, const uint16_t* tbl, bool want_codes, uint2* codes8) const {
     T2 g[4];
     uint4 o;
     o.x = f.apply(v.x, tbl, &g[0]);
@@ -329,7 +332,7 @@ __device__ __forceinline__ TileCtx make_tile_ctx(const LaunchParams& p, const Jo
 
 // Consumer side of one tile: v[it] is the vector at tile-local index warp*128 + it*32 + lane.
 template <int DT, int KIND, bool SYM, bool GIVEN>
-__device__ __forceinline__ void consume_tile(uint4 (&v)[kVPT], const TileCtx& t, const LaunchParams& p, const FpEntry* tbl, int warp,
+__device__ __forceinline__ void consume_tile(uint4 (&v)[kVPT], const TileCtx& t, const LaunchParams& p, const uint16_t* tbl, int warp,
                                              int lane) {
   const int lps = p.lps, vpl = p.vpl;
   uint32_t pk[kVPT];
@@ -379,8 +382,14 @@ __device__ __forceinline__ void consume_tile(uint4 (&v)[kVPT], const TileCtx& t,
   if (any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
 }
 
-__device__ __forceinline__ void load_fp_table(const LaunchParams& p, FpEntry* s_tbl) {
-  if (threadIdx.x < 40) s_tbl[threadIdx.x] = p.qc.tbl[threadIdx.x];
+// Copy the minifloat LUT into shared memory (all threads; caller syncs) and return the BIASED pointer:
+// entry of bit pattern b is at [b], valid for lut_lo_bits <= b <= fmax_bits.
+__device__ __forceinline__ const uint16_t* load_fp_lut(const LaunchParams& p, uint8_t* s_lut) {
+  const uint32_t words = (p.qc.lut_n + 1u) >> 1;
+  const uint32_t* g = reinterpret_cast<const uint32_t*>(p.lut);
+  uint32_t* s = reinterpret_cast<uint32_t*>(s_lut);
+  for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) s[i] = g[i];
+  return reinterpret_cast<const uint16_t*>(s_lut) - p.qc.lut_lo_bits;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -393,8 +402,8 @@ __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_c
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kMaxStages;
   TileCtx* ctx = reinterpret_cast<TileCtx*>(smem + 128);
-  FpEntry* s_tbl = reinterpret_cast<FpEntry*>(smem + 640);
-  uint8_t* data = smem + kSmemHeader;
+  const uint16_t* s_tbl = nullptr;
+  uint8_t* data = smem + kSmemHeader + p.lut_smem_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_stages = p.n_stages;
@@ -405,7 +414,7 @@ __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_c
     }
     fence_mbar_init();
   }
-  if (KIND == KIND_FP) load_fp_table(p, s_tbl);
+  if (KIND == KIND_FP) s_tbl = load_fp_lut(p, smem + kSmemHeader);
   __syncthreads();
 
   if (warp == kConsumerWarps) {
@@ -471,7 +480,7 @@ __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_c
 // One lane's share of a tile in seg4_tma_kernel: four vectors through registers, results back to the stage.
 // FAST = full 16 KB tile and no code emission: no per-vector predicates at all.
 template <int DT, int KIND, bool SYM, bool GIVEN, bool FAST>
-__device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParams& p, const FpEntry* s_tbl, uint8_t* lbase, uint32_t lane_vec,
+__device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParams& p, const uint16_t* s_tbl, uint8_t* lbase, uint32_t lane_vec,
                                              uint32_t rot, int lane, int lps) {
   uint4 v[4];
 #pragma unroll
@@ -519,8 +528,8 @@ __global__ void __launch_bounds__(kConsumers + 32) seg4_tma_kernel(const __grid_
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kMaxStages;
   TileCtx* ctx = reinterpret_cast<TileCtx*>(smem + 128);
-  FpEntry* s_tbl = reinterpret_cast<FpEntry*>(smem + 640);
-  uint8_t* data = smem + kSmemHeader;
+  const uint16_t* s_tbl = nullptr;
+  uint8_t* data = smem + kSmemHeader + p.lut_smem_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_stages = p.n_stages;
@@ -531,7 +540,7 @@ __global__ void __launch_bounds__(kConsumers + 32) seg4_tma_kernel(const __grid_
     }
     fence_mbar_init();
   }
-  if (KIND == KIND_FP) load_fp_table(p, s_tbl);
+  if (KIND == KIND_FP) s_tbl = load_fp_lut(p, smem + kSmemHeader);
   __syncthreads();
 
   if (warp == kConsumerWarps) {
@@ -596,9 +605,10 @@ __global__ void __launch_bounds__(kConsumers + 32) seg4_tma_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------
 template <int DT, int KIND, bool SYM, bool GIVEN>
 __global__ void __launch_bounds__(kConsumers) seg_direct_kernel(const __grid_constant__ LaunchParams p) {
-  __shared__ FpEntry s_tbl[40];
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint16_t* s_tbl = nullptr;
   if (KIND == KIND_FP) {
-    load_fp_table(p, s_tbl);
+    s_tbl = load_fp_lut(p, smem);
     __syncthreads();
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -620,7 +630,7 @@ __global__ void __launch_bounds__(kConsumers) seg_direct_kernel(const __grid_con
 
 // ------------------------------------------------------------------------------------------------
 // row_tma_kernel: one row (segment of `row_bytes`) per ring stage; blockDim.x = consumers + 32
-// shared memory header as above, with per-warp partial ranges at [960, 1024) x2 parities (16 warps max)
+// shared memory: header as above (partial ranges at [640, 768): 2 parities x 16 warps) | LUT | ring
 // ------------------------------------------------------------------------------------------------
 struct RowCtx {
   uint8_t* dst;
@@ -638,9 +648,9 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kMaxStages;
   RowCtx* ctx = reinterpret_cast<RowCtx*>(smem + 128);        // 8 x 48 B = 384 B
-  FpEntry* s_tbl = reinterpret_cast<FpEntry*>(smem + 640);    // 320 B
-  uint32_t* partial = reinterpret_cast<uint32_t*>(smem + 960); // [2][16]... 128 B -> spills into the pad before `data`
-  uint8_t* data = smem + kSmemHeader + 128;
+  const uint16_t* s_tbl = nullptr;
+  uint32_t* partial = reinterpret_cast<uint32_t*>(smem + 640); // [2][16] per-warp partial ranges
+  uint8_t* data = smem + kSmemHeader + p.lut_smem_bytes;
 
   const int n_cons = (int)blockDim.x - 32;
   const int n_cwarps = n_cons >> 5;
@@ -653,7 +663,7 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
     }
     fence_mbar_init();
   }
-  if (KIND == KIND_FP) load_fp_table(p, s_tbl);
+  if (KIND == KIND_FP) s_tbl = load_fp_lut(p, smem + kSmemHeader);
   __syncthreads();
 
   if (warp == n_cwarps) {
@@ -821,6 +831,31 @@ __global__ void fp_roundtrip_kernel(const uint32_t* __restrict__ x, uint32_t* __
       uint32_t c1 = fp_code_of<DT>((uint16_t)(vb >> 16), qc.exp_bits, qc.mant_bits);
       codes[i] = (uint16_t)(c0 | (c1 << 8));
     }
+  }
+}
+
+// Build the minifloat LUT of a format: lut[i] = grid(pattern lut_lo_bits + i) for a positive input.
+// Runs once per (device, dtype, E, M, flavour); the element kernels then replace the per-binade table walk
+// of grid() by one shared-memory load per element.
+template <int DT>
+__global__ void fp_lut_kernel(uint16_t* __restrict__ lut, const __grid_constant__ QuantConsts qc) {
+  __shared__ FpEntry s_tbl[40];
+  if (threadIdx.x < 40) s_tbl[threadIdx.x] = qc.tbl[threadIdx.x];
+  __syncthreads();
+  using T2 = typename DType<DT>::T2;
+  FpQ q;
+  q.S = 1.0f;
+  q.r = 1.0f;
+  q.mid = 0.f;
+  q.mid_h = 0.f;
+  q.bad = false;
+  q.slow_div = false;
+  FpTable<DT> f;
+  f.setup(q, qc);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < qc.lut_n; i += gridDim.x * blockDim.x) {
+    const uint32_t pat = (uint32_t)qc.lut_lo_bits + i;
+    const T2 v = f.grid(from_u32<T2>(pat | (pat << 16)), 0u, s_tbl);
+    lut[i] = (uint16_t)(as_u32(v) & 0xFFFFu);
   }
 }
 

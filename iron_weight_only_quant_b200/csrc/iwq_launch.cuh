@@ -72,18 +72,19 @@ static cudaError_t launch_seg_one(LaunchParams p, int variant, const LaunchTunin
   int grid = 0;
   if (variant == 1) {
     auto k = seg_direct_kernel<DT, KIND, SYM, GIVEN>;
-    cudaError_t e = persistent_grid(k, kConsumers, 0, tune.ctas_per_sm, p.total_units, &grid);
+    const size_t smem = p.lut_smem_bytes;
+    cudaError_t e = persistent_grid(k, kConsumers, smem, tune.ctas_per_sm, p.total_units, &grid);
     if (e != cudaSuccess) return e;
-    k<<<grid, kConsumers, 0, st>>>(p);
+    k<<<grid, kConsumers, smem, st>>>(p);
   } else if (variant == 0) {
     auto k = seg4_tma_kernel<DT, KIND, SYM, GIVEN>;
-    const size_t smem = kSmemHeader + (size_t)p.n_stages * kTileBytes;
+    const size_t smem = kSmemHeader + p.lut_smem_bytes + (size_t)p.n_stages * kTileBytes;
     cudaError_t e = persistent_grid(k, kConsumers + 32, smem, tune.ctas_per_sm, p.total_units, &grid);
     if (e != cudaSuccess) return e;
     k<<<grid, kConsumers + 32, smem, st>>>(p);
   } else {
     auto k = seg_tma_kernel<DT, KIND, SYM, GIVEN>;
-    const size_t smem = kSmemHeader + (size_t)p.n_stages * kTileBytes;
+    const size_t smem = kSmemHeader + p.lut_smem_bytes + (size_t)p.n_stages * kTileBytes;
     cudaError_t e = persistent_grid(k, kConsumers + 32, smem, tune.ctas_per_sm, p.total_units, &grid);
     if (e != cudaSuccess) return e;
     k<<<grid, kConsumers + 32, smem, st>>>(p);
@@ -102,7 +103,7 @@ cudaError_t launch_seg(const LaunchParams& p, bool sym, bool given, int variant,
 template <int DT, int KIND, bool SYM>
 static cudaError_t launch_row_one(LaunchParams p, int consumers, const LaunchTuning& tune, cudaStream_t st) {
   auto k = row_tma_kernel<DT, KIND, SYM>;
-  const size_t smem = kSmemHeader + 128 + (size_t)p.n_stages * p.stage_bytes;
+  const size_t smem = kSmemHeader + p.lut_smem_bytes + (size_t)p.n_stages * p.stage_bytes;
   int grid = 0;
   cudaError_t e = persistent_grid(k, consumers + 32, smem, tune.ctas_per_sm, p.total_units, &grid);
   if (e != cudaSuccess) return e;
