@@ -132,10 +132,52 @@ static inline int build_quant_consts(const iwq_config_t* cfg, QuantConsts* c, in
     c->lut_lo_bits = (uint16_t)((llo + DB) << MB);
   }
   c->fmax_bits = (uint16_t)(((emax + DB) << MB) | (((1 << M) - 1) << (MB - M)));
-  c->lut_n = (uint32_t)c->fmax_bits - (uint32_t)c->lut_lo_bits + 1u;
+  c->lut_shift = (uint16_t)(MB - M - 1);
+  c->lut_n = (((uint32_t)c->fmax_bits - (uint32_t)c->lut_lo_bits) >> c->lut_shift) + 1u;
   *kind = KIND_FP;
   return IWQ_OK;
 }
 
+
+// Step table (see FpStep): run the table-walk quantiser grid() on every bit pattern of every interval and
+// record the single value change.  Returns false if some interval changes value more than once (would mean
+// the format violates the assumption; none of the supported ones does).
+template <int DT>
+static inline bool build_step_table_t(const QuantConsts& c, FpStep* out) {
+  using T2 = typename DType<DT>::T2;
+  FpQ q;
+  q.S = 1.0f; q.r = 1.0f; q.mid = 0.f; q.mid_h = 0.f; q.bad = false; q.slow_div = false;
+  FpTable<DT> f;
+  f.setup(q, c);
+  const uint32_t W = 1u << c.lut_shift;
+  const uint16_t inf_bits = (uint16_t)DType<DT>::kInfBits;
+  for (uint32_t i = 0; i < c.lut_n; ++i) {
+    const uint32_t p0 = (uint32_t)c.lut_lo_bits + i * W;
+    auto g = [&](uint32_t pat) { return (uint16_t)(as_u32(f.grid(from_u32<T2>(pat | (pat << 16)), 0u, c.tbl)) & 0xFFFFu); };
+    FpStep e;
+    e.below = g(p0);
+    e.above = e.below;
+    e.thr = inf_bits;
+    e.pad = 0;
+    bool changed = false;
+    for (uint32_t p = p0 + 1; p < p0 + W && p <= c.fmax_bits; ++p) {
+      const uint16_t v = g(p);
+      if (!changed) {
+        if (v != e.below) {
+          changed = true;
+          e.thr = (uint16_t)p;
+          e.above = v;
+        }
+      } else if (v != e.above) {
+        return false;
+      }
+    }
+    out[i] = e;
+  }
+  return true;
+}
+static inline bool build_step_table(int dtype, const QuantConsts& c, FpStep* out) {
+  return dtype == IWQ_F16 ? build_step_table_t<IWQ_F16>(c, out) : build_step_table_t<IWQ_BF16>(c, out);
+}
 
 }  // namespace iwq

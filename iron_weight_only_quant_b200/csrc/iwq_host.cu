@@ -59,9 +59,9 @@ static int build_consts(const iwq_config_t* cfg, QuantConsts* c, int* kind) {
 // minifloat LUT cache: one small device buffer per (device, dtype, E, M, flavour), built on first use
 // ------------------------------------------------------------------------------------------------
 static std::mutex g_lut_mu;
-static std::map<std::tuple<int, int, int, int, int>, uint16_t*> g_luts;
+static std::map<std::tuple<int, int, int, int, int>, FpStep*> g_luts;
 
-static int get_fp_lut(const iwq_config_t* cfg, const QuantConsts& qc, cudaStream_t st, const uint16_t** out) {
+static int get_fp_lut(const iwq_config_t* cfg, const QuantConsts& qc, cudaStream_t st, const FpStep** out) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
@@ -72,20 +72,18 @@ static int get_fp_lut(const iwq_config_t* cfg, const QuantConsts& qc, cudaStream
     *out = it->second;
     return IWQ_OK;
   }
-  uint16_t* buf = nullptr;
-  const size_t bytes = ((size_t)qc.lut_n * 2 + 1023) & ~(size_t)1023;
-  e = cudaMalloc((void**)&buf, bytes);
-  if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(minifloat LUT)");
-  const int grid = (int)((qc.lut_n + 255) / 256);
-  if (cfg->dtype == IWQ_F16)
-    fp_lut_kernel<IWQ_F16><<<grid, 256, 0, st>>>(buf, qc);
-  else
-    fp_lut_kernel<IWQ_BF16><<<grid, 256, 0, st>>>(buf, qc);
-  e = cudaGetLastError();
+  if (qc.lut_n > 1024) return fail(IWQ_ERR_UNSUPPORTED, "minifloat step table too large");
+  std::vector<FpStep> host(qc.lut_n);
+  if (!build_step_table(cfg->dtype, qc, host.data()))
+    return fail(IWQ_ERR_UNSUPPORTED, "minifloat format changes value more than once inside a half-step interval");
+  FpStep* buf = nullptr;
+  e = cudaMalloc((void**)&buf, host.size() * sizeof(FpStep));
+  if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(minifloat step table)");
+  e = cudaMemcpyAsync(buf, host.data(), host.size() * sizeof(FpStep), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // one-time: later calls may come on any stream
   if (e != cudaSuccess) {
     cudaFree(buf);
-    return fail_cuda(e, "minifloat LUT build");
+    return fail_cuda(e, "minifloat step table upload");
   }
   g_luts[key] = buf;
   *out = buf;
@@ -304,7 +302,7 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
   if (kind == KIND_FP) {
     rc = get_fp_lut(cfg, p.qc, st, &p.lut);
     if (rc) return rc;
-    p.lut_smem_bytes = (uint32_t)(((size_t)p.qc.lut_n * 2 + 1023) & ~(size_t)1023);
+    p.lut_smem_bytes = (uint32_t)(((size_t)p.qc.lut_n * sizeof(FpStep) + 1023) & ~(size_t)1023);
   }
   Plan pl;
   rc = make_plan(cfg, ms[0].cols, p.lut_smem_bytes, &pl);

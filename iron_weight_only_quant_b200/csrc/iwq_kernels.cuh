@@ -60,7 +60,7 @@ struct LaunchParams {
   const float* ranges;     // GIVEN mode: {max|absmax, -min} per job
   float* ranges_out;       // minmax kernel output
   int32_t* status;
-  const uint16_t* lut;     // KIND_FP: device LUT (qc.lut_n entries), copied into shared memory by every CTA
+  const FpStep* lut;       // KIND_FP: device step table (qc.lut_n entries), copied into shared memory by every CTA
   uint32_t lut_smem_bytes; // bytes reserved for it in front of the ring (multiple of 1024; 0 for INT kinds)
   uint32_t pad0;
   QuantConsts qc;
@@ -189,14 +189,14 @@ struct PreparedInt {  // KIND_INT_FAST / KIND_INT_WIDE
   IntFast<DT, KIND == KIND_INT_WIDE> f;
   float scale, zero;
   bool bad;
-  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c, bool sym) {
+  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c, bool sym, const FpStep*) {
     IntQ q = int_segment_params<DT>(mx, mn, c, sym);
     f.setup(q);
     scale = q.s;
     zero = q.z;
     bad = q.bad;
   }
-  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts&, const uint16_t*, bool want_codes, uint2* codes8) const {
+  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts&, const FpStep*, bool want_codes, uint2* codes8) const {
     T2 d[4];
     uint4 o;
     o.x = f.apply(v.x, &d[0]);
@@ -226,13 +226,13 @@ struct Prepared<DT, KIND_INT_GENERIC> {
   IntQ q;
   float scale, zero;
   bool bad;
-  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c, bool sym) {
+  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c, bool sym, const FpStep*) {
     q = int_segment_params<DT>(mx, mn, c, sym);
     scale = q.s;
     zero = q.z;
     bad = q.bad;
   }
-  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts& c, const uint16_t*, bool want_codes, uint2* codes8) const {
+  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts& c, const FpStep*, bool want_codes, uint2* codes8) const {
     const uint32_t in[4] = {v.x, v.y, v.z, v.w};
     uint32_t out[4], cb[8];
 #pragma unroll
@@ -255,20 +255,26 @@ struct Prepared<DT, KIND_FP> {
   FpTable<DT> f;
   float scale, zero;
   bool bad;
-  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c, bool /*sym*/) {
+  __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c, bool /*sym*/, const FpStep* steps) {
     FpQ q = fp_segment_params<DT>(mx, mn, c);
-    f.setup(q, c);
+    f.setup(q, c, steps);
     scale = q.S;
     zero = q.mid;
     bad = q.bad;
   }
-  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts& c, const uint16_t* tbl, bool want_codes, uint2* codes8) const {
-    T2 g[4];
+  template <bool SLOW>
+  __device__ __forceinline__ uint4 apply_t(const uint4& v, T2 (&g)[4]) const {
     uint4 o;
-    o.x = f.apply(v.x, tbl, &g[0]);
-    o.y = f.apply(v.y, tbl, &g[1]);
-    o.z = f.apply(v.z, tbl, &g[2]);
-    o.w = f.apply(v.w, tbl, &g[3]);
+    o.x = f.template apply<SLOW>(v.x, &g[0]);
+    o.y = f.template apply<SLOW>(v.y, &g[1]);
+    o.z = f.template apply<SLOW>(v.z, &g[2]);
+    o.w = f.template apply<SLOW>(v.w, &g[3]);
+    return o;
+  }
+  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts& c, const FpStep*, bool want_codes, uint2* codes8) const {
+    T2 g[4];
+    // one (segment-uniform) branch per vector: IEEE division only for degenerate scales
+    const uint4 o = f.slow_div ? apply_t<true>(v, g) : apply_t<false>(v, g);
     if (want_codes) {
       uint32_t cb[8];
 #pragma unroll
@@ -332,7 +338,7 @@ __device__ __forceinline__ TileCtx make_tile_ctx(const LaunchParams& p, const Jo
 
 // Consumer side of one tile: v[it] is the vector at tile-local index warp*128 + it*32 + lane.
 template <int DT, int KIND, bool SYM, bool GIVEN>
-__device__ __forceinline__ void consume_tile(uint4 (&v)[kVPT], const TileCtx& t, const LaunchParams& p, const uint16_t* tbl, int warp,
+__device__ __forceinline__ void consume_tile(uint4 (&v)[kVPT], const TileCtx& t, const LaunchParams& p, const FpStep* tbl, int warp,
                                              int lane) {
   const int lps = p.lps, vpl = p.vpl;
   uint32_t pk[kVPT];
@@ -355,14 +361,14 @@ __device__ __forceinline__ void consume_tile(uint4 (&v)[kVPT], const TileCtx& t,
   const bool want_codes = t.codes != nullptr;
   bool any_bad = false;
   Prepared<DT, KIND> prep;
-  if (GIVEN) prep.setup(t.given_mx, t.given_mn, p.qc, SYM);
+  if (GIVEN) prep.setup(t.given_mx, t.given_mn, p.qc, SYM, tbl);
 #pragma unroll
   for (int it = 0; it < kVPT; ++it) {
     const uint32_t idx = (uint32_t)warp * (32 * kVPT) + it * 32 + lane;
     if (!GIVEN && (it & (vpl - 1)) == 0) {  // its of one segment share the parameters
       float mx, mn;
       range_unpack<DT>(pk[it], &mx, &mn);
-      prep.setup(mx, mn, p.qc, SYM);
+      prep.setup(mx, mn, p.qc, SYM, tbl);
     }
     uint2 codes8;
     const uint4 o = prep.apply(v[it], p.qc, tbl, want_codes, &codes8);
@@ -382,14 +388,12 @@ __device__ __forceinline__ void consume_tile(uint4 (&v)[kVPT], const TileCtx& t,
   if (any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
 }
 
-// Copy the minifloat LUT into shared memory (all threads; caller syncs) and return the BIASED pointer:
-// entry of bit pattern b is at [b], valid for lut_lo_bits <= b <= fmax_bits.
-__device__ __forceinline__ const uint16_t* load_fp_lut(const LaunchParams& p, uint8_t* s_lut) {
-  const uint32_t words = (p.qc.lut_n + 1u) >> 1;
-  const uint32_t* g = reinterpret_cast<const uint32_t*>(p.lut);
-  uint32_t* s = reinterpret_cast<uint32_t*>(s_lut);
-  for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) s[i] = g[i];
-  return reinterpret_cast<const uint16_t*>(s_lut) - p.qc.lut_lo_bits;
+// Copy the minifloat step table into shared memory (all threads; caller syncs).
+__device__ __forceinline__ const FpStep* load_fp_lut(const LaunchParams& p, uint8_t* s_lut) {
+  const uint2* g = reinterpret_cast<const uint2*>(p.lut);
+  uint2* s = reinterpret_cast<uint2*>(s_lut);
+  for (uint32_t i = threadIdx.x; i < p.qc.lut_n; i += blockDim.x) s[i] = g[i];
+  return reinterpret_cast<const FpStep*>(s_lut);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -402,7 +406,7 @@ __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_c
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kMaxStages;
   TileCtx* ctx = reinterpret_cast<TileCtx*>(smem + 128);
-  const uint16_t* s_tbl = nullptr;
+  const FpStep* s_tbl = nullptr;
   uint8_t* data = smem + kSmemHeader + p.lut_smem_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_c
 // One lane's share of a tile in seg4_tma_kernel: four vectors through registers, results back to the stage.
 // FAST = full 16 KB tile and no code emission: no per-vector predicates at all.
 template <int DT, int KIND, bool SYM, bool GIVEN, bool FAST>
-__device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParams& p, const uint16_t* s_tbl, uint8_t* lbase, uint32_t lane_vec,
+__device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParams& p, const FpStep* s_tbl, uint8_t* lbase, uint32_t lane_vec,
                                              uint32_t rot, int lane, int lps) {
   uint4 v[4];
 #pragma unroll
@@ -490,7 +494,7 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
   }
   Prepared<DT, KIND> prep;
   if (GIVEN) {
-    prep.setup(t.given_mx, t.given_mn, p.qc, SYM);
+    prep.setup(t.given_mx, t.given_mn, p.qc, SYM, s_tbl);
   } else {
     uint32_t pk = range_max<DT>(range_max<DT>(vec_range<DT, SYM>(v[0]), vec_range<DT, SYM>(v[1])),
                                 range_max<DT>(vec_range<DT, SYM>(v[2]), vec_range<DT, SYM>(v[3])));
@@ -500,7 +504,7 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
     }
     float mx, mn;
     range_unpack<DT>(pk, &mx, &mn);
-    prep.setup(mx, mn, p.qc, SYM);
+    prep.setup(mx, mn, p.qc, SYM, s_tbl);
   }
   const bool want_codes = !FAST && t.codes != nullptr;
 #pragma unroll
@@ -523,12 +527,12 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
 }
 
 template <int DT, int KIND, bool SYM, bool GIVEN>
-__global__ void __launch_bounds__(kConsumers + 32) seg4_tma_kernel(const __grid_constant__ LaunchParams p) {
+__global__ void __launch_bounds__(kConsumers + 32, 3) seg4_tma_kernel(const __grid_constant__ LaunchParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kMaxStages;
   TileCtx* ctx = reinterpret_cast<TileCtx*>(smem + 128);
-  const uint16_t* s_tbl = nullptr;
+  const FpStep* s_tbl = nullptr;
   uint8_t* data = smem + kSmemHeader + p.lut_smem_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -606,7 +610,7 @@ __global__ void __launch_bounds__(kConsumers + 32) seg4_tma_kernel(const __grid_
 template <int DT, int KIND, bool SYM, bool GIVEN>
 __global__ void __launch_bounds__(kConsumers) seg_direct_kernel(const __grid_constant__ LaunchParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint16_t* s_tbl = nullptr;
+  const FpStep* s_tbl = nullptr;
   if (KIND == KIND_FP) {
     s_tbl = load_fp_lut(p, smem);
     __syncthreads();
@@ -648,7 +652,7 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kMaxStages;
   RowCtx* ctx = reinterpret_cast<RowCtx*>(smem + 128);        // 8 x 48 B = 384 B
-  const uint16_t* s_tbl = nullptr;
+  const FpStep* s_tbl = nullptr;
   uint32_t* partial = reinterpret_cast<uint32_t*>(smem + 640); // [2][16] per-warp partial ranges
   uint8_t* data = smem + kSmemHeader + p.lut_smem_bytes;
 
@@ -716,7 +720,7 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
       // sweep 2: quantise from shared memory, store to global
       const bool want_codes = t.codes != nullptr;
       Prepared<DT, KIND> prep;
-      prep.setup(mx, mn, p.qc, SYM);
+      prep.setup(mx, mn, p.qc, SYM, s_tbl);
       for (uint32_t i = tid; i < t.n_vec; i += n_cons) {
         uint2 codes8;
         const uint4 o = prep.apply(lds128(sdata + (size_t)i * 16), p.qc, s_tbl, want_codes, &codes8);
@@ -831,31 +835,6 @@ __global__ void fp_roundtrip_kernel(const uint32_t* __restrict__ x, uint32_t* __
       uint32_t c1 = fp_code_of<DT>((uint16_t)(vb >> 16), qc.exp_bits, qc.mant_bits);
       codes[i] = (uint16_t)(c0 | (c1 << 8));
     }
-  }
-}
-
-// Build the minifloat LUT of a format: lut[i] = grid(pattern lut_lo_bits + i) for a positive input.
-// Runs once per (device, dtype, E, M, flavour); the element kernels then replace the per-binade table walk
-// of grid() by one shared-memory load per element.
-template <int DT>
-__global__ void fp_lut_kernel(uint16_t* __restrict__ lut, const __grid_constant__ QuantConsts qc) {
-  __shared__ FpEntry s_tbl[40];
-  if (threadIdx.x < 40) s_tbl[threadIdx.x] = qc.tbl[threadIdx.x];
-  __syncthreads();
-  using T2 = typename DType<DT>::T2;
-  FpQ q;
-  q.S = 1.0f;
-  q.r = 1.0f;
-  q.mid = 0.f;
-  q.mid_h = 0.f;
-  q.bad = false;
-  q.slow_div = false;
-  FpTable<DT> f;
-  f.setup(q, qc);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < qc.lut_n; i += gridDim.x * blockDim.x) {
-    const uint32_t pat = (uint32_t)qc.lut_lo_bits + i;
-    const T2 v = f.grid(from_u32<T2>(pat | (pat << 16)), 0u, s_tbl);
-    lut[i] = (uint16_t)(as_u32(v) & 0xFFFFu);
   }
 }
 

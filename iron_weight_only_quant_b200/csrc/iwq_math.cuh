@@ -186,6 +186,15 @@ struct FpEntry {      // one per binade of the clamped magnitude |n|
   uint16_t bump_val;  // ... and the result is 2^(e+1)
 };
 
+// Step table of a minifloat format: the quantiser is a monotone step function of the clamped magnitude, and
+// inside an interval of W consecutive bit patterns it changes value at most once (a round-to-even tie sits on
+// an interval's first pattern; a log2-bump threshold sits inside a binade's last interval).  Entry i covers
+// patterns [lut_lo_bits + i*W, +W):  value = pattern >= thr ? above : below.  Built on the host by running
+// grid() over every pattern (iwq_host.cu: build_step_table), <= 4 KB, copied to shared memory by each CTA.
+struct FpStep {
+  uint16_t thr, below, above, pad;
+};
+
 struct QuantConsts {
   int32_t scheme, bits, exp_bits, mant_bits, symmetric, flavour_rne;
   float min_int, max_int;  // INT: clamp bounds (quant_funcs.py:19-20, :26-27)
@@ -197,8 +206,8 @@ struct QuantConsts {
   int32_t tbl_base;        // biased D exponent of table entry 0
   int32_t tbl_n;
   uint16_t lut_lo_bits;    // D bits of 2^(emin-M-1): everything at or below it quantises to 0 (exact tie -> even)
-  uint16_t lut_pad;
-  uint32_t lut_n;          // LUT entries: bit patterns lut_lo_bits .. fmax_bits
+  uint16_t lut_shift;      // log2 of the interval width W = 2^(mantissa_bits(D) - M - 1) bit patterns (half a grid step)
+  uint32_t lut_n;          // number of FpStep intervals covering bit patterns lut_lo_bits .. fmax_bits
   FpEntry tbl[40];
 };
 
@@ -377,8 +386,18 @@ struct FpTable {
   float S, r;
   bool asym, rne, slow_div;
   int tbl_off;  // entry index = exponent_field - tbl_base
+  uint32_t lo2, sh;          // step table: packed low pattern, log2 interval width
+  const FpStep* steps;       // host: pointer; device: also as a 32-bit shared-memory address
+  uint32_t steps_saddr;
 
-  IWQ_HD void setup(const FpQ& q, const QuantConsts& c) {
+  IWQ_HD void setup(const FpQ& q, const QuantConsts& c, const FpStep* step_tbl = nullptr) {
+    steps = step_tbl;
+    steps_saddr = 0;
+#ifdef __CUDA_ARCH__
+    if (step_tbl) steps_saddr = (uint32_t)__cvta_generic_to_shared(step_tbl);
+#endif
+    lo2 = (uint32_t)c.lut_lo_bits | ((uint32_t)c.lut_lo_bits << 16);
+    sh = c.lut_shift;
     S2 = D::from_f32x2(q.S, q.S);
     mid2 = D::from_f32x2(q.mid, q.mid);
     midh2 = D::from_f32x2(q.mid_h, q.mid_h);
@@ -419,28 +438,42 @@ struct FpTable {
     return from_u32<T2>(vb | sgn);
   }
 
-  // Same function as grid(), evaluated through a look-up table over the bit patterns of the clamped
-  // magnitude (built once per format by running grid() on every pattern: iwq_host.cu).  `lut` is biased:
-  // lut[pattern] is valid for lut_lo_bits <= pattern <= fmax_bits.  12 ops per pair instead of 21.
-  IWQ_HD T2 grid_lut(T2 n2, uint32_t sign_src, const uint16_t* lut) const {
+  // Same function as grid(), evaluated through the step table: one 8-byte shared-memory load per element
+  // (intervals are few, so lanes mostly share entries and bank conflicts are rare), a packed compare and a
+  // select.  No per-binade constants, no table walk.
+  IWQ_HD T2 grid_steps(T2 n2, uint32_t sign_src) const {
     const uint32_t nb = as_u32(n2);
     T2 a = from_u32<T2>(nb & 0x7FFF7FFFu);
     a = __hmin2(a, fmax2);
     a = __hmax2(a, lutlo2);
-    const uint32_t ab = as_u32(a);
-    const uint32_t v0 = lut[ab & 0xFFFFu];
-    const uint32_t v1 = lut[ab >> 16];
+    const uint32_t d = as_u32(a) - lo2;  // per-half pattern offset; no borrow (a >= lo in both halves)
+    const uint32_t i0 = (d & 0xFFFFu) >> sh;
+    const uint32_t i1 = d >> (16u + sh);
+    uint2 e0, e1;
+#ifdef __CUDA_ARCH__
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(e0.x), "=r"(e0.y) : "r"(steps_saddr + i0 * 8u));
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(e1.x), "=r"(e1.y) : "r"(steps_saddr + i1 * 8u));
+#else
+    e0 = *reinterpret_cast<const uint2*>(steps + i0);
+    e1 = *reinterpret_cast<const uint2*>(steps + i1);
+#endif
+    const uint32_t thr = (e0.x & 0xFFFFu) | (e1.x << 16);
+    const uint32_t below = (e0.x >> 16) | (e1.x & 0xFFFF0000u);
+    const uint32_t above = (e0.y & 0xFFFFu) | (e1.y << 16);
+    const uint32_t m = __hge2_mask(a, from_u32<T2>(thr));
+    const uint32_t vb = (below & ~m) | (above & m);
     const uint32_t sgn = rne ? (sign_src & 0x80008000u) : (__hlt2_mask(n2, from_u32<T2>(0u)) & 0x80008000u);
-    return from_u32<T2>(v0 | (v1 << 16) | sgn);
+    return from_u32<T2>(vb | sgn);
   }
 
-  IWQ_HD uint32_t apply(uint32_t w2, const uint16_t* lut, T2* v2) const {
+  template <bool SLOW>
+  IWQ_HD uint32_t apply(uint32_t w2, T2* v2) const {
     T2 w = from_u32<T2>(w2);
     if (asym) w = __hsub2(w, mid2);                                   // weight - zeros            :755
-    T2 n = slow_div ? ieee_quot2<DT>(w, S) : fast_quot2<DT>(w, S, r); // / scales
-    T2 v = grid_lut(n, w2, lut);
-    // a NaN quotient (only possible when S is 0/inf/NaN, i.e. slow_div) must stay NaN: grid() clamped it
-    if (slow_div) v = from_u32<T2>(as_u32(v) | __hneu2_mask(n, n));
+    T2 n = SLOW ? ieee_quot2<DT>(w, S) : fast_quot2<DT>(w, S, r);     // / scales
+    T2 v = grid_steps(n, w2);
+    // a NaN quotient (only possible when S is 0/inf/NaN, i.e. the slow path) must stay NaN: the clamp removed it
+    if (SLOW) v = from_u32<T2>(as_u32(v) | __hneu2_mask(n, n));
     *v2 = v;
     T2 o = __hmul2(v, S2);                                            // decoded.to(D) * scales    :774
     if (asym) o = __hadd2(o, midh2);                                  // + zeros.half().to(D)      :776

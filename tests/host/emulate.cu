@@ -41,18 +41,11 @@ static int run(const iwq_config_t* cfg, const QuantConsts& c, int kind, const ui
   if (cfg->group > 0 && cols % cfg->group) return IWQ_ERR_INDIVISIBLE;
   if (seg % 2) return IWQ_ERR_UNSUPPORTED;
   const bool sym = c.symmetric != 0;
-  // the minifloat LUT, built exactly like fp_lut_kernel does on the device: grid() on every pattern
-  std::vector<uint16_t> lut;
+  // the minifloat step table, built by the same host code the library uses
+  std::vector<FpStep> steps;
   if (kind == KIND_FP) {
-    FpQ q1;
-    q1.S = 1.0f; q1.r = 1.0f; q1.mid = 0.f; q1.mid_h = 0.f; q1.bad = false; q1.slow_div = false;
-    FpTable<DT> f1;
-    f1.setup(q1, c);
-    lut.resize(c.lut_n);
-    for (uint32_t i = 0; i < c.lut_n; ++i) {
-      const uint32_t pat = (uint32_t)c.lut_lo_bits + i;
-      lut[i] = (uint16_t)(as_u32(f1.grid(from_u32<T2>(pat | (pat << 16)), 0u, c.tbl)) & 0xFFFFu);
-    }
+    steps.resize(c.lut_n);
+    if (!build_step_table(DT, c, steps.data())) return IWQ_ERR_UNSUPPORTED;
   }
   for (int64_t s0 = 0, g = 0; s0 < total; s0 += seg, ++g) {
     float mx, mn;
@@ -61,12 +54,11 @@ static int run(const iwq_config_t* cfg, const QuantConsts& c, int kind, const ui
     if (kind == KIND_FP) {
       FpQ q = fp_segment_params<DT>(mx, mn, c);
       FpTable<DT> f;
-      f.setup(q, c);
-      const uint16_t* lut_b = lut.data() - c.lut_lo_bits;  // biased, like the kernels' shared-memory copy
+      f.setup(q, c, steps.data());
       for (int64_t i = 0; i < seg; i += 2) {
         uint32_t w2 = (uint32_t)w[s0 + i] | ((uint32_t)w[s0 + i + 1] << 16);
         T2 v;
-        uint32_t o = f.apply(w2, lut_b, &v);
+        uint32_t o = q.slow_div ? f.template apply<true>(w2, &v) : f.template apply<false>(w2, &v);
         out[s0 + i] = (uint16_t)(o & 0xFFFF);
         out[s0 + i + 1] = (uint16_t)(o >> 16);
       }
