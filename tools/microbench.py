@@ -28,13 +28,19 @@ CONFIGS = {
     "fp4e2m1g128": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=2, mant_bits=1, symmetric=True),
     "fp8e4m3g128": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=4, mant_bits=3, symmetric=True),
     "fp4e2m1g128asym": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=2, mant_bits=1, symmetric=False),
+    "fp4e1m2g128": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=1, mant_bits=2, symmetric=True),
+    "fp6e3m2g128": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=3, mant_bits=2, symmetric=True),
+    "fp6e2m3g128": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=2, mant_bits=3, symmetric=True),
+    "fprne_e2m1g128": dict(scheme=_lib.SCHEME_FP_RNE, group=128, exp_bits=2, mant_bits=1, symmetric=True),
+    "int4pc_sym": dict(scheme=_lib.SCHEME_INT, group=-2, bits=4, symmetric=True),
+    "int4pt_sym": dict(scheme=_lib.SCHEME_INT, group=-1, bits=4, symmetric=True),
 }
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="llama-2-70b")
-    ap.add_argument("--layers", type=int, default=2)
+    ap.add_argument("--layers", type=int, default=2, help="decoder layers of the model to use (0 = all)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--dtype", default="f16")
     ap.add_argument("--configs", default="int4g128,int4g128sym,int4g32,int8pc,int4pt,fp4e2m1g128,fp8e4m3g128")
@@ -43,11 +49,11 @@ def main():
     dev = torch.device("cuda:0")
     dt = torch.float16 if args.dtype == "f16" else torch.bfloat16
     m = shapes.MODELS[args.model]
-    mats = m.matrices(range(args.layers))
+    mats = m.matrices(range(args.layers if args.layers > 0 else m.n_layers))
     ws = [(torch.randn(o, k, device=dev, dtype=torch.float32) * 0.02).to(dt) for o, k in mats]
     n = sum(w.numel() for w in ws)
     knobs = {k: os.environ[k] for k in os.environ if k.startswith("IWQ_")}
-    res = {"knobs": knobs, "dtype": args.dtype, "weights": n, "results": {}}
+    res = {"knobs": knobs, "model": args.model, "layers": args.layers if args.layers > 0 else m.n_layers, "dtype": args.dtype, "weights": n, "results": {}}
 
     def timeit(fn):
         for _ in range(3):
