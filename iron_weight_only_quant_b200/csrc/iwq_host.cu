@@ -42,6 +42,8 @@ struct Knobs {
   int row_ctas = env_int("IWQ_ROW_CTAS", 0);
   int row_smem_kb = env_int("IWQ_ROW_SMEM_KB", 0);  // per-CTA ring budget; 0 = automatic
   int variant = env_int("IWQ_VARIANT", -1);          // -1: use cfg->variant
+  int row_variant = env_int("IWQ_ROW_VARIANT", 0);   // 0: row4_tma_kernel, 1: row_tma_kernel
+  int row_warps = env_int("IWQ_ROW_WARPS", 0);       // consumer warps of the row kernels; 0 = automatic
 };
 static const Knobs& knobs() {
   static Knobs k;
@@ -194,9 +196,32 @@ static int make_plan(const iwq_config_t* cfg, int64_t cols, uint32_t lut_bytes, 
   pl->path = PATH_ROW;
   pl->stage_bytes = stage;
   const uint64_t vecs = row_bytes / 16;
-  pl->consumers = vecs >= 2048 ? 512 : (vecs >= 384 ? 256 : (vecs >= 96 ? 128 : 64));
-  // ring budget per CTA: aim for >= 3 CTAs per SM on short rows, 2 on long ones
-  uint64_t budget = knobs().row_smem_kb > 0 ? (uint64_t)knobs().row_smem_kb * 1024 : (stage <= 24 * 1024 ? 64 * 1024 : 100 * 1024);
+  if (knobs().row_variant == 0) {
+    // row4: 2 KB chunks dealt to the warps; one chunk per warp up to 16 warps, then an even split
+    const uint64_t chunks = (vecs + 127) / 128;
+    uint64_t warps = chunks <= 16 ? chunks : (chunks + ((chunks + 15) / 16) - 1) / ((chunks + 15) / 16);
+    if (knobs().row_warps > 0) warps = (uint64_t)knobs().row_warps;
+    if (warps < 1) warps = 1;
+    if (warps > 16) warps = 16;
+    pl->consumers = (int)warps * 32;
+  } else {
+    pl->consumers = vecs >= 2048 ? 512 : (vecs >= 384 ? 256 : (vecs >= 96 ? 128 : 64));
+  }
+  // ring budget per CTA
+  uint64_t budget;
+  if (knobs().row_smem_kb > 0) {
+    budget = (uint64_t)knobs().row_smem_kb * 1024;
+  } else if (knobs().row_variant == 0) {
+    // row4: aim for >= 24 consumer warps per SM, with at least 3 stages per CTA (the release of a stage lags
+    // one row behind, see the kernel), as long as the rows allow it
+    int ctas = 24 / (pl->consumers / 32);
+    if (ctas < 1) ctas = 1;
+    if (ctas > 8) ctas = 8;
+    while (ctas > 1 && (max_ring + lut_bytes) / ctas < 3ull * stage + lut_bytes + kSmemHeader) --ctas;
+    budget = (max_ring + lut_bytes) / ctas - lut_bytes - kSmemHeader;
+  } else {
+    budget = stage <= 24 * 1024 ? 64 * 1024 : 100 * 1024;
+  }
   if (budget > max_ring) budget = max_ring;
   int st = (int)(budget / stage);
   if (st < 2) st = 2;
@@ -324,6 +349,7 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
   const bool per_tensor = cfg->group == IWQ_GROUP_PER_TENSOR;
   LaunchTuning tune;
   tune.stages = p.n_stages;
+  tune.row_variant = knobs().row_variant;
   cudaError_t e;
   // kernel variant: 0 = seg4 (TMA in + TMA out, 4 vectors per lane; needs group >= 32), 1 = direct global
   // loads/stores, 2 = TMA in + register stores (one vector per lane-iteration; also serves group 8 / 16)
