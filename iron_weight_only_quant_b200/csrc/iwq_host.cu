@@ -42,7 +42,6 @@ struct Knobs {
   int row_ctas = env_int("IWQ_ROW_CTAS", 0);
   int row_smem_kb = env_int("IWQ_ROW_SMEM_KB", 0);  // per-CTA ring budget; 0 = automatic
   int variant = env_int("IWQ_VARIANT", -1);          // -1: use cfg->variant
-  int row_variant = env_int("IWQ_ROW_VARIANT", 0);   // 0: row4_tma_kernel, 1: row_tma_kernel
   int row_warps = env_int("IWQ_ROW_WARPS", 0);       // consumer warps of the row kernels; 0 = automatic
 };
 static const Knobs& knobs() {
@@ -196,35 +195,19 @@ static int make_plan(const iwq_config_t* cfg, int64_t cols, uint32_t lut_bytes, 
   pl->path = PATH_ROW;
   pl->stage_bytes = stage;
   const uint64_t vecs = row_bytes / 16;
-  if (knobs().row_variant == 0) {
-    // row4: 2 KB chunks dealt to the warps; one chunk per warp up to 16 warps, then an even split
-    const uint64_t chunks = (vecs + 127) / 128;
-    uint64_t warps = chunks <= 16 ? chunks : (chunks + ((chunks + 15) / 16) - 1) / ((chunks + 15) / 16);
-    if (knobs().row_warps > 0) warps = (uint64_t)knobs().row_warps;
-    if (warps < 1) warps = 1;
-    if (warps > 16) warps = 16;
-    pl->consumers = (int)warps * 32;
-  } else {
-    pl->consumers = vecs >= 2048 ? 512 : (vecs >= 384 ? 256 : (vecs >= 96 ? 128 : 64));
-  }
-  // ring budget per CTA
-  uint64_t budget;
-  if (knobs().row_smem_kb > 0) {
-    budget = (uint64_t)knobs().row_smem_kb * 1024;
-  } else if (knobs().row_variant == 0) {
-    // row4: aim for >= 24 consumer warps per SM, with at least 3 stages per CTA (the release of a stage lags
-    // one row behind, see the kernel), as long as the rows allow it
-    int ctas = 24 / (pl->consumers / 32);
-    if (ctas < 1) ctas = 1;
-    if (ctas > 8) ctas = 8;
-    while (ctas > 1 && (max_ring + lut_bytes) / ctas < 3ull * stage + lut_bytes + kSmemHeader) --ctas;
-    budget = (max_ring + lut_bytes) / ctas - lut_bytes - kSmemHeader;
-  } else {
-    budget = stage <= 24 * 1024 ? 64 * 1024 : 100 * 1024;
-  }
+  // Small CTAs, many per SM: the kernel pays one named barrier per row, which other resident CTAs hide.
+  // Measured on B200 (profiles/r01_row_kernel_sweep.txt): 2 consumer warps x ~28-36 KB ring for 8 KB rows,
+  // 4 warps x 72 KB for 16-56 KB rows.
+  int warps = vecs <= 128 ? 1 : (int)(vecs / 256);
+  if (warps < (vecs <= 128 ? 1 : 2)) warps = vecs <= 128 ? 1 : 2;
+  if (warps > 4) warps = 4;
+  if (knobs().row_warps > 0) warps = knobs().row_warps > 16 ? 16 : knobs().row_warps;
+  pl->consumers = 32 * warps;
+  uint64_t budget = knobs().row_smem_kb > 0 ? (uint64_t)knobs().row_smem_kb * 1024 : 72 * 1024;
   if (budget > max_ring) budget = max_ring;
   int st = (int)(budget / stage);
   if (st < 2) st = 2;
+  if (st > 4 && knobs().row_smem_kb <= 0) st = 4;
   if (st > kMaxStages) st = kMaxStages;
   pl->stages = st;
   return IWQ_OK;
@@ -349,7 +332,6 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
   const bool per_tensor = cfg->group == IWQ_GROUP_PER_TENSOR;
   LaunchTuning tune;
   tune.stages = p.n_stages;
-  tune.row_variant = knobs().row_variant;
   cudaError_t e;
   // kernel variant: 0 = seg4 (TMA in + TMA out, 4 vectors per lane; needs group >= 32), 1 = direct global
   // loads/stores, 2 = TMA in + register stores (one vector per lane-iteration; also serves group 8 / 16)

@@ -743,148 +743,6 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
-// row4_tma_kernel (default for per-channel rows): seg4's data path applied to whole rows.
-//   one bulk load per row into a ring stage; the row is cut into 2 KB chunks (128 vectors) dealt round-robin to
-//   the consumer warps; each lane owns 4 consecutive vectors of a chunk (rotated, conflict-free LDS/STS);
-//   sweep 1: range of the lane's vectors -> warp shuffle reduce -> one named barrier to combine the warps;
-//   sweep 2: quantise (from registers when every warp has a single chunk, else re-read from shared memory),
-//   results go back into the stage and leave through one bulk store per chunk; all stores of a row form one
-//   bulk group, and the stage is released when the previous row's group has finished reading (as in seg4).
-// blockDim.x = 32 * consumer warps + 32; shared memory: header (partials at [640,768)) | step table | ring.
-// ------------------------------------------------------------------------------------------------
-template <int DT, int KIND, bool SYM>
-__global__ void __launch_bounds__(512 + 32) row4_tma_kernel(const __grid_constant__ LaunchParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* empty = full + kMaxStages;
-  RowCtx* ctx = reinterpret_cast<RowCtx*>(smem + 128);
-  const FpStep* s_tbl = nullptr;
-  uint32_t* partial = reinterpret_cast<uint32_t*>(smem + 640);
-  uint8_t* data = smem + kSmemHeader + p.lut_smem_bytes;
-
-  const int n_cons = (int)blockDim.x - 32;
-  const int n_cwarps = n_cons >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_stages = p.n_stages;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < n_stages; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], n_cwarps);
-    }
-    fence_mbar_init();
-  }
-  if (KIND == KIND_FP) s_tbl = load_fp_lut(p, smem + kSmemHeader);
-  __syncthreads();
-
-  if (warp == n_cwarps) {
-    if (lane == 0) {
-      int stage = 0, cur = -1;
-      uint32_t phase = 0;
-      Job jb;
-      for (uint32_t row = blockIdx.x; row < p.total_units; row += gridDim.x) {
-        mbar_wait(&empty[stage], phase ^ 1u);
-        advance_job(p, row, &cur, &jb);
-        const uint64_t r = row - jb.first_unit;
-        RowCtx t;
-        t.dst = jb.dst + r * jb.row_bytes;
-        t.scales = jb.scales;
-        t.zeros = jb.zeros;
-        t.codes = jb.codes ? jb.codes + r * (jb.row_bytes >> 1) : nullptr;
-        t.row = r;
-        t.n_vec = jb.row_bytes >> 4;
-        t.pad = 0;
-        ctx[stage] = t;
-        mbar_arrive_expect_tx(&full[stage], jb.row_bytes);
-        tma_load_1d(data + (size_t)stage * p.stage_bytes, jb.src + r * jb.row_bytes, jb.row_bytes, &full[stage]);
-        if (++stage == n_stages) {
-          stage = 0;
-          phase ^= 1u;
-        }
-      }
-    }
-    return;
-  }
-
-  const uint32_t ident = SYM ? 0u : (DT == IWQ_F16 ? 0xFC00FC00u : 0xFF80FF80u);
-  const uint32_t rot = (uint32_t)lane >> 1;
-  int stage = 0, prev_stage = -1;
-  uint32_t phase = 0, par = 0;
-  for (uint32_t row = blockIdx.x; row < p.total_units; row += gridDim.x) {
-    mbar_wait(&full[stage], phase);
-    const RowCtx t = ctx[stage];
-    uint8_t* sdata = data + (size_t)stage * p.stage_bytes;
-    const uint32_t n_chunks = (t.n_vec + 127u) >> 7;
-    const bool single = n_chunks <= (uint32_t)n_cwarps;  // block-uniform: at most one chunk per warp
-    // ---- sweep 1: range ----
-    uint32_t pk = ident;
-    uint4 v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = make_uint4(0u, 0u, 0u, 0u);
-    for (uint32_t c = (uint32_t)warp; c < n_chunks; c += (uint32_t)n_cwarps) {
-      const uint32_t lv = c * 128u + (uint32_t)lane * 4u;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t j = (k + rot) & 3u;
-        if (lv + j < t.n_vec) {
-          v[k] = lds128(sdata + (size_t)(lv + j) * 16);
-          pk = range_max<DT>(pk, vec_range<DT, SYM>(v[k]));
-        }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) pk = range_max<DT>(pk, __shfl_xor_sync(0xFFFFFFFFu, pk, o));
-    if (lane == 0) partial[par * 16 + warp] = pk;
-    asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory");
-    uint32_t all = partial[par * 16];
-    for (int w = 1; w < n_cwarps; ++w) all = range_max<DT>(all, partial[par * 16 + w]);
-    par ^= 1u;
-    float mx, mn;
-    range_unpack<DT>(all, &mx, &mn);
-    Prepared<DT, KIND> prep;
-    prep.setup(mx, mn, p.qc, SYM, s_tbl);
-    // ---- sweep 2: quantise, write back into the stage, bulk-store chunk by chunk ----
-    const bool want_codes = t.codes != nullptr;
-    for (uint32_t c = (uint32_t)warp; c < n_chunks; c += (uint32_t)n_cwarps) {
-      const uint32_t lv = c * 128u + (uint32_t)lane * 4u;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t j = (k + rot) & 3u;
-        if (lv + j < t.n_vec) {
-          const uint4 in = single ? v[k] : lds128(sdata + (size_t)(lv + j) * 16);
-          uint2 codes8;
-          const uint4 o = prep.apply(in, p.qc, s_tbl, want_codes, &codes8);
-          sts128(sdata + (size_t)(lv + j) * 16, o);
-          if (want_codes) *reinterpret_cast<uint2*>(t.codes + (size_t)(lv + j) * 8) = codes8;
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        const uint32_t v0 = c * 128u;
-        const uint32_t nv = t.n_vec - v0 < 128u ? t.n_vec - v0 : 128u;
-        tma_store_1d(t.dst + (size_t)v0 * 16, sdata + (size_t)v0 * 16, nv * 16u);
-      }
-    }
-    if (threadIdx.x == 0) {
-      if (t.scales) reinterpret_cast<uint16_t*>(t.scales)[t.row] = DType<DT>::from_f32(prep.scale);
-      if (t.zeros) reinterpret_cast<uint16_t*>(t.zeros)[t.row] = DType<DT>::from_f32(prep.zero);
-      if (prep.bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
-    }
-    if (lane == 0) {
-      tma_store_commit();            // one bulk group per row and warp (possibly empty)
-      tma_store_wait_read<1>();      // the previous row's stores have finished reading their stage
-      if (prev_stage >= 0) mbar_arrive(&empty[prev_stage]);
-    }
-    prev_stage = stage;
-    if (++stage == n_stages) {
-      stage = 0;
-      phase ^= 1u;
-    }
-  }
-  if (lane == 0) tma_store_wait_all();
-}
-
-// ------------------------------------------------------------------------------------------------
 // per-tensor granularity, pass 1
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {

@@ -16,7 +16,6 @@ namespace iwq {
 struct LaunchTuning {
   int stages;        // ring depth of the TMA kernels (2..8)
   int ctas_per_sm;   // 0 = as many as fit
-  int row_variant;   // 0 = row4_tma_kernel (TMA in + TMA out), 1 = row_tma_kernel (register stores)
 };
 
 // grid size for a persistent kernel: resident CTAs per SM (occupancy API) x SM count, cached
@@ -103,15 +102,6 @@ cudaError_t launch_seg(const LaunchParams& p, bool sym, bool given, int variant,
 
 template <int DT, int KIND, bool SYM>
 static cudaError_t launch_row_one(LaunchParams p, int consumers, const LaunchTuning& tune, cudaStream_t st) {
-  if (tune.row_variant == 0) {
-    auto k4 = row4_tma_kernel<DT, KIND, SYM>;
-    const size_t smem4 = kSmemHeader + p.lut_smem_bytes + (size_t)p.n_stages * p.stage_bytes;
-    int grid4 = 0;
-    cudaError_t e4 = persistent_grid(k4, consumers + 32, smem4, tune.ctas_per_sm, p.total_units, &grid4);
-    if (e4 != cudaSuccess) return e4;
-    k4<<<grid4, consumers + 32, smem4, st>>>(p);
-    return cudaGetLastError();
-  }
   auto k = row_tma_kernel<DT, KIND, SYM>;
   const size_t smem = kSmemHeader + p.lut_smem_bytes + (size_t)p.n_stages * p.stage_bytes;
   int grid = 0;

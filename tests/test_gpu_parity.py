@@ -453,3 +453,38 @@ def test_full_size_properties(shape):
     oc = quant_funcs.pseudo_quantize_tensor(w, n_bits=8, zero_point=True)
     ref = O.int_fake_quant(bits(w[idx.to(DEV)]), "f16", 8, True, -2)["out"]
     assert np.array_equal(bits(oc[idx.to(DEV)]), ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's real callers: HuggingFace LLaMA / OPT modules walked by quantize_model
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("family", ["llama", "opt"])
+def test_quantize_model_on_hf_architectures(family):
+    """Random-init tiny LLaMA / OPT (the two families main.py targets) on the GPU in fp16, walked exactly as
+    main.py:326 does; every Linear except lm_head is replaced, weights equal the oracle, generation-style
+    forward still runs."""
+    transformers = pytest.importorskip("transformers")
+    torch.manual_seed(0)
+    if family == "llama":
+        cfg = transformers.LlamaConfig(hidden_size=256, intermediate_size=768, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, vocab_size=512, max_position_embeddings=128)
+        model = transformers.LlamaForCausalLM(cfg)
+        n_lin = 2 * 7
+    else:
+        cfg = transformers.OPTConfig(hidden_size=256, ffn_dim=1024, num_hidden_layers=2, num_attention_heads=4, vocab_size=512, max_position_embeddings=128, word_embed_proj_dim=256)
+        model = transformers.OPTForCausalLM(cfg)
+        n_lin = 2 * 6
+    model = model.half().to(DEV).eval()
+    before = {n: bits(m.weight.data) for n, m in model.named_modules() if isinstance(m, torch.nn.Linear)}
+    args = _Args(w_bit=4, w_group_size=128, w_symmetric=False)
+    quant_wrapper.quantize_model(model, args)
+    q = {n: m for n, m in model.named_modules() if isinstance(m, quant_linear.QuantLinear)}
+    assert len(q) == n_lin
+    assert not any("lm_head" in n for n in q)
+    for n, m in q.items():
+        ref = O.int_fake_quant(before[n], "f16", 4, True, 128)
+        assert_bits(bits(m.weight.data), ref["out"], "f16", n)
+        assert_bits(bits(m.scales.reshape(-1)), ref["scales"], "f16", n + " scales")
+    ids = torch.randint(0, 512, (2, 16), device=DEV)
+    with torch.no_grad():
+        out = model(ids)
+    assert out.logits.shape == (2, 16, 512) and torch.isfinite(out.logits).all()
