@@ -34,7 +34,9 @@ enum { IWQ_F16 = 0, IWQ_BF16 = 1 };
 enum {
   IWQ_SCHEME_INT = 0,      /* quant_funcs.py:4-46 == quant_linear.py:885-956 (INT min-max, asym/sym)   */
   IWQ_SCHEME_FP_CODEC = 1, /* quant_linear.py:724-883 + _float_to_fp :126-163 + _fp_to_float :213-235 */
-  IWQ_SCHEME_FP_RNE = 2    /* fp4_quantize_cpu.py:37-72 (_fp_scale, ideal RNE minifloat, absmax scale) */
+  IWQ_SCHEME_FP_RNE = 2,   /* fp4_quantize_cpu.py:37-72 (_fp_scale, ideal RNE minifloat, absmax scale) */
+  IWQ_SCHEME_BFP = 3       /* quant_linear.py:648-723 (block floating point: shared exponent per group,
+                              `bits` = w_bit: sign + min(w_bit-1, 11) mantissa bits; group > 0 only)   */
 };
 
 /* granularity: `group` > 0 -> contiguous runs of `group` elements along `cols`
@@ -61,7 +63,7 @@ enum {
 typedef struct iwq_config {
   int32_t dtype;     /* IWQ_F16 / IWQ_BF16                                                             */
   int32_t scheme;    /* IWQ_SCHEME_*                                                                   */
-  int32_t bits;      /* INT: n_bits (1..15).  FP schemes: ignored                                      */
+  int32_t bits;      /* INT: n_bits (1..15).  BFP: w_bit (2..15).  FP schemes: ignored                 */
   int32_t exp_bits;  /* FP schemes: exponent bits E (1..5)                                             */
   int32_t mant_bits; /* FP schemes: mantissa bits M (0..6)                                             */
   int32_t symmetric; /* 1: absmax scale, no zero point (zero_point=False); 0: min/max (zero_point=True)*/

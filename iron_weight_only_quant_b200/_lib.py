@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IWQ_LIB", os.path.join(_HERE, "libiwq_b200.so"))
 
 IWQ_F16, IWQ_BF16 = 0, 1
-SCHEME_INT, SCHEME_FP_CODEC, SCHEME_FP_RNE = 0, 1, 2
+SCHEME_INT, SCHEME_FP_CODEC, SCHEME_FP_RNE, SCHEME_BFP = 0, 1, 2, 3
 GROUP_PER_TENSOR, GROUP_PER_CHANNEL = -1, -2
 STATUS_NAN = 1
 

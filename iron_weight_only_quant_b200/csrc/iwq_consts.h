@@ -13,7 +13,7 @@
 
 namespace iwq {
 
-enum { KIND_INT_FAST = 0, KIND_INT_WIDE = 1, KIND_FP = 2, KIND_INT_GENERIC = 3 };
+enum { KIND_INT_FAST = 0, KIND_INT_WIDE = 1, KIND_FP = 2, KIND_INT_GENERIC = 3, KIND_BFP = 4 };
 
 static inline float round_to_dtype(int dtype, float x) { return dtype == IWQ_F16 ? rD<IWQ_F16>(x) : rD<IWQ_BF16>(x); }
 
@@ -71,6 +71,17 @@ static inline int build_quant_consts(const iwq_config_t* cfg, QuantConsts* c, in
     if (getenv("IWQ_FORCE_GENERIC")) *kind = KIND_INT_GENERIC;
     // max_int is a value of the 16-bit dtype on the packed paths (<= 255): exact reciprocal-multiply division
     c->inv_div = (*kind == KIND_INT_GENERIC) ? 0.0f : 1.0f / c->max_int;
+    return IWQ_OK;
+  }
+  if (cfg->scheme == IWQ_SCHEME_BFP) {
+    const int b = cfg->bits;
+    if (b < 2 || b > 15) return fail(IWQ_ERR_INVALID, "BFP w_bit must be in [2, 15]");
+    if (cfg->group <= 0) return fail(IWQ_ERR_INVALID, "BFP needs a positive group size (quant_linear.py:650)");
+    c->symmetric = 1;  // the range pass is the absolute maximum
+    c->bfp_target = b - 1 < 11 ? b - 1 : 11;
+    c->bfp_sd = 11 - c->bfp_target;
+    c->bfp_round_mant = (dt == IWQ_BF16 && c->bfp_target > 8) ? 1 : 0;
+    *kind = KIND_BFP;
     return IWQ_OK;
   }
   if (cfg->scheme != IWQ_SCHEME_FP_CODEC && cfg->scheme != IWQ_SCHEME_FP_RNE) return fail(IWQ_ERR_INVALID, "unknown scheme");

@@ -100,6 +100,7 @@ static cudaError_t dispatch_seg(int dt, int kind, const LaunchParams& p, bool sy
     switch (kind) {
       case KIND_INT_FAST: return launch_seg<IWQ_F16, KIND_INT_FAST>(p, sym, given, variant, t, st);
       case KIND_FP: return launch_seg<IWQ_F16, KIND_FP>(p, sym, given, variant, t, st);
+      case KIND_BFP: return launch_seg<IWQ_F16, KIND_BFP>(p, sym, given, variant, t, st);
       default: return launch_seg<IWQ_F16, KIND_INT_GENERIC>(p, sym, given, variant, t, st);
     }
   }
@@ -107,6 +108,7 @@ static cudaError_t dispatch_seg(int dt, int kind, const LaunchParams& p, bool sy
     case KIND_INT_FAST: return launch_seg<IWQ_BF16, KIND_INT_FAST>(p, sym, given, variant, t, st);
     case KIND_INT_WIDE: return launch_seg<IWQ_BF16, KIND_INT_WIDE>(p, sym, given, variant, t, st);
     case KIND_FP: return launch_seg<IWQ_BF16, KIND_FP>(p, sym, given, variant, t, st);
+    case KIND_BFP: return launch_seg<IWQ_BF16, KIND_BFP>(p, sym, given, variant, t, st);
     default: return launch_seg<IWQ_BF16, KIND_INT_GENERIC>(p, sym, given, variant, t, st);
   }
 }
@@ -115,6 +117,7 @@ static cudaError_t dispatch_row(int dt, int kind, const LaunchParams& p, bool sy
     switch (kind) {
       case KIND_INT_FAST: return launch_row<IWQ_F16, KIND_INT_FAST>(p, sym, consumers, t, st);
       case KIND_FP: return launch_row<IWQ_F16, KIND_FP>(p, sym, consumers, t, st);
+      case KIND_BFP: return launch_row<IWQ_F16, KIND_BFP>(p, sym, consumers, t, st);
       default: return launch_row<IWQ_F16, KIND_INT_GENERIC>(p, sym, consumers, t, st);
     }
   }
@@ -122,6 +125,7 @@ static cudaError_t dispatch_row(int dt, int kind, const LaunchParams& p, bool sy
     case KIND_INT_FAST: return launch_row<IWQ_BF16, KIND_INT_FAST>(p, sym, consumers, t, st);
     case KIND_INT_WIDE: return launch_row<IWQ_BF16, KIND_INT_WIDE>(p, sym, consumers, t, st);
     case KIND_FP: return launch_row<IWQ_BF16, KIND_FP>(p, sym, consumers, t, st);
+    case KIND_BFP: return launch_row<IWQ_BF16, KIND_BFP>(p, sym, consumers, t, st);
     default: return launch_row<IWQ_BF16, KIND_INT_GENERIC>(p, sym, consumers, t, st);
   }
 }

@@ -289,6 +289,23 @@ struct Prepared<DT, KIND_FP> {
   }
 };
 
+template <int DT>
+struct Prepared<DT, KIND_BFP> {
+  BfpApply<DT> f;
+  float scale, zero;
+  bool bad;
+  __device__ __forceinline__ void setup(float mx, float /*mn*/, const QuantConsts& c, bool /*sym*/, const FpStep*) {
+    f.setup(bfp_segment_params<DT>(mx, c), c);
+    scale = 0.f;
+    zero = 0.f;
+    bad = false;
+  }
+  __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts&, const FpStep*, bool want_codes, uint2* codes8) const {
+    if (want_codes) *codes8 = make_uint2(0u, 0u);  // the reference keeps no BFP codes (quant_linear.py:712-715)
+    return make_uint4(f.apply(v.x), f.apply(v.y), f.apply(v.z), f.apply(v.w));
+  }
+};
+
 // per-tile context handed from the producer to the consumers through shared memory
 struct TileCtx {
   uint8_t* dst;      // output address of the tile's first byte

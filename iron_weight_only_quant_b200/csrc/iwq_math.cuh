@@ -205,6 +205,9 @@ struct QuantConsts {
   uint16_t tiny_bits;      // D bits of 2^(emin - M - 3): magnitudes are clamped up to it before the table lookup
   int32_t tbl_base;        // biased D exponent of table entry 0
   int32_t tbl_n;
+  int32_t bfp_target;      // BFP: mantissa bits kept incl. the leading one = min(w_bit-1, 11)   quant_linear.py:673
+  int32_t bfp_sd;          // BFP: 11 - bfp_target (rounding right shift)                          quant_linear.py:674
+  int32_t bfp_round_mant;  // BFP on bf16 with more than 8 mantissa bits: `mant_rounded.to(bf16)` rounds (:707)
   uint16_t lut_lo_bits;    // D bits of 2^(emin-M-1): everything at or below it quantises to 0 (exact tie -> even)
   uint16_t lut_shift;      // log2 of the interval width W = 2^(mantissa_bits(D) - M - 1) bit patterns (half a grid step)
   uint32_t lut_n;          // number of FpStep intervals covering bit patterns lut_lo_bits .. fmax_bits
@@ -478,6 +481,91 @@ struct FpTable {
     T2 o = __hmul2(v, S2);                                            // decoded.to(D) * scales    :774
     if (asym) o = __hadd2(o, midh2);                                  // + zeros.half().to(D)      :776
     return as_u32(o);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// block floating point          quant_linear.py:648-723 (+ _rounding_rshift :112-123)
+//
+// The reference works on the fp16 bit fields: m = (implicit one << 10 | mantissa) >> (E_max - E), then
+// (m + 2^(sd-1)) >> sd, clamp to 2^target - 1, times 2^(E_max - 15 - (target-1)).  With
+//     a_ref = (implicit one << 10 | mantissa) * 2^(E - 25)   (= |w|, except that exponent field 0 counts HALF:
+//                                                              the reference treats field 0 like exponent -15)
+// and step = 2^(E_max - 25 + sd) this is   q = floor(a_ref / step + 1/2)   (truncate-then-round-half-up collapses
+// to one floor), clamped, times step.  All of it is exact in fp32: a_ref/step has <= 11 significant bits,
+// adding 2^-12 turns round-half-even (the magic-number add) into round-half-up without touching non-ties.
+// ------------------------------------------------------------------------------------------------
+struct BfpQ {
+  float step, inv_step, top, tie;
+};
+
+template <int DT>
+IWQ_HD BfpQ bfp_segment_params(float absmax, const QuantConsts& c) {
+  // E_max = exponent field of the group's largest magnitude after the cast to fp16 (:656, :668)
+  const uint32_t hb = DType<IWQ_F16>::from_f32(absmax);
+  const int eb = (int)((hb >> 10) & 31u);
+  BfpQ q;
+  q.step = bits_f32((uint32_t)(eb - 25 + c.bfp_sd + 127) << 23);
+  q.inv_step = bits_f32((uint32_t)(25 - eb - c.bfp_sd + 127) << 23);
+  q.top = (float)((1 << c.bfp_target) - 1) + 0.25f;  // floor(min(x, M + 1/4) + 1/2) == min(floor(x + 1/2), M)
+  // sd > 0: round half up = RNE(x + 2^-12).  sd == 0 (w_bit >= 12): no rounding shift at all, plain truncation
+  // (:674-699) = floor(x) = round-half-up(x - 1/2).
+  q.tie = c.bfp_sd > 0 ? 0.000244140625f : (0.000244140625f - 0.5f);
+  return q;
+}
+
+// exact fp32 product of two fp16 values (one FHFMA on sm_100a: fma.rn.f32.f16)
+IWQ_HD float mul_f16_to_f32(uint16_t a, uint16_t b) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r) : "h"(a), "h"(b), "f"(0.0f));
+  return r;
+#else
+  return DType<IWQ_F16>::to_f32(a) * DType<IWQ_F16>::to_f32(b);
+#endif
+}
+
+template <int DT>
+struct BfpApply {
+  using D = DType<DT>;
+  using T2 = typename D::T2;
+  float step, inv_step, top, tie;
+  bool round_mant;
+
+  IWQ_HD void setup(const BfpQ& q, const QuantConsts& c) {
+    step = q.step;
+    inv_step = q.inv_step;
+    top = q.top;
+    tie = q.tie;
+    round_mant = c.bfp_round_mant != 0;
+  }
+
+  IWQ_HD uint32_t apply(uint32_t w2) const {
+    // .to(torch.float16)                                                                     :656
+    uint32_t h2 = w2;
+    if (DT != IWQ_F16) {
+      float2 f = D::to_f32x2(from_u32<T2>(w2));
+      __half2 h = __floats2half2_rn(f.x, f.y);
+      h2 = *reinterpret_cast<uint32_t*>(&h);
+    }
+    const uint32_t ab = h2 & 0x7FFF7FFFu;
+    // exponent field 0 (|w| < 2^-14): no implicit one AND the field is used as-is -> a_ref = |w| / 2   :664-670
+    const uint32_t sub = __hlt2_mask(from_u32<__half2>(ab), from_u32<__half2>(0x04000400u));
+    const uint32_t mul2 = 0x3C003C00u ^ (sub & 0x04000400u);  // 1.0, or 0.5 where the field is 0
+    float x0 = mul_f16_to_f32((uint16_t)(ab & 0xFFFFu), (uint16_t)(mul2 & 0xFFFFu)) * inv_step;
+    float x1 = mul_f16_to_f32((uint16_t)(ab >> 16), (uint16_t)(mul2 >> 16)) * inv_step;
+    x0 = fminf(x0, top);                                                                   // clamp  :700-701
+    x1 = fminf(x1, top);
+    const float kMagic = 12582912.0f;                         // 1.5 * 2^23
+    float q0 = ((x0 + tie) + kMagic) - kMagic;                // floor(x + 1/2): align shift + _rounding_rshift
+    float q1 = ((x1 + tie) + kMagic) - kMagic;
+    if (round_mant) {                                          // mant_rounded.to(bf16)               :707
+      q0 = rD<DT>(q0);
+      q1 = rD<DT>(q1);
+    }
+    const float s0 = bits_f32(f32_bits(step) | ((h2 << 16) & 0x80000000u));  // scale * sign_factor    :705-707
+    const float s1 = bits_f32(f32_bits(step) | (h2 & 0x80000000u));
+    return as_u32(D::from_f32x2(q0 * s0, q1 * s1));            // .to(weight dtype)                    :708
   }
 };
 

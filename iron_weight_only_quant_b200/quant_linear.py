@@ -15,8 +15,9 @@ Different on purpose: the arithmetic is ONE fused CUDA pass per matrix (libiwq_b
 CPU weight when called from `from_linear` (quant_linear.py:444,460-468 costs ~12 ns per weight);
 no `torch.cuda.empty_cache()` per layer (:954, :162).
 
-Not implemented yet (raise NotImplementedError): weight_format='bfp' (:648-723), approximate /
-double_approximate decode (:237-363, :470-632), quant_dim=1 (:478-483, :640-647).
+Also implemented: weight_format='bfp' (block floating point, :648-723).
+Not implemented yet (raise NotImplementedError): approximate / double_approximate decode (:237-363,
+:470-632), quant_dim=1 (:478-483, :640-647).
 """
 from __future__ import annotations
 
@@ -192,10 +193,8 @@ class QuantLinear(nn.Module):
             raise NotImplementedError("approximate / double_approximate decode is not implemented in iron_weight_only_quant_b200 yet")
         if self.quant_dim == 1:
             raise NotImplementedError("quant_dim=1 (grouping along the output dim) is not implemented in iron_weight_only_quant_b200 yet")
-        if self.weight_format == "bfp":
-            if self.w_group_size <= 0:
-                raise ValueError("BFP 仅支持分组量化，请将 w_group_size 设为正数")  # quant_linear.py:650
-            raise NotImplementedError("weight_format='bfp' is not implemented in iron_weight_only_quant_b200 yet")
+        if self.weight_format == "bfp" and self.w_group_size <= 0:
+            raise ValueError("BFP 仅支持分组量化，请将 w_group_size 设为正数")  # quant_linear.py:650
         w = self.weight.data
         rows, cols = w.shape
         g = self.w_group_size
@@ -203,6 +202,10 @@ class QuantLinear(nn.Module):
             assert cols % g == 0  # quant_linear.py:728 / :897
         elif g not in (-1, -2):
             raise ValueError("Invalid w_group_size")  # quant_linear.py:737 / :906
+        if self.weight_format == "bfp":
+            # sign + min(w_bit-1, 11) mantissa bits around the group's max exponent; no scales / zeros buffers
+            cfg = _lib.make_config(w.dtype, _lib.SCHEME_BFP, g, bits=self.w_bit, symmetric=True)
+            return cfg, 0, False
         if self.weight_format == "int":
             if self.w_bit >= 16:
                 return None
@@ -214,6 +217,8 @@ class QuantLinear(nn.Module):
 
     def _alloc_qparams(self, G: int, wants_zeros: bool):
         w = self.weight.data
+        if G == 0:  # BFP: the reference stores neither scales nor zeros (quant_linear.py:716-717)
+            return None, None
         scales = torch.empty(G, 1, dtype=w.dtype, device=w.device)
         zeros = torch.empty(G, 1, dtype=w.dtype, device=w.device) if wants_zeros else None
         return scales, zeros
@@ -221,7 +226,12 @@ class QuantLinear(nn.Module):
     def _finish(self, scales, zeros):
         """Store buffers the way the reference does: INT keeps the weight dtype (quant_linear.py:924-932);
         FP formats store `.half()` copies (:761-768, quirk Q1)."""
-        if self.weight_format == "int":
+        if self.weight_format == "bfp":
+            self.scales = None
+            self.zeros = None
+            self.weight_bfp_mantissa = None
+            self.weight_bfp_exponent = None
+        elif self.weight_format == "int":
             self.scales = scales
             self.zeros = zeros
         else:

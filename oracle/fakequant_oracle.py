@@ -375,3 +375,43 @@ def minmax_of(w_bits: np.ndarray, dtype: str):
     min/max all-reduce; exact and order independent, so sharded == unsharded."""
     w = from_bits(w_bits, dtype)
     return np.float32(w.max()), np.float32(w.min()), np.float32(np.abs(w).max())
+
+
+# --------------------------------------------------------------------------------------------
+# block floating point (shared exponent per group)   quant_linear.py:648-723, _rounding_rshift :112-123
+# --------------------------------------------------------------------------------------------
+
+
+def bfp_fake_quant(w_bits: np.ndarray, dtype: str, w_bit: int, group: int):
+    """QuantLinear.quantize_weight, weight_format='bfp' (quant_linear.py:648-723), followed literally:
+    fp16 field split (:658-661), implicit one except for exponent field 0 (:664-665), truncating right shift to
+    the group's max exponent FIELD (:668-670), round-half-up right shift to `min(w_bit-1, 11)` mantissa bits
+    (:673-698, _rounding_rshift :112-123), clamp (:700-701), dequantise with 2^(exp_block-15-frac) (:704-708).
+    Note the reference's treatment of fp16 subnormals (exponent field 0 is used as if it were exponent -15,
+    i.e. subnormal inputs count half) is reproduced, not fixed."""
+    if group <= 0:
+        raise ValueError("BFP 仅支持分组量化，请将 w_group_size 设为正数")
+    w = from_bits(w_bits, dtype)
+    shape = w.shape
+    g = _group_view(w, group)
+    with np.errstate(over="ignore"):
+        b = g.astype(np.float16).view(np.uint16).astype(np.int64)  # .to(torch.float16).view(int16).to(int32)
+    sign = (b >> 15) & 1
+    exp = (b >> 10) & 0x1F
+    mant = b & 0x3FF
+    lead = np.where(exp == 0, 0, 1)
+    m = (lead << 10) | mant
+    exp_block = exp.max(axis=1, keepdims=True)
+    shift = np.clip(exp_block - exp, 0, None)
+    m = m >> shift
+    target = min(w_bit - 1, 11)
+    sd = max(0, 11 - target)
+    if sd > 0:
+        m = (m + (1 << (sd - 1))) >> sd
+    m = np.minimum(m, (1 << target) - 1)
+    frac = target - 1
+    scale = np.exp2((exp_block - 15).astype(np.float32) - np.float32(frac)).astype(np.float32)
+    sf = np.where(sign == 1, np.float32(-1.0), np.float32(1.0))
+    with np.errstate(over="ignore"):
+        out = rD(rD(m.astype(np.float32), dtype) * scale * rD(sf, dtype), dtype)
+    return dict(out=to_bits(out, dtype).reshape(shape))

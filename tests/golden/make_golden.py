@@ -170,9 +170,23 @@ def gen_fp_rne(out: dict):
     out["main_out"] = bits_of(fp4_quantize_cpu.quantize_fp16_to_fp4_e1m2(wm, group_size=128))
 
 
+def gen_bfp(out: dict):
+    """weight_format='bfp' (quant_linear.py:648-723) on the INT input matrix."""
+    master = build_input()
+    for dn, dt in TORCH_DT.items():
+        w = master.to(dt)
+        out[f"w_{dn}"] = bits_of(w)
+        for w_bit in (3, 4, 5, 6, 8, 12):
+            for grp in (32, 64, 128, 512):
+                lin = torch.nn.Linear(w.shape[1], w.shape[0], bias=False)
+                lin.weight.data = w.clone()
+                ql = quant_linear.QuantLinear.from_linear(lin, w_bit=w_bit, w_group_size=grp, symmetric=True, weight_format="bfp")
+                out[f"{dn}_b{w_bit}_g{grp}"] = bits_of(ql.weight.data)
+
+
 def main():
     torch.set_num_threads(8)
-    for name, fn in (("golden_int", gen_int), ("golden_fp_chain", gen_fp_chain), ("golden_fp_tables", gen_fp_tables), ("golden_fp_rne", gen_fp_rne)):
+    for name, fn in (("golden_int", gen_int), ("golden_fp_chain", gen_fp_chain), ("golden_fp_tables", gen_fp_tables), ("golden_fp_rne", gen_fp_rne), ("golden_bfp", gen_bfp)):
         d = {}
         fn(d)
         d["_meta"] = np.array([f"torch {torch.__version__}; reference at {REF}; cpu"], dtype="U")

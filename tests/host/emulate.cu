@@ -51,7 +51,16 @@ static int run(const iwq_config_t* cfg, const QuantConsts& c, int kind, const ui
     float mx, mn;
     seg_range<DT>(w + s0, seg, sym, &mx, &mn);
     float sc = 0, zp = 0;
-    if (kind == KIND_FP) {
+    if (kind == KIND_BFP) {
+      BfpApply<DT> f;
+      f.setup(bfp_segment_params<DT>(mx, c), c);
+      for (int64_t i = 0; i < seg; i += 2) {
+        uint32_t w2 = (uint32_t)w[s0 + i] | ((uint32_t)w[s0 + i + 1] << 16);
+        uint32_t o = f.apply(w2);
+        out[s0 + i] = (uint16_t)(o & 0xFFFF);
+        out[s0 + i + 1] = (uint16_t)(o >> 16);
+      }
+    } else if (kind == KIND_FP) {
       FpQ q = fp_segment_params<DT>(mx, mn, c);
       FpTable<DT> f;
       f.setup(q, c, steps.data());

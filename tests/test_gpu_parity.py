@@ -372,6 +372,10 @@ def test_wrapper_gates_and_errors():
     with pytest.raises(ValueError):
         quant_wrapper.quantize_model(model, _Args(w_format="bfp", w_group_size=-1))  # quant_wrapper.py:19-20
     with pytest.raises(NotImplementedError):
+        quant_wrapper.quantize_model(model, _Args(w_format="fp4", approximate=True))  # not built yet: fails loudly
+    with pytest.raises(NotImplementedError):
+        quant_wrapper.quantize_model(model, _Args(quant_dim=1))
+    with pytest.raises(NotImplementedError):
         quant_wrapper.quantize_model(model, _Args(gptq=True, w_format="fp4"))  # quant_wrapper.py:24-25
 
 
@@ -488,3 +492,32 @@ def test_quantize_model_on_hf_architectures(family):
     with torch.no_grad():
         out = model(ids)
     assert out.logits.shape == (2, 16, 512) and torch.isfinite(out.logits).all()
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_bfp_matches_reference_golden(golden, dt):
+    """weight_format='bfp' (quant_linear.py:648-723) through QuantLinear.from_linear and quantize_model."""
+    g = golden("golden_bfp")
+    w = tensor_of(g[f"w_{dt}"], dt)
+    for w_bit in (3, 4, 5, 6, 8, 12):
+        for grp in (32, 64, 128, 512):
+            lin = torch.nn.Linear(w.shape[1], w.shape[0], bias=False, device=DEV, dtype=TDT[dt])
+            lin.weight.data.copy_(w)
+            ql = quant_linear.QuantLinear.from_linear(lin, w_bit=w_bit, w_group_size=grp, symmetric=True, weight_format="bfp")
+            assert_bits(bits(ql.weight.data), g[f"{dt}_b{w_bit}_g{grp}"], dt, f"b{w_bit} g{grp}")
+            assert ql.scales is None and ql.zeros is None and bool(ql.quantized)
+    lin = torch.nn.Linear(w.shape[1], w.shape[0], bias=False, device=DEV, dtype=TDT[dt])
+    with pytest.raises(ValueError):
+        quant_linear.QuantLinear.from_linear(lin, w_bit=4, w_group_size=-1, weight_format="bfp")  # quant_linear.py:650
+
+
+def test_bfp_vs_oracle_large_and_batched():
+    w = seeded(512, 4096, "f16", 17)
+    ref = O.bfp_fake_quant(bits(w), "f16", 4, 128)["out"]
+    model = torch.nn.Sequential(torch.nn.Linear(4096, 512, bias=False), torch.nn.Linear(4096, 512, bias=False)).half().to(DEV)
+    for m in model:
+        m.weight.data.copy_(w.to(DEV))
+    quant_wrapper.quantize_model(model, _Args(w_bit=4, w_group_size=128, w_symmetric=True, w_format="bfp4"))
+    for m in model:
+        assert isinstance(m, quant_linear.QuantLinear) and m.weight_format == "bfp"
+        assert np.array_equal(bits(m.weight.data), ref)

@@ -17,7 +17,7 @@ SRC = os.path.join(ROOT, "tests", "host", "emulate.cu")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 F16, BF16 = 0, 1
-SCHEME_INT, SCHEME_FP_CODEC, SCHEME_FP_RNE = 0, 1, 2
+SCHEME_INT, SCHEME_FP_CODEC, SCHEME_FP_RNE, SCHEME_BFP = 0, 1, 2, 3
 KIND_INT_FAST, KIND_INT_WIDE, KIND_FP, KIND_INT_GENERIC = 0, 1, 2, 3
 FORMATS = {"e2m1": (2, 1), "e1m2": (1, 2), "e3m2": (3, 2), "e2m3": (2, 3), "e4m3": (4, 3), "e5m2": (5, 2)}
 
@@ -162,3 +162,13 @@ def test_fp_rne_chain_matches_reference(emu, golden):
         assert_bits_equal(out.reshape(-1, grp), g[f"e2m1_g{grp}"], "f16", str(grp))
     out, _, _ = run_emu(emu, w, F16, SCHEME_FP_RNE, -1, E=2, M=1, sym=True)
     assert_bits_equal(out.reshape(1, -1), g["e2m1_pt"], "f16", "pt")
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_bfp_math_matches_reference(emu, golden, dt):
+    g = golden("golden_bfp")
+    w = g[f"w_{dt}"]
+    for w_bit in (3, 4, 5, 6, 8, 12):
+        for grp in (32, 64, 128, 512):
+            out, _, _ = run_emu(emu, w, F16 if dt == "f16" else BF16, SCHEME_BFP, grp, bits=w_bit, sym=True)
+            assert_bits_equal(out, g[f"{dt}_b{w_bit}_g{grp}"], dt, f"b{w_bit} g{grp}")

@@ -179,3 +179,15 @@ def test_torch_cpu_port_matches_reference(golden):
             key = f"f16_{fmt}_{'sym' if sym else 'asym'}_g128"
             o = P.fp_codec_fake_quant(w, E, M, sym, 128)
             assert _nan_equal_bits(o.view(torch.int16).numpy().view(np.uint16), g[f"ql_{key}_out"], "f16"), key
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+def test_bfp_matches_reference(golden, dtype):
+    g = golden("golden_bfp")
+    w = g[f"w_{dtype}"]
+    for w_bit in (3, 4, 5, 6, 8, 12):
+        for grp in (32, 64, 128, 512):
+            r = O.bfp_fake_quant(w, dtype, w_bit, grp)
+            assert _nan_equal_bits(r["out"], g[f"{dtype}_b{w_bit}_g{grp}"], dtype), (w_bit, grp)
+    with pytest.raises(ValueError):
+        O.bfp_fake_quant(w, dtype, 4, -1)

@@ -32,6 +32,8 @@ CONFIGS = {
     "fp6e3m2g128": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=3, mant_bits=2, symmetric=True),
     "fp6e2m3g128": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=2, mant_bits=3, symmetric=True),
     "fprne_e2m1g128": dict(scheme=_lib.SCHEME_FP_RNE, group=128, exp_bits=2, mant_bits=1, symmetric=True),
+    "bfp4g128": dict(scheme=_lib.SCHEME_BFP, group=128, bits=4, symmetric=True),
+    "bfp6g64": dict(scheme=_lib.SCHEME_BFP, group=64, bits=6, symmetric=True),
     "int4pc_sym": dict(scheme=_lib.SCHEME_INT, group=-2, bits=4, symmetric=True),
     "int4pt_sym": dict(scheme=_lib.SCHEME_INT, group=-1, bits=4, symmetric=True),
 }
@@ -79,7 +81,7 @@ def main():
         for w in ws:
             o, k = w.shape
             G = _lib.num_segments(o, k, c["group"])
-            s = None if args.no_emit else torch.empty(G, dtype=dt, device=dev)
+            s = None if (args.no_emit or c["scheme"] == _lib.SCHEME_BFP) else torch.empty(G, dtype=dt, device=dev)
             z = None if (args.no_emit or c["symmetric"]) else torch.empty(G, dtype=dt, device=dev)
             keep.append((s, z))
             descs.append(_lib.matrix_desc(w, w, o, k, s, z))
