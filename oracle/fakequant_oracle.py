@@ -415,3 +415,142 @@ def bfp_fake_quant(w_bits: np.ndarray, dtype: str, w_bit: int, group: int):
     with np.errstate(over="ignore"):
         out = rD(rD(m.astype(np.float32), dtype) * scale * rD(sf, dtype), dtype)
     return dict(out=to_bits(out, dtype).reshape(shape))
+
+
+# --------------------------------------------------------------------------------------------
+# quant_dim = 1: groups run along the OUTPUT dimension      quant_linear.py:478-483, :640-647
+# --------------------------------------------------------------------------------------------
+
+
+def along_output_dim(fn, w_bits: np.ndarray, *args, **kw):
+    """The reference transposes the weight, quantises with groups along the (new) last dim and transposes
+    back (`weight.t()` ... `_reshape_back`, quant_linear.py:640-647).  `fn` is any oracle above that takes the
+    2-D bit array first; per-segment outputs (scales, ...) keep the transposed group order, like the reference."""
+    r = fn(np.ascontiguousarray(w_bits.T), *args, **kw)
+    r = dict(r)
+    r["out"] = np.ascontiguousarray(r["out"].T)
+    if "codes" in r and getattr(r["codes"], "ndim", 0) == 2:
+        r["codes"] = np.ascontiguousarray(r["codes"].T)
+    return r
+
+
+# --------------------------------------------------------------------------------------------
+# "approximate" aligned decode      quant_linear.py:237-285 (single), :288-363 (double), driver :470-632
+# --------------------------------------------------------------------------------------------
+
+
+def _wrap8(x):
+    """two's-complement wrap to int8: the double-approximate decoder keeps its fields in torch.int8 tensors
+    (quant_linear.py:311-313), so `1 << 7`, `val + offset` and left shifts overflow exactly like this."""
+    return ((np.asarray(x, dtype=np.int64) + 128) % 256) - 128
+
+
+def _rounding_rshift(val, shift, int8: bool = False):
+    """quant_linear.py:112-123: (val + (1 << (shift-1) if shift > 0 else 0)) >> shift, element-wise.
+    int8=True reproduces the overflow of the int8 tensors the double-approximate decoder passes in."""
+    val = np.asarray(val, dtype=np.int64)
+    shift = np.broadcast_to(np.asarray(shift, dtype=np.int64), val.shape)
+    off = np.where(shift > 0, np.int64(1) << np.minimum(np.maximum(shift - 1, 0), 40), 0)
+    if int8:
+        return _wrap8(val + _wrap8(off)) >> np.minimum(shift, 62)
+    return (val + off) >> shift
+
+
+def fp_decode_aligned(code, hi_align_start, hi_align_exp_field, tail_pad_bits, exp_bits, mant_bits, dtype):
+    """_fp_decode_aligned (quant_linear.py:237-285) with align_subnorm_exp_as_one=True,
+    limit_align_exp_to_field=True, decode_dtype = weight dtype -- the only way the driver calls it
+    (:499-509 etc.).  Returns a D array."""
+    bias = 2 ** (exp_bits - 1) - 1
+    code = np.asarray(code, dtype=np.uint8).astype(np.int64)
+    zero = code == 0
+    sign = (code >> (exp_bits + mant_bits)) & 1
+    ef = (code >> mant_bits) & ((1 << exp_bits) - 1)
+    mf = code & ((1 << mant_bits) - 1)
+    align_exp = np.where(ef == 0, 1, ef)
+    lead = np.where(ef == 0, 0, 1)
+    mant_full = (lead << mant_bits) | mf
+    if tail_pad_bits >= 0:
+        mant_padded = mant_full << tail_pad_bits
+    else:
+        mant_padded = _rounding_rshift(mant_full, abs(tail_pad_bits))
+    # value_normal is computed in the weight dtype (every op rounds to D)                        :268-269
+    exp_unb = rD(np.where(ef == 0, 1 - bias, ef - bias).astype(np.float32), dtype)
+    vn = rD(rD(mant_full.astype(np.float32), dtype) / np.float32(2.0 ** mant_bits), dtype)
+    vn = rD(vn * rD(np.exp2(exp_unb), dtype), dtype)
+    hi = (align_exp >= hi_align_start) & (align_exp <= hi_align_exp_field)
+    shift = np.clip(hi_align_exp_field - align_exp, 0, None)
+    mant_aligned = _rounding_rshift(mant_padded, shift)
+    # value_hi is fp32 (.float(), python scalars)                                                :281
+    vh = mant_aligned.astype(np.float32) / np.float32(2.0 ** (mant_bits + tail_pad_bits)) * np.float32(2.0 ** float(hi_align_exp_field - bias))
+    v = np.where(hi, vh, vn).astype(np.float32)
+    v = np.where(sign == 1, -v, v)
+    v = np.where(zero, np.float32(0.0), v)
+    return rD(v, dtype)  # `.to(self.weight.data.dtype)` at the call site
+
+
+def fp_decode_aligned_double(code_2d, hi_align_start, hi_align_exp_field, tail_pad_bits, exp_bits, mant_bits, dtype):
+    """fp_decode_aligned_double_approx (quant_linear.py:288-363) with align_subnorm_exp_as_one=True and
+    handle_max_outlier=True (the driver's arguments).  `code_2d` is the [G, group] code matrix; groups of 4
+    are taken along the flattened TRANSPOSE (:309, :329), the result has the shape of `code_2d`."""
+    bias = 2 ** (exp_bits - 1) - 1
+    code = np.asarray(code_2d, dtype=np.uint8).T.astype(np.int64)
+    shape_t = code.shape
+    zero = code == 0
+    sign = (code >> (exp_bits + mant_bits)) & 1
+    ef = (code >> mant_bits) & ((1 << exp_bits) - 1)
+    mf = code & ((1 << mant_bits) - 1)
+    align_exp = np.where(ef == 0, 1, ef)
+    lead = np.where(ef == 0, 0, 1)
+    mant_full = (lead << mant_bits) | mf
+    mant_padded = _wrap8(mant_full << tail_pad_bits) if tail_pad_bits >= 0 else _rounding_rshift(mant_full, abs(tail_pad_bits), int8=True)
+    if code.size % 4 != 0:
+        raise ValueError("double approx requires total elements divisible by 4")
+    e4 = align_exp.reshape(-1, 4)
+    m4 = mant_padded.reshape(-1, 4)
+    s4 = sign.reshape(-1, 4)
+    z4 = zero.reshape(-1, 4)
+    outl = (e4 < hi_align_start) | (e4 > hi_align_exp_field)
+    cnt = outl.sum(axis=1, keepdims=True)
+    gmax = e4.max(axis=1, keepdims=True)
+    target = np.where(cnt <= 1, hi_align_exp_field, gmax)
+    max_exp = (1 << exp_bits) - 1
+    has_max = ((e4 == max_exp) & outl).any(axis=1, keepdims=True)
+    target = np.where(has_max, max_exp, target)
+    shift = target - e4
+    right = _rounding_rshift(m4, np.clip(shift, 0, None), int8=True)
+    left = _wrap8(m4 << np.clip(-shift, 0, None))
+    cap = (((1 << (mant_bits + 1)) - 1) << tail_pad_bits) if tail_pad_bits >= 0 else (((1 << (mant_bits + 1)) - 1) >> abs(tail_pad_bits))
+    left = np.minimum(left, cap)
+    aligned = np.where(shift >= 0, right, left)
+    # value: D arithmetic (mant_aligned.to(dtype) / python float * pow(dtype))                   :357-358
+    hi_unb = rD((target - bias).astype(np.float32), dtype)
+    v = rD(rD(aligned.astype(np.float32), dtype) / np.float32(2.0 ** (mant_bits + tail_pad_bits)), dtype)
+    v = rD(v * rD(np.exp2(hi_unb), dtype), dtype)
+    v = np.where(s4 == 1, -v, v)
+    v = np.where(z4, np.float32(0.0), v)
+    return np.ascontiguousarray(v.reshape(shape_t).T.astype(np.float32))
+
+
+def fp_approx_fake_quant(w_bits: np.ndarray, dtype: str, exp_bits: int, mant_bits: int, group: int, hi_align_start: int, hi_align_exp_field: int,
+                         tail_pad_bits: int, double: bool):
+    """QuantLinear.quantize_weight_approximate for quant_dim = 0 (quant_linear.py:470-632): symmetric absmax
+    scale (:492-494), the ordinary encoder (:495), the aligned decoder, `decoded * scales` (:606).  Which
+    decoder runs follows the driver: FP4 with one exponent bit never uses the double variant (:496-509).
+    Use `along_output_dim(fp_approx_fake_quant, ...)` for quant_dim = 1."""
+    if group <= 0:
+        raise ValueError("approximate 仅支持分组量化，w_group_size 必须 > 0")
+    _, _, _, fmax = fp_format(exp_bits, mant_bits)
+    w = from_bits(w_bits, dtype)
+    shape = w.shape
+    g = _group_view(w, group)
+    with np.errstate(invalid="ignore", over="ignore"):
+        mx = rD(_clamp(_nanmax(np.abs(g)), lo=1e-5), dtype)
+        S = rD(_clamp(rD(_div(mx, np.float32(fmax)), dtype), lo=1e-5), dtype)
+        n = _clamp(rD(_div(g, S), dtype), -fmax, fmax)
+        code = fp_codec_encode(n, exp_bits, mant_bits, dtype)
+        if double and not (exp_bits == 1):
+            v = rD(fp_decode_aligned_double(code, hi_align_start, hi_align_exp_field, tail_pad_bits, exp_bits, mant_bits, dtype), dtype)
+        else:
+            v = fp_decode_aligned(code, hi_align_start, hi_align_exp_field, tail_pad_bits, exp_bits, mant_bits, dtype)
+        out = rD(v * S, dtype)
+    return dict(out=to_bits(out, dtype).reshape(shape), scales=to_bits(S, dtype).reshape(-1), scales_half=to_bits(S, F16).reshape(-1), codes=code.reshape(shape))

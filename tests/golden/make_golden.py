@@ -184,9 +184,75 @@ def gen_bfp(out: dict):
                 out[f"{dn}_b{w_bit}_g{grp}"] = bits_of(ql.weight.data)
 
 
+def build_input_tall(seed: int = 3, rows: int = 512, cols: int = 64) -> torch.Tensor:
+    """[512, 64] master for quant_dim = 1 (groups run down the 512 rows): random columns plus adversarial ones."""
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(rows, cols, generator=g) * 0.02
+    w[:, 40] = 0.0113
+    w[:, 41] = 0.0
+    w[:, 42] = torch.randn(rows, generator=g).abs() * 0.05 + 0.01
+    w[:, 43] = torch.randn(rows, generator=g) * 1e-6
+    w[:, 44] = torch.randn(rows, generator=g) * 30.0
+    w[::3, 45] = 0.0
+    w[1::6, 45] = -0.0
+    w[100, 46] = 2.0
+    w[:, 47] = torch.randn(rows, generator=g) * 1e-3
+    return w
+
+
+APPROX_CASES = [  # (name, weight_format, E, M, hi_align_start, hi_align_exp_field, tail_pad_bits, double)  -- from scripts/opt-6.7b/scripts_4.sh
+    ("e1m2_s", "fp4", 1, 2, 1, 1, 0, False),
+    ("e2m1_s", "fp4", 2, 1, 1, 1, 0, False),
+    ("e2m1_d", "fp4", 2, 1, 0, 2, 1, True),
+    ("e2m3_s", "fp6", 2, 3, 4, 7, 2, False),
+    ("e2m3_d", "fp6", 2, 3, 0, 2, -1, True),
+    ("e3m2_s", "fp6", 3, 2, 4, 7, 2, False),
+    ("e3m2_d", "fp6", 3, 2, 4, 6, 0, True),
+    ("e4m3_s", "fp8", 4, 3, 12, 15, 1, False),
+    ("e4m3_d", "fp8", 4, 3, 13, 15, -1, True),
+    ("e4m3_d0", "fp8", 4, 3, 12, 15, 0, True),
+]
+
+
+def gen_dim1_approx(out: dict):
+    """quant_dim = 1 for every scheme, and the approximate / double-approximate decode (quant_dim 0 and 1)."""
+    master = build_input_tall()
+    for dn, dt in TORCH_DT.items():
+        w = master.to(dt)
+        out[f"w_{dn}"] = bits_of(w)
+
+        def run(key, **kw):
+            lin = torch.nn.Linear(w.shape[1], w.shape[0], bias=False)
+            lin.weight.data = w.clone()
+            ql = quant_linear.QuantLinear.from_linear(lin, **kw)
+            out[f"{dn}_{key}_out"] = bits_of(ql.weight.data)
+            if ql.scales is not None:
+                out[f"{dn}_{key}_scales"] = bits_of(ql.scales.reshape(-1))
+            if ql.zeros is not None:
+                out[f"{dn}_{key}_zeros"] = bits_of(ql.zeros.reshape(-1))
+
+        for grp in (32, 128):
+            for sym in (False, True):
+                tag = "sym" if sym else "asym"
+                run(f"int4_{tag}_g{grp}_d1", w_bit=4, w_group_size=grp, symmetric=sym, weight_format="int", quant_dim=1)
+                quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
+                run(f"fp4_{tag}_g{grp}_d1", w_bit=4, w_group_size=grp, symmetric=sym, weight_format="fp4", quant_dim=1)
+                run(f"fp8_{tag}_g{grp}_d1", w_bit=8, w_group_size=grp, symmetric=sym, weight_format="fp8", quant_dim=1)
+            run(f"int8_asym_g{grp}_d1", w_bit=8, w_group_size=grp, symmetric=False, weight_format="int", quant_dim=1)
+            run(f"bfp4_g{grp}_d1", w_bit=4, w_group_size=grp, symmetric=True, weight_format="bfp", quant_dim=1)
+        run("int4_asym_pc_d1", w_bit=4, w_group_size=-2, symmetric=False, weight_format="int", quant_dim=1)
+        for name, wf, E, M, hs, hf, tp, dbl in APPROX_CASES:
+            quant_linear.configure_fp_formats(**{f"{wf}_exp_bits": E, f"{wf}_mantissa_bits": M})
+            kw = {f"{wf}_hi_align_start": hs, f"{wf}_hi_align_exp_field": hf, f"{wf}_tail_pad_bits": tp}
+            for qd in (0, 1):
+                grp = 32 if qd == 0 else 128
+                run(f"approx_{name}_g{grp}_d{qd}", w_bit=4, w_group_size=grp, symmetric=True, weight_format=wf, approximate=True, double_approximate=dbl, quant_dim=qd, **kw)
+            quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
+
+
 def main():
     torch.set_num_threads(8)
-    for name, fn in (("golden_int", gen_int), ("golden_fp_chain", gen_fp_chain), ("golden_fp_tables", gen_fp_tables), ("golden_fp_rne", gen_fp_rne), ("golden_bfp", gen_bfp)):
+    for name, fn in (("golden_int", gen_int), ("golden_fp_chain", gen_fp_chain), ("golden_fp_tables", gen_fp_tables), ("golden_fp_rne", gen_fp_rne), ("golden_bfp", gen_bfp), ("golden_dim1_approx", gen_dim1_approx)):
         d = {}
         fn(d)
         d["_meta"] = np.array([f"torch {torch.__version__}; reference at {REF}; cpu"], dtype="U")

@@ -191,3 +191,53 @@ def test_bfp_matches_reference(golden, dtype):
             assert _nan_equal_bits(r["out"], g[f"{dtype}_b{w_bit}_g{grp}"], dtype), (w_bit, grp)
     with pytest.raises(ValueError):
         O.bfp_fake_quant(w, dtype, 4, -1)
+
+
+APPROX_CASES = [  # must mirror tests/golden/make_golden.py
+    ("e1m2_s", 1, 2, 1, 1, 0, False),
+    ("e2m1_s", 2, 1, 1, 1, 0, False),
+    ("e2m1_d", 2, 1, 0, 2, 1, True),
+    ("e2m3_s", 2, 3, 4, 7, 2, False),
+    ("e2m3_d", 2, 3, 0, 2, -1, True),
+    ("e3m2_s", 3, 2, 4, 7, 2, False),
+    ("e3m2_d", 3, 2, 4, 6, 0, True),
+    ("e4m3_s", 4, 3, 12, 15, 1, False),
+    ("e4m3_d", 4, 3, 13, 15, -1, True),
+    ("e4m3_d0", 4, 3, 12, 15, 0, True),
+]
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+def test_quant_dim1_matches_reference(golden, dtype):
+    g = golden("golden_dim1_approx")
+    w = g[f"w_{dtype}"]
+    for grp in (32, 128):
+        for sym in (False, True):
+            tag = "sym" if sym else "asym"
+            r = O.along_output_dim(O.int_fake_quant, w, dtype, 4, not sym, grp)
+            assert _nan_equal_bits(r["out"], g[f"{dtype}_int4_{tag}_g{grp}_d1_out"], dtype), (grp, sym)
+            assert _nan_equal_bits(r["scales"], g[f"{dtype}_int4_{tag}_g{grp}_d1_scales"], dtype), (grp, sym)
+            for fmt, (E, M) in (("fp4", (2, 1)), ("fp8", (4, 3))):
+                r = O.along_output_dim(O.fp_codec_fake_quant, w, dtype, E, M, sym, grp)
+                assert _nan_equal_bits(r["out"], g[f"{dtype}_{fmt}_{tag}_g{grp}_d1_out"], dtype), (fmt, grp, sym)
+                assert np.array_equal(r["scales_half"], g[f"{dtype}_{fmt}_{tag}_g{grp}_d1_scales"]), (fmt, grp, sym)
+        r = O.along_output_dim(O.int_fake_quant, w, dtype, 8, True, grp)
+        assert _nan_equal_bits(r["out"], g[f"{dtype}_int8_asym_g{grp}_d1_out"], dtype)
+        r = O.along_output_dim(O.bfp_fake_quant, w, dtype, 4, grp)
+        assert _nan_equal_bits(r["out"], g[f"{dtype}_bfp4_g{grp}_d1_out"], dtype)
+    r = O.along_output_dim(O.int_fake_quant, w, dtype, 4, True, -2)
+    assert _nan_equal_bits(r["out"], g[f"{dtype}_int4_asym_pc_d1_out"], dtype)
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+@pytest.mark.parametrize("case", APPROX_CASES, ids=[c[0] for c in APPROX_CASES])
+def test_approximate_decode_matches_reference(golden, dtype, case):
+    name, E, M, hs, hf, tp, dbl = case
+    g = golden("golden_dim1_approx")
+    w = g[f"w_{dtype}"]
+    r = O.fp_approx_fake_quant(w, dtype, E, M, 32, hs, hf, tp, dbl)
+    assert _nan_equal_bits(r["out"], g[f"{dtype}_approx_{name}_g32_d0_out"], dtype), "quant_dim 0"
+    assert np.array_equal(r["scales_half"], g[f"{dtype}_approx_{name}_g32_d0_scales"])
+    r = O.along_output_dim(O.fp_approx_fake_quant, w, dtype, E, M, 128, hs, hf, tp, dbl)
+    assert _nan_equal_bits(r["out"], g[f"{dtype}_approx_{name}_g128_d1_out"], dtype), "quant_dim 1"
+    assert np.array_equal(r["scales_half"], g[f"{dtype}_approx_{name}_g128_d1_scales"])
