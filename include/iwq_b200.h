@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define IWQ_ABI_VERSION 1
+#define IWQ_ABI_VERSION 2
 
 /* storage dtype of weights, scales and zeros */
 enum { IWQ_F16 = 0, IWQ_BF16 = 1 };
@@ -69,6 +69,15 @@ typedef struct iwq_config {
   int32_t symmetric; /* 1: absmax scale, no zero point (zero_point=False); 0: min/max (zero_point=True)*/
   int32_t group;     /* > 0, IWQ_GROUP_PER_TENSOR, IWQ_GROUP_PER_CHANNEL                               */
   int32_t variant;   /* kernel variant: 0 = default (TMA bulk-copy staged), 1 = direct global loads    */
+  int32_t quant_dim; /* 0: segments run along `cols` (default); 1: along `rows`, i.e. the reference's
+                        quant_dim=1 "transpose, group, transpose back" (quant_linear.py:640-647); `group`
+                        then divides `rows`, per-channel means one segment per COLUMN                   */
+  int32_t approx;    /* FP_CODEC only: 0 exact decode; 1 aligned ("approximate") decode, _fp_decode_aligned
+                        quant_linear.py:237-285; 2 double-approximate, :288-363 (quant_dim 1 only).  Both
+                        force the symmetric absmax scale like quantize_weight_approximate (:470-632)     */
+  int32_t hi_align_start;     /* approx: fp{4,6,8}_hi_align_start                                       */
+  int32_t hi_align_exp_field; /* approx: fp{4,6,8}_hi_align_exp_field                                   */
+  int32_t tail_pad_bits;      /* approx: fp{4,6,8}_tail_pad_bits (may be negative)                      */
 } iwq_config_t;
 
 typedef struct iwq_matrix {

@@ -92,6 +92,18 @@ static inline int build_quant_consts(const iwq_config_t* cfg, QuantConsts* c, in
   if (rne && dt != IWQ_F16) return fail(IWQ_ERR_UNSUPPORTED, "FP_RNE flavour is fp16 only (the reference casts to fp16: fp4_quantize_cpu.py:48-49)");
   if (rne) c->symmetric = 1;
   c->flavour_rne = rne ? 1 : 0;
+  if (cfg->approx) {
+    if (rne) return fail(IWQ_ERR_INVALID, "approximate decode applies to the FP_CODEC scheme only");
+    if (cfg->approx < 0 || cfg->approx > 2) return fail(IWQ_ERR_INVALID, "approx must be 0, 1 or 2");
+    if (cfg->group <= 0) return fail(IWQ_ERR_INVALID, "approximate 仅支持分组量化，w_group_size 必须 > 0");  // quant_linear.py:475-476
+    c->symmetric = 1;  // quantize_weight_approximate always uses the absmax scale (:492-494)
+    // FP4 with a single exponent bit never takes the double variant (:496-509)
+    c->approx = (cfg->approx == 2 && E == 1) ? 1 : cfg->approx;
+    c->hi_start = cfg->hi_align_start;
+    c->hi_field = cfg->hi_align_exp_field;
+    c->tail_pad = cfg->tail_pad_bits;
+    if (c->tail_pad < -8 || c->tail_pad > 8) return fail(IWQ_ERR_INVALID, "tail_pad_bits out of range");
+  }
   const int MB = dt == IWQ_F16 ? 10 : 7, DB = dt == IWQ_F16 ? 15 : 127;
   const int max_field = dt == IWQ_F16 ? 30 : 254;
   const int bias = (1 << (E - 1)) - 1, emin = 1 - bias, emax = (1 << E) - 1 - bias;
@@ -150,6 +162,36 @@ static inline int build_quant_consts(const iwq_config_t* cfg, QuantConsts* c, in
 }
 
 
+// _fp_decode_aligned (quant_linear.py:237-285; align_subnorm_exp_as_one=True, limit_align_exp_to_field=True,
+// decode_dtype = weight dtype, as the driver calls it) for the code of a POSITIVE grid value: the single
+// "approximate" mode only changes which value a code decodes to, so it is folded into the step table.
+template <int DT>
+static inline uint16_t approx_decode_single(uint16_t vbits, const QuantConsts& c) {
+  const int E = c.exp_bits, M = c.mant_bits, bias = (1 << (E - 1)) - 1;
+  const uint32_t code = fp_code_of<DT>(vbits, E, M);
+  if (code == 0) return 0;
+  const int ef = (int)((code >> M) & ((1u << E) - 1u)), mf = (int)(code & ((1u << M) - 1u));
+  const int align_exp = ef == 0 ? 1 : ef;
+  const int mant_full = ((ef == 0 ? 0 : 1) << M) | mf;
+  int mant_padded;
+  if (c.tail_pad >= 0) {
+    mant_padded = mant_full << c.tail_pad;
+  } else {
+    const int sh = -c.tail_pad;
+    mant_padded = (mant_full + (1 << (sh - 1))) >> sh;
+  }
+  float v;
+  if (align_exp >= c.hi_start && align_exp <= c.hi_field) {
+    const int shift = c.hi_field - align_exp;
+    const int aligned = shift > 0 ? (mant_padded + (1 << (shift - 1))) >> shift : mant_padded;
+    v = (float)aligned / ldexpf(1.0f, M + c.tail_pad) * ldexpf(1.0f, c.hi_field - bias);       // fp32  (:281)
+  } else {
+    float a = rD<DT>(rD<DT>((float)mant_full) / ldexpf(1.0f, M));                               // D ops (:268-269)
+    v = rD<DT>(a * rD<DT>(ldexpf(1.0f, ef == 0 ? 1 - bias : ef - bias)));
+  }
+  return DType<DT>::from_f32(v);
+}
+
 // Step table (see FpStep): run the table-walk quantiser grid() on every bit pattern of every interval and
 // record the single value change.  Returns false if some interval changes value more than once (would mean
 // the format violates the assumption; none of the supported ones does).
@@ -182,6 +224,10 @@ static inline bool build_step_table_t(const QuantConsts& c, FpStep* out) {
       } else if (v != e.above) {
         return false;
       }
+    }
+    if (c.approx == 1) {
+      e.below = approx_decode_single<DT>(e.below, c);
+      e.above = approx_decode_single<DT>(e.above, c);
     }
     out[i] = e;
   }

@@ -60,13 +60,14 @@ static int build_consts(const iwq_config_t* cfg, QuantConsts* c, int* kind) {
 // minifloat LUT cache: one small device buffer per (device, dtype, E, M, flavour), built on first use
 // ------------------------------------------------------------------------------------------------
 static std::mutex g_lut_mu;
-static std::map<std::tuple<int, int, int, int, int>, FpStep*> g_luts;
+static std::map<std::tuple<int, int, int, int, int, int, int, int, int>, FpStep*> g_luts;
 
 static int get_fp_lut(const iwq_config_t* cfg, const QuantConsts& qc, cudaStream_t st, const FpStep** out) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
-  auto key = std::make_tuple(dev, cfg->dtype, cfg->exp_bits, cfg->mant_bits, qc.flavour_rne);
+  auto key = std::make_tuple(dev, cfg->dtype, cfg->exp_bits, cfg->mant_bits, qc.flavour_rne, qc.approx == 1 ? 1 : 0,
+                             qc.approx == 1 ? qc.hi_start : 0, qc.approx == 1 ? qc.hi_field : 0, qc.approx == 1 ? qc.tail_pad : 0);
   std::lock_guard<std::mutex> lk(g_lut_mu);
   auto it = g_luts.find(key);
   if (it != g_luts.end()) {
@@ -129,6 +130,27 @@ static cudaError_t dispatch_row(int dt, int kind, const LaunchParams& p, bool sy
     default: return launch_row<IWQ_BF16, KIND_INT_GENERIC>(p, sym, consumers, t, st);
   }
 }
+
+static cudaError_t dispatch_col(int dt, int kind, const LaunchParams& p, bool sym, const LaunchTuning& t, cudaStream_t st) {
+  if (dt == IWQ_F16) {
+    switch (kind) {
+      case KIND_INT_FAST: return launch_col<IWQ_F16, KIND_INT_FAST>(p, sym, t, st);
+      case KIND_FP: return launch_col<IWQ_F16, KIND_FP>(p, sym, t, st);
+      case KIND_BFP: return launch_col<IWQ_F16, KIND_BFP>(p, sym, t, st);
+      default: return launch_col<IWQ_F16, KIND_INT_GENERIC>(p, sym, t, st);
+    }
+  }
+  switch (kind) {
+    case KIND_INT_FAST: return launch_col<IWQ_BF16, KIND_INT_FAST>(p, sym, t, st);
+    case KIND_INT_WIDE: return launch_col<IWQ_BF16, KIND_INT_WIDE>(p, sym, t, st);
+    case KIND_FP: return launch_col<IWQ_BF16, KIND_FP>(p, sym, t, st);
+    case KIND_BFP: return launch_col<IWQ_BF16, KIND_BFP>(p, sym, t, st);
+    default: return launch_col<IWQ_BF16, KIND_INT_GENERIC>(p, sym, t, st);
+  }
+}
+
+// quant_dim = 1 (segments down the rows): one launch of col_kernel over all matrices
+static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, LaunchParams& p, int kind, void* workspace, size_t ws_bytes, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // work-list construction
@@ -316,6 +338,16 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
     if (rc) return rc;
     p.lut_smem_bytes = (uint32_t)(((size_t)p.qc.lut_n * sizeof(FpStep) + 1023) & ~(size_t)1023);
   }
+  if (p.qc.approx == 2) {
+    if (cfg->quant_dim != 1) return fail(IWQ_ERR_UNSUPPORTED, "double-approximate decode is implemented for quant_dim = 1 only");
+    return fail(IWQ_ERR_UNSUPPORTED, "double-approximate decode is not implemented yet");
+  }
+  if (cfg->quant_dim == 1 && cfg->group != IWQ_GROUP_PER_TENSOR) {
+    if (given_range || minmax_only) return fail(IWQ_ERR_INVALID, "range entry points are for per-tensor granularity");
+    p.status = status;
+    return run_col(cfg, ms, n, p, kind, workspace, ws_bytes, st);
+  }
+  if (cfg->quant_dim != 0 && cfg->quant_dim != 1) return fail(IWQ_ERR_INVALID, "quant_dim must be 0 or 1");
   Plan pl;
   rc = make_plan(cfg, ms[0].cols, p.lut_smem_bytes, &pl);
   if (rc) return rc;
@@ -366,6 +398,44 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
     e = dispatch_row(cfg->dtype, kind, p, sym, pl.consumers, tune, st);
   }
   if (e != cudaSuccess) return fail_cuda(e, "fake-quant kernel launch");
+  return IWQ_OK;
+}
+
+static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, LaunchParams& p, int kind, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  std::vector<Job> jobs;
+  uint64_t units = 0;
+  for (int i = 0; i < n; ++i) {
+    int rc = check_matrix(&ms[i]);
+    if (rc) return rc;
+    const int64_t rows = ms[i].rows, cols = ms[i].cols;
+    int64_t g;
+    if (cfg->group > 0) {
+      if (rows % cfg->group != 0) return fail(IWQ_ERR_INDIVISIBLE, "rows is not divisible by the group size (quant_dim = 1)");
+      g = cfg->group;
+    } else if (cfg->group == IWQ_GROUP_PER_CHANNEL) {
+      g = rows;
+    } else {
+      return fail(IWQ_ERR_INVALID, "Invalid w_group_size");
+    }
+    if (cols % 8 != 0) return fail(IWQ_ERR_UNSUPPORTED, "quant_dim = 1 needs cols to be a multiple of 8 (16-byte vectors)");
+    if (g >= (1ll << 31)) return fail(IWQ_ERR_INVALID, "segment too long");
+    Job j = make_job(&ms[i], (uint32_t)units);
+    units += (uint64_t)(rows / g) * (uint64_t)((cols + kColTile - 1) / kColTile);
+    if (units >= 0xFFFFFFFFull) return fail(IWQ_ERR_INVALID, "too much work for one launch");
+    jobs.push_back(j);
+  }
+  p.n_jobs = n;
+  p.total_units = (uint32_t)units;
+  p.single = jobs[0];
+  p.jobs = nullptr;
+  p.col_group = cfg->group > 0 ? (uint32_t)cfg->group : 0u;
+  int rc = upload_jobs(jobs, workspace, ws_bytes, &p, st);
+  if (rc) return rc;
+  LaunchTuning tune;
+  tune.stages = 0;
+  tune.ctas_per_sm = 0;
+  cudaError_t e = dispatch_col(cfg->dtype, kind, p, p.qc.symmetric != 0, tune, st);
+  if (e != cudaSuccess) return fail_cuda(e, "column-group kernel launch");
   return IWQ_OK;
 }
 

@@ -62,7 +62,7 @@ struct LaunchParams {
   int32_t* status;
   const FpStep* lut;       // KIND_FP: device step table (qc.lut_n entries), copied into shared memory by every CTA
   uint32_t lut_smem_bytes; // bytes reserved for it in front of the ring (multiple of 1024; 0 for INT kinds)
-  uint32_t pad0;
+  uint32_t col_group;      // quant_dim = 1: rows per segment (0: the whole column, i.e. per-channel)
   QuantConsts qc;
 };
 
@@ -754,6 +754,228 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
       if (++stage == n_stages) {
         stage = 0;
         phase ^= 1u;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// quant_dim = 1: segments run DOWN the rows (reference: transpose, group along the last dim, transpose back;
+// quant_linear.py:478-483, :640-647).  No transpose here: columns are independent, so the whole path is
+// vectorised ACROSS columns.
+//
+//   tile = `g` rows x 256 columns.  A lane owns 8 adjacent columns (one 16-byte vector per row: a warp reads
+//   512 contiguous bytes of a row), the 8 warps take rows k = warp, warp+8, ...  The range of a column is a
+//   plain element-wise HMNMX2 over the rows a warp visits (no shuffles at all), combined across the warps
+//   through shared memory.  Every lane then derives the parameters of its 8 columns; because the two halves of
+//   a packed register now belong to different segments, the element stage uses the PAIR forms (per-half scale
+//   and reciprocal).  The second sweep re-reads the tile (64 KB for g = 128: served by L2) and stores in place.
+// Units of the work list: tiles, column tile fastest.  blockDim.x = 256.
+// ------------------------------------------------------------------------------------------------
+template <int DT, int KIND>
+struct PreparedPair;
+
+template <int DT, int KIND>
+struct PreparedPairInt {
+  IntFast<DT, KIND == KIND_INT_WIDE, true> f;
+  __device__ __forceinline__ void setup2(float mxa, float mna, float mxb, float mnb, const QuantConsts& c, bool sym, const FpStep*, float* sa, float* za, float* sb,
+                                         float* zb, bool* bad) {
+    IntQ qa = int_segment_params<DT>(mxa, mna, c, sym), qb = int_segment_params<DT>(mxb, mnb, c, sym);
+    f.setup2(qa, qb);
+    *sa = qa.s; *za = qa.z; *sb = qb.s; *zb = qb.z;
+    *bad = qa.bad || qb.bad;
+  }
+  __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const {
+    typename DType<DT>::T2 d;
+    return f.apply(w2, &d);
+  }
+};
+template <int DT>
+struct PreparedPair<DT, KIND_INT_FAST> : PreparedPairInt<DT, KIND_INT_FAST> {};
+template <int DT>
+struct PreparedPair<DT, KIND_INT_WIDE> : PreparedPairInt<DT, KIND_INT_WIDE> {};
+
+template <int DT>
+struct PreparedPair<DT, KIND_INT_GENERIC> {
+  IntQ qa, qb;
+  __device__ __forceinline__ void setup2(float mxa, float mna, float mxb, float mnb, const QuantConsts& c, bool sym, const FpStep*, float* sa, float* za, float* sb,
+                                         float* zb, bool* bad) {
+    qa = int_segment_params<DT>(mxa, mna, c, sym);
+    qb = int_segment_params<DT>(mxb, mnb, c, sym);
+    *sa = qa.s; *za = qa.z; *sb = qb.s; *zb = qb.z;
+    *bad = qa.bad || qb.bad;
+  }
+  __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts& c) const {
+    float k;
+    const uint32_t lo = int_generic_elem<DT>((uint16_t)(w2 & 0xFFFFu), qa, c, &k);
+    const uint32_t hi = int_generic_elem<DT>((uint16_t)(w2 >> 16), qb, c, &k);
+    return lo | (hi << 16);
+  }
+};
+
+template <int DT>
+struct PreparedPair<DT, KIND_FP> {
+  FpTable<DT, true> f;
+  __device__ __forceinline__ void setup2(float mxa, float mna, float mxb, float mnb, const QuantConsts& c, bool, const FpStep* steps, float* sa, float* za, float* sb,
+                                         float* zb, bool* bad) {
+    FpQ qa = fp_segment_params<DT>(mxa, mna, c), qb = fp_segment_params<DT>(mxb, mnb, c);
+    f.setup2(qa, qb, c, steps);
+    *sa = qa.S; *za = qa.mid; *sb = qb.S; *zb = qb.mid;
+    *bad = qa.bad || qb.bad;
+  }
+  __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const {
+    typename DType<DT>::T2 v;
+    return f.slow_div ? f.template apply<true>(w2, &v) : f.template apply<false>(w2, &v);
+  }
+};
+
+template <int DT>
+struct PreparedPair<DT, KIND_BFP> {
+  BfpApply<DT, true> f;
+  __device__ __forceinline__ void setup2(float mxa, float, float mxb, float, const QuantConsts& c, bool, const FpStep*, float* sa, float* za, float* sb, float* zb,
+                                         bool* bad) {
+    f.setup2(bfp_segment_params<DT>(mxa, c), bfp_segment_params<DT>(mxb, c), c);
+    *sa = 0.f; *za = 0.f; *sb = 0.f; *zb = 0.f;
+    *bad = false;
+  }
+  __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const { return f.apply(w2); }
+};
+
+constexpr int kColTile = 256;  // columns per tile: 32 lanes x 8
+
+template <int DT, int KIND, bool SYM>
+__global__ void __launch_bounds__(256) col_kernel(const __grid_constant__ LaunchParams p) {
+  using T2 = typename DType<DT>::T2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // [2 parities][8 warps][2 (max | min)][32 lanes] uint4 = 16 KB, then the minifloat step table
+  uint4* part = reinterpret_cast<uint4*>(smem);
+  const FpStep* s_tbl = nullptr;
+  if (KIND == KIND_FP) s_tbl = load_fp_lut(p, smem + 16384);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ident_max = SYM ? 0u : (DT == IWQ_F16 ? 0xFC00FC00u : 0xFF80FF80u);  // {0,0} | {-inf,-inf}
+  const uint32_t ident_min = DT == IWQ_F16 ? 0x7C007C00u : 0x7F807F80u;                // {+inf,+inf}
+  int cur = -1;
+  Job jb;
+  uint32_t par = 0;
+  for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+    advance_job(p, tile, &cur, &jb);
+    const uint32_t cols = jb.row_bytes >> 1;
+    const uint32_t rows = (uint32_t)(jb.bytes / jb.row_bytes);
+    const uint32_t g = p.col_group ? p.col_group : rows;
+    const uint32_t n_ct = (cols + kColTile - 1) / kColTile;
+    const uint32_t local = tile - jb.first_unit;
+    const uint32_t rb = local / n_ct, ct = local - rb * n_ct;
+    const uint32_t col = ct * kColTile + (uint32_t)lane * 8u;
+    const bool live = col < cols;  // cols is a multiple of 8 (checked on the host)
+    const size_t off = (size_t)rb * g * jb.row_bytes + (size_t)col * 2;
+    const uint8_t* src = jb.src + off;
+    uint8_t* dst = jb.dst + off;
+
+    // ---- sweep 1: per-column range over the rows this warp visits ----
+    uint32_t mx[4] = {ident_max, ident_max, ident_max, ident_max};
+    uint32_t mn[4] = {ident_min, ident_min, ident_min, ident_min};
+    if (live) {
+      uint32_t k = (uint32_t)warp;
+      for (; k + 24 < g; k += 32) {  // 4 rows in flight
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldg128(src + (size_t)(k + 8 * u) * jb.row_bytes);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (SYM) {
+              mx[j] = as_u32(__hmax2_nan(from_u32<T2>(mx[j]), from_u32<T2>(w4[j] & 0x7FFF7FFFu)));
+            } else {
+              mx[j] = as_u32(__hmax2_nan(from_u32<T2>(mx[j]), from_u32<T2>(w4[j])));
+              mn[j] = as_u32(__hmin2_nan(from_u32<T2>(mn[j]), from_u32<T2>(w4[j])));
+            }
+          }
+        }
+      }
+      for (; k < g; k += 8) {
+        const uint4 v = ldg128(src + (size_t)k * jb.row_bytes);
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (SYM) {
+            mx[j] = as_u32(__hmax2_nan(from_u32<T2>(mx[j]), from_u32<T2>(w4[j] & 0x7FFF7FFFu)));
+          } else {
+            mx[j] = as_u32(__hmax2_nan(from_u32<T2>(mx[j]), from_u32<T2>(w4[j])));
+            mn[j] = as_u32(__hmin2_nan(from_u32<T2>(mn[j]), from_u32<T2>(w4[j])));
+          }
+        }
+      }
+    }
+    uint4* mine = part + ((par * 8 + warp) * 2) * 32 + lane;
+    mine[0] = make_uint4(mx[0], mx[1], mx[2], mx[3]);
+    if (!SYM) mine[32] = make_uint4(mn[0], mn[1], mn[2], mn[3]);
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const uint4* o = part + ((par * 8 + w) * 2) * 32 + lane;
+      const uint4 a = o[0];
+      mx[0] = as_u32(__hmax2_nan(from_u32<T2>(mx[0]), from_u32<T2>(a.x)));
+      mx[1] = as_u32(__hmax2_nan(from_u32<T2>(mx[1]), from_u32<T2>(a.y)));
+      mx[2] = as_u32(__hmax2_nan(from_u32<T2>(mx[2]), from_u32<T2>(a.z)));
+      mx[3] = as_u32(__hmax2_nan(from_u32<T2>(mx[3]), from_u32<T2>(a.w)));
+      if (!SYM) {
+        const uint4 b = o[32];
+        mn[0] = as_u32(__hmin2_nan(from_u32<T2>(mn[0]), from_u32<T2>(b.x)));
+        mn[1] = as_u32(__hmin2_nan(from_u32<T2>(mn[1]), from_u32<T2>(b.y)));
+        mn[2] = as_u32(__hmin2_nan(from_u32<T2>(mn[2]), from_u32<T2>(b.z)));
+        mn[3] = as_u32(__hmin2_nan(from_u32<T2>(mn[3]), from_u32<T2>(b.w)));
+      }
+    }
+    par ^= 1u;  // the next tile writes the other half: one barrier per tile is enough
+
+    // ---- per-column parameters: 4 packed pairs per lane ----
+    PreparedPair<DT, KIND> prep[4];
+    bool any_bad = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float mxa = DType<DT>::to_f32((uint16_t)(mx[j] & 0xFFFFu)), mxb = DType<DT>::to_f32((uint16_t)(mx[j] >> 16));
+      const float mna = DType<DT>::to_f32((uint16_t)(mn[j] & 0xFFFFu)), mnb = DType<DT>::to_f32((uint16_t)(mn[j] >> 16));
+      float sa, za, sb, zb;
+      bool bad;
+      prep[j].setup2(mxa, SYM ? -mxa : mna, mxb, SYM ? -mxb : mnb, p.qc, SYM, s_tbl, &sa, &za, &sb, &zb, &bad);
+      any_bad |= bad;
+      if (live && warp == 0) {
+        // segment order of the reference for quant_dim = 1: column-major over (column, row block)
+        const size_t n_rb = rows / g;
+        const size_t ga = (size_t)(col + 2 * j) * n_rb + rb, gb = ga + n_rb;
+        if (jb.scales) {
+          reinterpret_cast<uint16_t*>(jb.scales)[ga] = DType<DT>::from_f32(sa);
+          reinterpret_cast<uint16_t*>(jb.scales)[gb] = DType<DT>::from_f32(sb);
+        }
+        if (jb.zeros) {
+          reinterpret_cast<uint16_t*>(jb.zeros)[ga] = DType<DT>::from_f32(za);
+          reinterpret_cast<uint16_t*>(jb.zeros)[gb] = DType<DT>::from_f32(zb);
+        }
+      }
+    }
+    if (live && any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
+
+    // ---- sweep 2: quantise (tile re-read from L2), store in place ----
+    if (live) {
+      uint32_t k = (uint32_t)warp;
+      for (; k + 8 < g; k += 16) {  // 2 rows in flight
+        const uint4 v0 = ldg128(src + (size_t)k * jb.row_bytes);
+        const uint4 v1 = ldg128(src + (size_t)(k + 8) * jb.row_bytes);
+        uint4 o0, o1;
+        o0.x = prep[0].apply(v0.x, p.qc); o0.y = prep[1].apply(v0.y, p.qc); o0.z = prep[2].apply(v0.z, p.qc); o0.w = prep[3].apply(v0.w, p.qc);
+        o1.x = prep[0].apply(v1.x, p.qc); o1.y = prep[1].apply(v1.y, p.qc); o1.z = prep[2].apply(v1.z, p.qc); o1.w = prep[3].apply(v1.w, p.qc);
+        stg128(dst + (size_t)k * jb.row_bytes, o0);
+        stg128(dst + (size_t)(k + 8) * jb.row_bytes, o1);
+      }
+      for (; k < g; k += 8) {
+        const uint4 v0 = ldg128(src + (size_t)k * jb.row_bytes);
+        uint4 o0;
+        o0.x = prep[0].apply(v0.x, p.qc); o0.y = prep[1].apply(v0.y, p.qc); o0.z = prep[2].apply(v0.z, p.qc); o0.w = prep[3].apply(v0.w, p.qc);
+        stg128(dst + (size_t)k * jb.row_bytes, o0);
       }
     }
   }

@@ -65,7 +65,26 @@ cudaError_t launch_seg(const LaunchParams& p, bool sym, bool given, int variant,
 template <int DT, int KIND>
 cudaError_t launch_row(const LaunchParams& p, bool sym, int consumers, const LaunchTuning& tune, cudaStream_t st);
 
+template <int DT, int KIND>
+cudaError_t launch_col(const LaunchParams& p, bool sym, const LaunchTuning& tune, cudaStream_t st);
+
 #ifdef IWQ_INSTANTIATE
+
+template <int DT, int KIND, bool SYM>
+static cudaError_t launch_col_one(LaunchParams p, const LaunchTuning& tune, cudaStream_t st) {
+  auto k = col_kernel<DT, KIND, SYM>;
+  const size_t smem = 16384 + p.lut_smem_bytes;
+  int grid = 0;
+  cudaError_t e = persistent_grid(k, 256, smem, tune.ctas_per_sm, p.total_units, &grid);
+  if (e != cudaSuccess) return e;
+  k<<<grid, 256, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int DT, int KIND>
+cudaError_t launch_col(const LaunchParams& p, bool sym, const LaunchTuning& tune, cudaStream_t st) {
+  return sym ? launch_col_one<DT, KIND, true>(p, tune, st) : launch_col_one<DT, KIND, false>(p, tune, st);
+}
 
 template <int DT, int KIND, bool SYM, bool GIVEN>
 static cudaError_t launch_seg_one(LaunchParams p, int variant, const LaunchTuning& tune, cudaStream_t st) {
@@ -118,7 +137,8 @@ cudaError_t launch_row(const LaunchParams& p, bool sym, int consumers, const Lau
 
 #define IWQ_INSTANTIATE_KIND(DT, KIND)                                                                                       \
   template cudaError_t launch_seg<DT, KIND>(const LaunchParams&, bool, bool, int, const LaunchTuning&, cudaStream_t);       \
-  template cudaError_t launch_row<DT, KIND>(const LaunchParams&, bool, int, const LaunchTuning&, cudaStream_t);
+  template cudaError_t launch_row<DT, KIND>(const LaunchParams&, bool, int, const LaunchTuning&, cudaStream_t);   \
+  template cudaError_t launch_col<DT, KIND>(const LaunchParams&, bool, const LaunchTuning&, cudaStream_t);
 
 #endif  // IWQ_INSTANTIATE
 

@@ -176,6 +176,42 @@ IWQ_HD typename DType<DT>::T2 ieee_quot2(typename DType<DT>::T2 w2, float s) {
   return DType<DT>::from_f32x2(ieee_div(w.x, s), ieee_div(w.y, s));
 }
 
+// Pair forms: the two halves of a packed register belong to DIFFERENT segments (quant_dim = 1: adjacent
+// columns), so scale and reciprocal are per half.
+template <int DT>
+IWQ_HD typename DType<DT>::T2 fast_quot2(typename DType<DT>::T2 w2, float2 s, float2 r) {
+  float2 w = DType<DT>::to_f32x2(w2);
+#ifdef __CUDA_ARCH__
+  const float2 ns = make_float2(-s.x, -s.y);
+  float2 t = __fmul2_rn(w, r);
+  float2 e = __ffma2_rn(ns, t, w);
+  float2 q = __ffma2_rn(r, e, t);
+  return DType<DT>::from_f32x2(q.x, q.y);
+#else
+  return DType<DT>::from_f32x2(fast_quot(w.x, s.x, r.x), fast_quot(w.y, s.y, r.y));
+#endif
+}
+template <int DT>
+IWQ_HD typename DType<DT>::T2 ieee_quot2(typename DType<DT>::T2 w2, float2 s) {
+  float2 w = DType<DT>::to_f32x2(w2);
+  return DType<DT>::from_f32x2(ieee_div(w.x, s.x), ieee_div(w.y, s.y));
+}
+
+template <bool PAIR>
+struct PerHalf {  // a per-segment fp32 constant: one value, or one per half of a packed pair
+  using F = float;
+  static IWQ_HD float make(float a, float) { return a; }
+  static IWQ_HD float lo(float v) { return v; }
+  static IWQ_HD float hi(float v) { return v; }
+};
+template <>
+struct PerHalf<true> {
+  using F = float2;
+  static IWQ_HD float2 make(float a, float b) { return make_float2(a, b); }
+  static IWQ_HD float lo(float2 v) { return v.x; }
+  static IWQ_HD float hi(float2 v) { return v.y; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // configuration constants shared by all segments of a launch (built on the host: iwq_host.cu)
 // ------------------------------------------------------------------------------------------------
@@ -205,6 +241,7 @@ struct QuantConsts {
   uint16_t tiny_bits;      // D bits of 2^(emin - M - 3): magnitudes are clamped up to it before the table lookup
   int32_t tbl_base;        // biased D exponent of table entry 0
   int32_t tbl_n;
+  int32_t approx, hi_start, hi_field, tail_pad;  // aligned ("approximate") decode, quant_linear.py:237-363
   int32_t bfp_target;      // BFP: mantissa bits kept incl. the leading one = min(w_bit-1, 11)   quant_linear.py:673
   int32_t bfp_sd;          // BFP: 11 - bfp_target (rounding right shift)                          quant_linear.py:674
   int32_t bfp_round_mant;  // BFP on bf16 with more than 8 mantissa bits: `mant_rounded.to(bf16)` rounds (:707)
@@ -270,21 +307,24 @@ IWQ_HD IntQ int_segment_params(float mx, float mn, const QuantConsts& c, bool sy
 //   d  = clamp(r, lo, hi)          == clamp(r + z, min_int, max_int) - z   (all values are small integers)
 //   out= fma(d, s, +0)             == rD(d * s), and turns -0 into +0 exactly like "(-0.0) + zeros" does
 // Valid when |lo|,|hi| <= 512 (fp16) / 64 (bf16); kWide extends bf16 to 256 via the |x|+128 trick.
-template <int DT, bool kWide>
+template <int DT, bool kWide, bool PAIR = false>
 struct IntFast {
   using D = DType<DT>;
   using T2 = typename D::T2;
+  using F = typename PerHalf<PAIR>::F;
   T2 lo2, hi2, s2;
-  float s, r;
+  F s, r;
   bool slow_div;
 
-  IWQ_HD void setup(const IntQ& q) {
-    lo2 = D::from_f32x2(q.lo, q.lo);
-    hi2 = D::from_f32x2(q.hi, q.hi);
-    s2 = D::from_f32x2(q.s, q.s);
-    s = q.s;
-    r = q.r;
-    slow_div = q.slow_div;
+  IWQ_HD void setup(const IntQ& q) { setup2(q, q); }
+  // low half <- qa, high half <- qb (equal for the row-grouped kernels)
+  IWQ_HD void setup2(const IntQ& qa, const IntQ& qb) {
+    lo2 = D::from_f32x2(qa.lo, qb.lo);
+    hi2 = D::from_f32x2(qa.hi, qb.hi);
+    s2 = D::from_f32x2(qa.s, qb.s);
+    s = PerHalf<PAIR>::make(qa.s, qb.s);
+    r = PerHalf<PAIR>::make(qa.r, qb.r);
+    slow_div = qa.slow_div || qb.slow_div;
   }
 
   IWQ_HD T2 rint2(T2 x) const {
@@ -381,19 +421,21 @@ IWQ_HD FpQ fp_segment_params(float mx, float mn, const QuantConsts& c) {
 //   sign: codec -> (n < 0), so a negative input that flushes to zero gives -0.0 (quirk Q4, :130,:234)
 //         RNE   -> sign bit of n (rint(-0.0/sc)*sc = -0.0, fp4_quantize_cpu.py:42-43)
 //   out = rD(v * S) [+ mid_h]                                                      :774-777
-template <int DT>
+template <int DT, bool PAIR = false>
 struct FpTable {
   using D = DType<DT>;
   using T2 = typename D::T2;
+  using F = typename PerHalf<PAIR>::F;
   T2 S2, mid2, midh2, fmax2, tiny2, lutlo2;
-  float S, r;
+  F S, r;
   bool asym, rne, slow_div;
   int tbl_off;  // entry index = exponent_field - tbl_base
   uint32_t lo2, sh;          // step table: packed low pattern, log2 interval width
   const FpStep* steps;       // host: pointer; device: also as a 32-bit shared-memory address
   uint32_t steps_saddr;
 
-  IWQ_HD void setup(const FpQ& q, const QuantConsts& c, const FpStep* step_tbl = nullptr) {
+  IWQ_HD void setup(const FpQ& q, const QuantConsts& c, const FpStep* step_tbl = nullptr) { setup2(q, q, c, step_tbl); }
+  IWQ_HD void setup2(const FpQ& q, const FpQ& qb, const QuantConsts& c, const FpStep* step_tbl = nullptr) {
     steps = step_tbl;
     steps_saddr = 0;
 #ifdef __CUDA_ARCH__
@@ -401,17 +443,17 @@ struct FpTable {
 #endif
     lo2 = (uint32_t)c.lut_lo_bits | ((uint32_t)c.lut_lo_bits << 16);
     sh = c.lut_shift;
-    S2 = D::from_f32x2(q.S, q.S);
-    mid2 = D::from_f32x2(q.mid, q.mid);
-    midh2 = D::from_f32x2(q.mid_h, q.mid_h);
+    S2 = D::from_f32x2(q.S, qb.S);
+    mid2 = D::from_f32x2(q.mid, qb.mid);
+    midh2 = D::from_f32x2(q.mid_h, qb.mid_h);
     fmax2 = D::bcast(c.fmax_bits);
     tiny2 = D::bcast(c.tiny_bits);
     lutlo2 = D::bcast(c.lut_lo_bits);
-    S = q.S;
-    r = q.r;
+    S = PerHalf<PAIR>::make(q.S, qb.S);
+    r = PerHalf<PAIR>::make(q.r, qb.r);
     asym = !c.symmetric && !c.flavour_rne;
     rne = c.flavour_rne != 0;
-    slow_div = q.slow_div;
+    slow_div = q.slow_div || qb.slow_div;
     tbl_off = c.tbl_base;
   }
 
@@ -525,16 +567,19 @@ IWQ_HD float mul_f16_to_f32(uint16_t a, uint16_t b) {
 #endif
 }
 
-template <int DT>
+template <int DT, bool PAIR = false>
 struct BfpApply {
   using D = DType<DT>;
   using T2 = typename D::T2;
-  float step, inv_step, top, tie;
+  using F = typename PerHalf<PAIR>::F;
+  F step, inv_step;
+  float top, tie;
   bool round_mant;
 
-  IWQ_HD void setup(const BfpQ& q, const QuantConsts& c) {
-    step = q.step;
-    inv_step = q.inv_step;
+  IWQ_HD void setup(const BfpQ& q, const QuantConsts& c) { setup2(q, q, c); }
+  IWQ_HD void setup2(const BfpQ& q, const BfpQ& qb, const QuantConsts& c) {
+    step = PerHalf<PAIR>::make(q.step, qb.step);
+    inv_step = PerHalf<PAIR>::make(q.inv_step, qb.inv_step);
     top = q.top;
     tie = q.tie;
     round_mant = c.bfp_round_mant != 0;
@@ -552,8 +597,8 @@ struct BfpApply {
     // exponent field 0 (|w| < 2^-14): no implicit one AND the field is used as-is -> a_ref = |w| / 2   :664-670
     const uint32_t sub = __hlt2_mask(from_u32<__half2>(ab), from_u32<__half2>(0x04000400u));
     const uint32_t mul2 = 0x3C003C00u ^ (sub & 0x04000400u);  // 1.0, or 0.5 where the field is 0
-    float x0 = mul_f16_to_f32((uint16_t)(ab & 0xFFFFu), (uint16_t)(mul2 & 0xFFFFu)) * inv_step;
-    float x1 = mul_f16_to_f32((uint16_t)(ab >> 16), (uint16_t)(mul2 >> 16)) * inv_step;
+    float x0 = mul_f16_to_f32((uint16_t)(ab & 0xFFFFu), (uint16_t)(mul2 & 0xFFFFu)) * PerHalf<PAIR>::lo(inv_step);
+    float x1 = mul_f16_to_f32((uint16_t)(ab >> 16), (uint16_t)(mul2 >> 16)) * PerHalf<PAIR>::hi(inv_step);
     x0 = fminf(x0, top);                                                                   // clamp  :700-701
     x1 = fminf(x1, top);
     const float kMagic = 12582912.0f;                         // 1.5 * 2^23
@@ -563,8 +608,8 @@ struct BfpApply {
       q0 = rD<DT>(q0);
       q1 = rD<DT>(q1);
     }
-    const float s0 = bits_f32(f32_bits(step) | ((h2 << 16) & 0x80000000u));  // scale * sign_factor    :705-707
-    const float s1 = bits_f32(f32_bits(step) | (h2 & 0x80000000u));
+    const float s0 = bits_f32(f32_bits(PerHalf<PAIR>::lo(step)) | ((h2 << 16) & 0x80000000u));  // scale * sign_factor :705-707
+    const float s1 = bits_f32(f32_bits(PerHalf<PAIR>::hi(step)) | (h2 & 0x80000000u));
     return as_u32(D::from_f32x2(q0 * s0, q1 * s1));            // .to(weight dtype)                    :708
   }
 };

@@ -15,9 +15,10 @@ Different on purpose: the arithmetic is ONE fused CUDA pass per matrix (libiwq_b
 CPU weight when called from `from_linear` (quant_linear.py:444,460-468 costs ~12 ns per weight);
 no `torch.cuda.empty_cache()` per layer (:954, :162).
 
-Also implemented: weight_format='bfp' (block floating point, :648-723).
-Not implemented yet (raise NotImplementedError): approximate / double_approximate decode (:237-363,
-:470-632), quant_dim=1 (:478-483, :640-647).
+Also implemented: weight_format='bfp' (block floating point, :648-723); quant_dim=1 (segments along the
+output dimension, :478-483, :640-647) for every scheme; the single aligned ("approximate") decode
+(_fp_decode_aligned, :237-285, driver :470-632).
+Not implemented yet (raise NotImplementedError): double_approximate (:288-363).
 """
 from __future__ import annotations
 
@@ -187,33 +188,45 @@ class QuantLinear(nn.Module):
     def _plan(self):
         """Validate the configuration and return (cfg, G, wants_zeros) or None when nothing is to be done
         (w_bit >= 16, quant_linear.py:887-892).  Raises what the reference raises."""
-        if self.approximate:
-            if self.weight_format == "int":
-                raise NotImplementedError("approximate 目前仅支持 fp4/fp6/fp8")  # quant_linear.py:601
-            raise NotImplementedError("approximate / double_approximate decode is not implemented in iron_weight_only_quant_b200 yet")
-        if self.quant_dim == 1:
-            raise NotImplementedError("quant_dim=1 (grouping along the output dim) is not implemented in iron_weight_only_quant_b200 yet")
-        if self.weight_format == "bfp" and self.w_group_size <= 0:
-            raise ValueError("BFP 仅支持分组量化，请将 w_group_size 设为正数")  # quant_linear.py:650
         w = self.weight.data
         rows, cols = w.shape
         g = self.w_group_size
+        qd = 1 if self.quant_dim == 1 else 0
+        seg_dim = rows if qd == 1 else cols  # the dimension the groups run along (after the reference's transpose)
+        if self.approximate:
+            # quantize_weight_approximate (quant_linear.py:470-632): grouped, symmetric absmax scale, FP formats only
+            if g <= 0:
+                raise ValueError("approximate 仅支持分组量化，w_group_size 必须 > 0")  # :475-476
+            assert seg_dim % g == 0  # :480 / :485
+            if self.weight_format not in ("fp4", "fp6", "fp8"):
+                raise NotImplementedError("approximate 目前仅支持 fp4/fp6/fp8")  # :601
+            E, M = fp_format_of(self.weight_format)
+            hs, hf, tp = {
+                "fp4": (self.fp4_hi_align_start, self.fp4_hi_align_exp_field, self.fp4_tail_pad_bits),
+                "fp6": (self.fp6_hi_align_start, self.fp6_hi_align_exp_field, self.fp6_tail_pad_bits),
+                "fp8": (self.fp8_hi_align_start, self.fp8_hi_align_exp_field, self.fp8_tail_pad_bits),
+            }[self.weight_format]
+            double = bool(self.double_approximate) and not (self.weight_format == "fp4" and E == 1)  # :496-523
+            cfg = _lib.make_config(w.dtype, _lib.SCHEME_FP_CODEC, g, exp_bits=E, mant_bits=M, symmetric=True, quant_dim=qd, approx=2 if double else 1, hi_align_start=hs, hi_align_exp_field=hf, tail_pad_bits=tp)
+            return cfg, _lib.num_segments(rows, cols, g, qd), False
+        if self.weight_format == "bfp" and g <= 0:
+            raise ValueError("BFP 仅支持分组量化，请将 w_group_size 设为正数")  # quant_linear.py:650
         if g > 0:
-            assert cols % g == 0  # quant_linear.py:728 / :897
+            assert seg_dim % g == 0  # quant_linear.py:653 / :728 / :897 (on the transposed shape when quant_dim == 1)
         elif g not in (-1, -2):
             raise ValueError("Invalid w_group_size")  # quant_linear.py:737 / :906
         if self.weight_format == "bfp":
             # sign + min(w_bit-1, 11) mantissa bits around the group's max exponent; no scales / zeros buffers
-            cfg = _lib.make_config(w.dtype, _lib.SCHEME_BFP, g, bits=self.w_bit, symmetric=True)
+            cfg = _lib.make_config(w.dtype, _lib.SCHEME_BFP, g, bits=self.w_bit, symmetric=True, quant_dim=qd)
             return cfg, 0, False
         if self.weight_format == "int":
             if self.w_bit >= 16:
                 return None
-            cfg = _lib.make_config(w.dtype, _lib.SCHEME_INT, g, bits=self.w_bit, symmetric=self.symmetric)
+            cfg = _lib.make_config(w.dtype, _lib.SCHEME_INT, g, bits=self.w_bit, symmetric=self.symmetric, quant_dim=qd)
         else:
             E, M = fp_format_of(self.weight_format)
-            cfg = _lib.make_config(w.dtype, _lib.SCHEME_FP_CODEC, g, exp_bits=E, mant_bits=M, symmetric=self.symmetric)
-        return cfg, _lib.num_segments(rows, cols, g), (not self.symmetric)
+            cfg = _lib.make_config(w.dtype, _lib.SCHEME_FP_CODEC, g, exp_bits=E, mant_bits=M, symmetric=self.symmetric, quant_dim=qd)
+        return cfg, _lib.num_segments(rows, cols, g, qd), (not self.symmetric)
 
     def _alloc_qparams(self, G: int, wants_zeros: bool):
         w = self.weight.data
@@ -265,6 +278,8 @@ class QuantLinear(nn.Module):
                 _lib.fake_quant_(tmp, tmp, cfg, rows, cols, scales=scales, zeros=zeros, track_status=False)
                 w.copy_(tmp)
             self._finish(scales, zeros)
+            if self.approximate:
+                self.approximate = True  # quant_linear.py:628
 
     def forward(self, input):
         """quant_linear.py:960-972"""

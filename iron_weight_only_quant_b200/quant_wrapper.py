@@ -52,7 +52,7 @@ def quantize_linears_batched(shells):
             ql.quantize_weight()  # rare: strided / misaligned storage goes through the single-matrix call
             continue
         rows, cols = w.shape
-        key = (w.device, w.dtype, cols if ql.w_group_size == _lib.GROUP_PER_CHANNEL else 0)
+        key = (w.device, w.dtype, cols if (ql.w_group_size == _lib.GROUP_PER_CHANNEL and cfg.quant_dim == 0) else 0)
         scales, zeros = ql._alloc_qparams(G, wants_zeros)
         groups[key].append((ql, cfg, _lib.matrix_desc(w, w, rows, cols, scales, zeros), scales, zeros))
     for (device, _, _), items in groups.items():

@@ -38,14 +38,72 @@ static int run(const iwq_config_t* cfg, const QuantConsts& c, int kind, const ui
   using T2 = typename DType<DT>::T2;
   const int64_t total = rows * cols;
   int64_t seg = cfg->group > 0 ? cfg->group : (cfg->group == IWQ_GROUP_PER_TENSOR ? total : cols);
-  if (cfg->group > 0 && cols % cfg->group) return IWQ_ERR_INDIVISIBLE;
-  if (seg % 2) return IWQ_ERR_UNSUPPORTED;
+  const bool by_col = cfg->quant_dim == 1 && cfg->group != IWQ_GROUP_PER_TENSOR;
+  if (!by_col && cfg->group > 0 && cols % cfg->group) return IWQ_ERR_INDIVISIBLE;
+  if (!by_col && seg % 2) return IWQ_ERR_UNSUPPORTED;
   const bool sym = c.symmetric != 0;
   // the minifloat step table, built by the same host code the library uses
   std::vector<FpStep> steps;
   if (kind == KIND_FP) {
     steps.resize(c.lut_n);
     if (!build_step_table(DT, c, steps.data())) return IWQ_ERR_UNSUPPORTED;
+  }
+  if (cfg->quant_dim == 1 && cfg->group != IWQ_GROUP_PER_TENSOR) {
+    // column segments, processed as PAIRS of adjacent columns like col_kernel does
+    const int64_t g = cfg->group > 0 ? cfg->group : rows;
+    if (rows % g) return IWQ_ERR_INDIVISIBLE;
+    if (cols % 2) return IWQ_ERR_UNSUPPORTED;
+    const int64_t n_rb = rows / g;
+    std::vector<uint16_t> col(g);
+    for (int64_t rb = 0; rb < n_rb; ++rb) {
+      for (int64_t cc = 0; cc < cols; cc += 2) {
+        float mxv[2], mnv[2];
+        for (int h = 0; h < 2; ++h) {
+          for (int64_t k = 0; k < g; ++k) col[k] = w[(rb * g + k) * cols + cc + h];
+          seg_range<DT>(col.data(), g, sym, &mxv[h], &mnv[h]);
+        }
+        float sa = 0, za = 0, sb = 0, zb = 0;
+        IntFast<DT, false, true> fi;
+        IntFast<DT, true, true> fw;
+        FpTable<DT, true> ff;
+        BfpApply<DT, true> fb;
+        IntQ qa, qb;
+        if (kind == KIND_FP) {
+          FpQ a = fp_segment_params<DT>(mxv[0], mnv[0], c), b = fp_segment_params<DT>(mxv[1], mnv[1], c);
+          ff.setup2(a, b, c, steps.data());
+          sa = a.S; za = a.mid; sb = b.S; zb = b.mid;
+        } else if (kind == KIND_BFP) {
+          fb.setup2(bfp_segment_params<DT>(mxv[0], c), bfp_segment_params<DT>(mxv[1], c), c);
+        } else {
+          qa = int_segment_params<DT>(mxv[0], mnv[0], c, sym);
+          qb = int_segment_params<DT>(mxv[1], mnv[1], c, sym);
+          fi.setup2(qa, qb);
+          fw.setup2(qa, qb);
+          sa = qa.s; za = qa.z; sb = qb.s; zb = qb.z;
+        }
+        for (int64_t k = 0; k < g; ++k) {
+          const int64_t idx = (rb * g + k) * cols + cc;
+          const uint32_t w2 = (uint32_t)w[idx] | ((uint32_t)w[idx + 1] << 16);
+          uint32_t o;
+          T2 tmp;
+          if (kind == KIND_FP) {
+            o = ff.slow_div ? ff.template apply<true>(w2, &tmp) : ff.template apply<false>(w2, &tmp);
+          } else if (kind == KIND_BFP) {
+            o = fb.apply(w2);
+          } else if (kind == KIND_INT_GENERIC) {
+            float code;
+            o = (uint32_t)int_generic_elem<DT>(w[idx], qa, c, &code) | ((uint32_t)int_generic_elem<DT>(w[idx + 1], qb, c, &code) << 16);
+          } else {
+            o = kind == KIND_INT_WIDE ? fw.apply(w2, &tmp) : fi.apply(w2, &tmp);
+          }
+          out[idx] = (uint16_t)(o & 0xFFFF);
+          out[idx + 1] = (uint16_t)(o >> 16);
+        }
+        if (scales) { scales[cc * n_rb + rb] = DType<DT>::from_f32(sa); scales[(cc + 1) * n_rb + rb] = DType<DT>::from_f32(sb); }
+        if (zeros) { zeros[cc * n_rb + rb] = DType<DT>::from_f32(za); zeros[(cc + 1) * n_rb + rb] = DType<DT>::from_f32(zb); }
+      }
+    }
+    return 0;
   }
   for (int64_t s0 = 0, g = 0; s0 < total; s0 += seg, ++g) {
     float mx, mn;

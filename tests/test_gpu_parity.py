@@ -521,3 +521,95 @@ def test_bfp_vs_oracle_large_and_batched():
     for m in model:
         assert isinstance(m, quant_linear.QuantLinear) and m.weight_format == "bfp"
         assert np.array_equal(bits(m.weight.data), ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# quant_dim = 1 (segments along the output dimension) and the aligned "approximate" decode
+# ------------------------------------------------------------------------------------------------
+def _from_linear(w, dt, **kw):
+    lin = torch.nn.Linear(w.shape[1], w.shape[0], bias=False, device=DEV, dtype=TDT[dt])
+    lin.weight.data.copy_(w)
+    return quant_linear.QuantLinear.from_linear(lin, **kw)
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_quant_dim1_matches_reference_golden(golden, dt):
+    g = golden("golden_dim1_approx")
+    w = tensor_of(g[f"w_{dt}"], dt)
+    quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
+    for grp in (32, 128):
+        for sym in (False, True):
+            tag = "sym" if sym else "asym"
+            for name, kw in (("int4", dict(w_bit=4, weight_format="int")), ("fp4", dict(w_bit=4, weight_format="fp4")), ("fp8", dict(w_bit=8, weight_format="fp8"))):
+                key = f"{dt}_{name}_{tag}_g{grp}_d1"
+                ql = _from_linear(w, dt, w_group_size=grp, symmetric=sym, quant_dim=1, **kw)
+                assert_bits(bits(ql.weight.data), g[key + "_out"], dt, key)
+                sd = dt if name == "int4" else "f16"
+                assert_bits(bits(ql.scales.reshape(-1)), g[key + "_scales"], sd, key + " scales")
+                if sym:
+                    assert ql.zeros is None
+                else:
+                    assert np.array_equal(O.from_bits(bits(ql.zeros.reshape(-1)), sd), O.from_bits(g[key + "_zeros"], sd)), key + " zeros"
+        ql = _from_linear(w, dt, w_bit=8, w_group_size=grp, symmetric=False, weight_format="int", quant_dim=1)
+        assert_bits(bits(ql.weight.data), g[f"{dt}_int8_asym_g{grp}_d1_out"], dt, f"int8 g{grp}")
+        ql = _from_linear(w, dt, w_bit=4, w_group_size=grp, symmetric=True, weight_format="bfp", quant_dim=1)
+        assert_bits(bits(ql.weight.data), g[f"{dt}_bfp4_g{grp}_d1_out"], dt, f"bfp4 g{grp}")
+    ql = _from_linear(w, dt, w_bit=4, w_group_size=-2, symmetric=False, weight_format="int", quant_dim=1)
+    assert_bits(bits(ql.weight.data), g[f"{dt}_int4_asym_pc_d1_out"], dt, "per-channel d1")
+    assert_bits(bits(ql.scales.reshape(-1)), g[f"{dt}_int4_asym_pc_d1_scales"], dt, "per-channel d1 scales")
+    lin = torch.nn.Linear(64, 100, bias=False, device=DEV, dtype=TDT[dt])
+    with pytest.raises(AssertionError):
+        quant_linear.QuantLinear.from_linear(lin, w_group_size=32, quant_dim=1)  # 100 % 32 != 0 on the transposed shape
+
+
+SINGLE_APPROX = [("e1m2_s", "fp4", 1, 2, 1, 1, 0), ("e2m1_s", "fp4", 2, 1, 1, 1, 0), ("e2m3_s", "fp6", 2, 3, 4, 7, 2), ("e3m2_s", "fp6", 3, 2, 4, 7, 2), ("e4m3_s", "fp8", 4, 3, 12, 15, 1)]
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("case", SINGLE_APPROX, ids=[c[0] for c in SINGLE_APPROX])
+def test_single_approximate_matches_reference_golden(golden, dt, case):
+    name, wf, E, M, hs, hf, tp = case
+    g = golden("golden_dim1_approx")
+    w = tensor_of(g[f"w_{dt}"], dt)
+    quant_linear.configure_fp_formats(**{f"{wf}_exp_bits": E, f"{wf}_mantissa_bits": M})
+    try:
+        kw = {f"{wf}_hi_align_start": hs, f"{wf}_hi_align_exp_field": hf, f"{wf}_tail_pad_bits": tp}
+        for qd, grp in ((0, 32), (1, 128)):
+            ql = _from_linear(w, dt, w_bit=4, w_group_size=grp, symmetric=True, weight_format=wf, approximate=True, quant_dim=qd, **kw)
+            key = f"{dt}_approx_{name}_g{grp}_d{qd}"
+            assert_bits(bits(ql.weight.data), g[key + "_out"], dt, key)
+            assert np.array_equal(bits(ql.scales.reshape(-1)), g[key + "_scales"]), key + " scales"
+            assert ql.zeros is None and ql.approximate is True
+        with pytest.raises(ValueError):
+            _from_linear(w, dt, w_group_size=-1, weight_format=wf, approximate=True)  # quant_linear.py:475-476
+        with pytest.raises(NotImplementedError):
+            _from_linear(w, dt, w_group_size=32, weight_format="int", approximate=True)  # quant_linear.py:601
+        if not (wf == "fp4" and E == 1):
+            with pytest.raises(NotImplementedError):
+                _from_linear(w, dt, w_group_size=128, weight_format=wf, approximate=True, double_approximate=True, quant_dim=1, **kw)
+    finally:
+        quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_quant_dim1_vs_oracle_larger(dt):
+    """column-group kernel on shapes with several row blocks, a ragged last column tile and whole-column segments"""
+    for rows, cols, grp, nb, sym in [(1024, 520, 128, 4, False), (512, 1032, 64, 4, True), (384, 264, -2, 8, False), (2048, 256, 256, 3, False)]:
+        w = seeded(rows, cols, dt, rows + cols + 1)
+        ref = O.along_output_dim(O.int_fake_quant, bits(w), dt, nb, not sym, grp)
+        G = _lib.num_segments(rows, cols, grp, 1)
+        wd = w.to(DEV)
+        scales = torch.empty(G, dtype=TDT[dt], device=DEV)
+        zeros = torch.empty(G, dtype=TDT[dt], device=DEV)
+        cfg = _lib.make_config(TDT[dt], _lib.SCHEME_INT, grp, bits=nb, symmetric=sym, quant_dim=1)
+        _lib.fake_quant_(wd, wd, cfg, rows, cols, scales=scales, zeros=zeros)
+        tag = f"{dt} [{rows},{cols}] g{grp} b{nb} sym={sym}"
+        assert_bits(bits(wd), ref["out"], dt, tag)
+        assert_bits(bits(scales), ref["scales"], dt, tag + " scales")
+        assert np.array_equal(O.from_bits(bits(zeros), dt), O.from_bits(ref["zeros"], dt)), tag + " zeros"
+    w = seeded(512, 768, dt, 77)
+    ref = O.along_output_dim(O.fp_approx_fake_quant, bits(w), dt, 4, 3, 128, 12, 15, 1, False)
+    wd = w.to(DEV)
+    cfg = _lib.make_config(TDT[dt], _lib.SCHEME_FP_CODEC, 128, exp_bits=4, mant_bits=3, symmetric=True, quant_dim=1, approx=1, hi_align_start=12, hi_align_exp_field=15, tail_pad_bits=1)
+    _lib.fake_quant_(wd, wd, cfg, 512, 768)
+    assert_bits(bits(wd), ref["out"], dt, "approx e4m3 d1")

@@ -23,7 +23,7 @@ FORMATS = {"e2m1": (2, 1), "e1m2": (1, 2), "e3m2": (3, 2), "e2m3": (2, 3), "e4m3
 
 
 class Cfg(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int32) for n in ("dtype", "scheme", "bits", "exp_bits", "mant_bits", "symmetric", "group", "variant")]
+    _fields_ = [(n, ctypes.c_int32) for n in ("dtype", "scheme", "bits", "exp_bits", "mant_bits", "symmetric", "group", "variant", "quant_dim", "approx", "hi_align_start", "hi_align_exp_field", "tail_pad_bits")]
 
 
 @pytest.fixture(scope="module")
@@ -43,11 +43,11 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def run_emu(lib, w, dtype, scheme, group, bits=4, E=0, M=0, sym=False, force_kind=-1):
-    cfg = Cfg(dtype=dtype, scheme=scheme, bits=bits, exp_bits=E, mant_bits=M, symmetric=int(sym), group=group, variant=0)
+def run_emu(lib, w, dtype, scheme, group, bits=4, E=0, M=0, sym=False, force_kind=-1, quant_dim=0, approx=0, hs=0, hf=0, tp=0):
+    cfg = Cfg(dtype=dtype, scheme=scheme, bits=bits, exp_bits=E, mant_bits=M, symmetric=int(sym), group=group, variant=0, quant_dim=quant_dim, approx=approx, hi_align_start=hs, hi_align_exp_field=hf, tail_pad_bits=tp)
     w = np.ascontiguousarray(w, dtype=np.uint16)
     rows, cols = w.shape
-    G = rows * cols // group if group > 0 else (1 if group == -1 else rows)
+    G = rows * cols // group if group > 0 else (1 if group == -1 else (cols if quant_dim == 1 else rows))
     out = np.empty_like(w)
     scales = np.empty(G, np.uint16)
     zeros = np.empty(G, np.uint16)
@@ -172,3 +172,41 @@ def test_bfp_math_matches_reference(emu, golden, dt):
         for grp in (32, 64, 128, 512):
             out, _, _ = run_emu(emu, w, F16 if dt == "f16" else BF16, SCHEME_BFP, grp, bits=w_bit, sym=True)
             assert_bits_equal(out, g[f"{dt}_b{w_bit}_g{grp}"], dt, f"b{w_bit} g{grp}")
+
+
+SINGLE_APPROX = [("e1m2_s", 1, 2, 1, 1, 0), ("e2m1_s", 2, 1, 1, 1, 0), ("e2m3_s", 2, 3, 4, 7, 2), ("e3m2_s", 3, 2, 4, 7, 2), ("e4m3_s", 4, 3, 12, 15, 1)]
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_quant_dim1_math_matches_reference(emu, golden, dt):
+    g = golden("golden_dim1_approx")
+    w = g[f"w_{dt}"]
+    d = F16 if dt == "f16" else BF16
+    for grp in (32, 128):
+        for sym in (False, True):
+            tag = "sym" if sym else "asym"
+            out, scales, _ = run_emu(emu, w, d, SCHEME_INT, grp, bits=4, sym=sym, quant_dim=1)
+            assert_bits_equal(out, g[f"{dt}_int4_{tag}_g{grp}_d1_out"], dt, f"int4 {tag} g{grp}")
+            assert_bits_equal(scales, g[f"{dt}_int4_{tag}_g{grp}_d1_scales"], dt, f"int4 {tag} g{grp} scales")
+            for fmt, (E, M) in (("fp4", (2, 1)), ("fp8", (4, 3))):
+                out, _, _ = run_emu(emu, w, d, SCHEME_FP_CODEC, grp, E=E, M=M, sym=sym, quant_dim=1)
+                assert_bits_equal(out, g[f"{dt}_{fmt}_{tag}_g{grp}_d1_out"], dt, f"{fmt} {tag} g{grp}")
+        out, _, _ = run_emu(emu, w, d, SCHEME_INT, grp, bits=8, sym=False, quant_dim=1)
+        assert_bits_equal(out, g[f"{dt}_int8_asym_g{grp}_d1_out"], dt, f"int8 g{grp}")
+        out, _, _ = run_emu(emu, w, d, SCHEME_BFP, grp, bits=4, sym=True, quant_dim=1)
+        assert_bits_equal(out, g[f"{dt}_bfp4_g{grp}_d1_out"], dt, f"bfp4 g{grp}")
+    out, _, _ = run_emu(emu, w, d, SCHEME_INT, -2, bits=4, sym=False, quant_dim=1)
+    assert_bits_equal(out, g[f"{dt}_int4_asym_pc_d1_out"], dt, "per-channel d1")
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("case", SINGLE_APPROX, ids=[c[0] for c in SINGLE_APPROX])
+def test_single_approximate_math_matches_reference(emu, golden, dt, case):
+    name, E, M, hs, hf, tp = case
+    g = golden("golden_dim1_approx")
+    w = g[f"w_{dt}"]
+    d = F16 if dt == "f16" else BF16
+    out, _, _ = run_emu(emu, w, d, SCHEME_FP_CODEC, 32, E=E, M=M, sym=True, approx=1, hs=hs, hf=hf, tp=tp)
+    assert_bits_equal(out, g[f"{dt}_approx_{name}_g32_d0_out"], dt, "quant_dim 0")
+    out, _, _ = run_emu(emu, w, d, SCHEME_FP_CODEC, 128, E=E, M=M, sym=True, approx=1, hs=hs, hf=hf, tp=tp, quant_dim=1)
+    assert_bits_equal(out, g[f"{dt}_approx_{name}_g128_d1_out"], dt, "quant_dim 1")

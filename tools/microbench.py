@@ -34,6 +34,9 @@ CONFIGS = {
     "fprne_e2m1g128": dict(scheme=_lib.SCHEME_FP_RNE, group=128, exp_bits=2, mant_bits=1, symmetric=True),
     "bfp4g128": dict(scheme=_lib.SCHEME_BFP, group=128, bits=4, symmetric=True),
     "bfp6g64": dict(scheme=_lib.SCHEME_BFP, group=64, bits=6, symmetric=True),
+    "int4g128_d1": dict(scheme=_lib.SCHEME_INT, group=128, bits=4, symmetric=False, quant_dim=1),
+    "fp4e2m1g128_d1": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=2, mant_bits=1, symmetric=True, quant_dim=1),
+    "fp4e2m1g128_d1_approx": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=2, mant_bits=1, symmetric=True, quant_dim=1, approx=1, hi_align_start=1, hi_align_exp_field=1, tail_pad_bits=0),
     "int4pc_sym": dict(scheme=_lib.SCHEME_INT, group=-2, bits=4, symmetric=True),
     "int4pt_sym": dict(scheme=_lib.SCHEME_INT, group=-1, bits=4, symmetric=True),
 }
@@ -76,11 +79,11 @@ def main():
     del dst
     for name in args.configs.split(","):
         c = CONFIGS[name]
-        cfg = _lib.make_config(dt, c["scheme"], c["group"], bits=c.get("bits", 0), exp_bits=c.get("exp_bits", 0), mant_bits=c.get("mant_bits", 0), symmetric=c["symmetric"])
+        cfg = _lib.make_config(dt, c["scheme"], c["group"], bits=c.get("bits", 0), exp_bits=c.get("exp_bits", 0), mant_bits=c.get("mant_bits", 0), symmetric=c["symmetric"], quant_dim=c.get("quant_dim", 0), approx=c.get("approx", 0), hi_align_start=c.get("hi_align_start", 0), hi_align_exp_field=c.get("hi_align_exp_field", 0), tail_pad_bits=c.get("tail_pad_bits", 0))
         descs, keep = [], []
         for w in ws:
             o, k = w.shape
-            G = _lib.num_segments(o, k, c["group"])
+            G = _lib.num_segments(o, k, c["group"], c.get("quant_dim", 0))
             s = None if (args.no_emit or c["scheme"] == _lib.SCHEME_BFP) else torch.empty(G, dtype=dt, device=dev)
             z = None if (args.no_emit or c["symmetric"]) else torch.empty(G, dtype=dt, device=dev)
             keep.append((s, z))
@@ -91,7 +94,7 @@ def main():
             def fn():
                 _lib.minmax_(descs, cfg, dev, rng)
                 _lib.fake_quant_with_range_(descs, cfg, dev, rng, track_status=False)
-        elif c["group"] == -2:
+        elif c["group"] == -2 and c.get("quant_dim", 0) == 0:
             by_cols = {}
             for d, w in zip(descs, ws):
                 by_cols.setdefault(w.shape[1], []).append(d)
