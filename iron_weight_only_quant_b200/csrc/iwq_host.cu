@@ -338,10 +338,8 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
     if (rc) return rc;
     p.lut_smem_bytes = (uint32_t)(((size_t)p.qc.lut_n * sizeof(FpStep) + 1023) & ~(size_t)1023);
   }
-  if (p.qc.approx == 2) {
-    if (cfg->quant_dim != 1) return fail(IWQ_ERR_UNSUPPORTED, "double-approximate decode is implemented for quant_dim = 1 only");
-    return fail(IWQ_ERR_UNSUPPORTED, "double-approximate decode is not implemented yet");
-  }
+  if (p.qc.approx == 2 && cfg->quant_dim != 1)
+    return fail(IWQ_ERR_UNSUPPORTED, "double-approximate decode is implemented for quant_dim = 1 only (what the reference's scripts use)");
   if (cfg->quant_dim == 1 && cfg->group != IWQ_GROUP_PER_TENSOR) {
     if (given_range || minmax_only) return fail(IWQ_ERR_INVALID, "range entry points are for per-tensor granularity");
     p.status = status;
@@ -420,7 +418,14 @@ static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, Launc
     if (cols % 8 != 0) return fail(IWQ_ERR_UNSUPPORTED, "quant_dim = 1 needs cols to be a multiple of 8 (16-byte vectors)");
     if (g >= (1ll << 31)) return fail(IWQ_ERR_INVALID, "segment too long");
     Job j = make_job(&ms[i], (uint32_t)units);
-    units += (uint64_t)(rows / g) * (uint64_t)((cols + kColTile - 1) / kColTile);
+    uint64_t row_blocks = (uint64_t)(rows / g);
+    if (p.qc.approx == 2) {
+      // the reference groups 4 codes along the flattened transpose; they share a column only when the number of
+      // row blocks is a multiple of 4 (true for every LLaMA / OPT shape at group 32..256)
+      if (row_blocks % 4 != 0) return fail(IWQ_ERR_UNSUPPORTED, "double-approximate decode needs (rows / group) % 4 == 0");
+      row_blocks /= 4;
+    }
+    units += row_blocks * (uint64_t)((cols + kColTile - 1) / kColTile);
     if (units >= 0xFFFFFFFFull) return fail(IWQ_ERR_INVALID, "too much work for one launch");
     jobs.push_back(j);
   }
@@ -434,7 +439,11 @@ static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, Launc
   LaunchTuning tune;
   tune.stages = 0;
   tune.ctas_per_sm = 0;
-  cudaError_t e = dispatch_col(cfg->dtype, kind, p, p.qc.symmetric != 0, tune, st);
+  cudaError_t e;
+  if (p.qc.approx == 2)
+    e = cfg->dtype == IWQ_F16 ? launch_col_double<IWQ_F16>(p, st) : launch_col_double<IWQ_BF16>(p, st);
+  else
+    e = dispatch_col(cfg->dtype, kind, p, p.qc.symmetric != 0, tune, st);
   if (e != cudaSuccess) return fail_cuda(e, "column-group kernel launch");
   return IWQ_OK;
 }

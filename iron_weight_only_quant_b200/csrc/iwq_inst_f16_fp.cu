@@ -3,4 +3,5 @@
 #include "iwq_launch.cuh"
 namespace iwq {
 IWQ_INSTANTIATE_KIND(IWQ_F16, KIND_FP)
+template cudaError_t launch_col_double<IWQ_F16>(const LaunchParams&, cudaStream_t);
 }

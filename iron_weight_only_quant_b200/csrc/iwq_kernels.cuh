@@ -982,6 +982,149 @@ __global__ void __launch_bounds__(256) col_kernel(const __grid_constant__ Launch
 }
 
 // ------------------------------------------------------------------------------------------------
+// col_double_kernel: quant_dim = 1 with the double-approximate decode (quant_linear.py:288-363).
+// The reference forms groups of four codes along the flattened transpose of the [segments, group] code
+// matrix; with (rows / group) % 4 == 0 those are the codes at the same row offset k of FOUR consecutive row
+// blocks of one column.  So a tile is 4 row blocks x 256 columns, a lane again owns 8 columns, and for every k
+// it holds the four vectors (one per block) whose columns form the groups: the neighbourhood never leaves the
+// thread.  Element stage: normalise with the block's scale, quantise through the exact step table, rebuild
+// the code, decode the four codes jointly (double_approx_decode4), multiply by the scale.  This is scalar
+// integer work (~100 ops per 4 elements): correctness first, it is the research path of the reference.
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(256) col_double_kernel(const __grid_constant__ LaunchParams p) {
+  using D = DType<DT>;
+  using T2 = typename D::T2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // [2 parities][8 warps][4 blocks][32 lanes] uint4 = 32 KB, then the step table
+  uint4* part = reinterpret_cast<uint4*>(smem);
+  const FpStep* s_tbl = load_fp_lut(p, smem + 32768);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int cur = -1;
+  Job jb;
+  uint32_t par = 0;
+  FpQ q1;
+  q1.S = 1.f; q1.r = 1.f; q1.mid = 0.f; q1.mid_h = 0.f; q1.bad = false; q1.slow_div = false;
+  FpTable<DT, true> grid;  // only its scale-independent members are used (clamp bounds, step table)
+  grid.setup2(q1, q1, p.qc, s_tbl);
+  for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+    advance_job(p, tile, &cur, &jb);
+    const uint32_t cols = jb.row_bytes >> 1;
+    const uint32_t rows = (uint32_t)(jb.bytes / jb.row_bytes);
+    const uint32_t g = p.col_group;
+    const uint32_t n_ct = (cols + kColTile - 1) / kColTile;
+    const uint32_t local = tile - jb.first_unit;
+    const uint32_t rb4 = local / n_ct, ct = local - rb4 * n_ct;  // rb4 counts groups of 4 row blocks
+    const uint32_t col = ct * kColTile + (uint32_t)lane * 8u;
+    const bool live = col < cols;
+    const size_t off = (size_t)rb4 * 4 * g * jb.row_bytes + (size_t)col * 2;
+    const uint8_t* src = jb.src + off;
+    uint8_t* dst = jb.dst + off;
+    const size_t blk = (size_t)g * jb.row_bytes;
+
+    // ---- sweep 1: absmax per (block, column) ----
+    uint32_t mx[4][4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mx[b][j] = 0u;
+    if (live) {
+      for (uint32_t k = (uint32_t)warp; k < g; k += 8) {
+        uint4 v[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v[b] = ldg128(src + b * blk + (size_t)k * jb.row_bytes);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t w4[4] = {v[b].x, v[b].y, v[b].z, v[b].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mx[b][j] = as_u32(__hmax2_nan(from_u32<T2>(mx[b][j]), from_u32<T2>(w4[j] & 0x7FFF7FFFu)));
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) part[((par * 8 + warp) * 4 + b) * 32 + lane] = make_uint4(mx[b][0], mx[b][1], mx[b][2], mx[b][3]);
+    __syncthreads();
+    for (int w = 0; w < 8; ++w) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint4 a = part[((par * 8 + w) * 4 + b) * 32 + lane];
+        mx[b][0] = as_u32(__hmax2_nan(from_u32<T2>(mx[b][0]), from_u32<T2>(a.x)));
+        mx[b][1] = as_u32(__hmax2_nan(from_u32<T2>(mx[b][1]), from_u32<T2>(a.y)));
+        mx[b][2] = as_u32(__hmax2_nan(from_u32<T2>(mx[b][2]), from_u32<T2>(a.z)));
+        mx[b][3] = as_u32(__hmax2_nan(from_u32<T2>(mx[b][3]), from_u32<T2>(a.w)));
+      }
+    }
+    par ^= 1u;
+
+    // ---- scales per (block, column pair) ----
+    float2 S[4][4], R[4][4];
+    uint32_t S2[4][4];
+    bool any_bad = false, slow = false;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float mxa = D::to_f32((uint16_t)(mx[b][j] & 0xFFFFu)), mxb = D::to_f32((uint16_t)(mx[b][j] >> 16));
+        const FpQ qa = fp_segment_params<DT>(mxa, -mxa, p.qc), qb = fp_segment_params<DT>(mxb, -mxb, p.qc);
+        S[b][j] = make_float2(qa.S, qb.S);
+        R[b][j] = make_float2(qa.r, qb.r);
+        S2[b][j] = as_u32(D::from_f32x2(qa.S, qb.S));
+        any_bad |= qa.bad || qb.bad;
+        slow |= qa.slow_div || qb.slow_div;
+        if (live && warp == 0 && jb.scales) {
+          const size_t n_rb = rows / g;
+          const size_t ga = (size_t)(col + 2 * j) * n_rb + (size_t)rb4 * 4 + b;
+          reinterpret_cast<uint16_t*>(jb.scales)[ga] = D::from_f32(qa.S);
+          reinterpret_cast<uint16_t*>(jb.scales)[ga + n_rb] = D::from_f32(qb.S);
+        }
+      }
+    }
+    if (live && any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
+
+    // ---- sweep 2 ----
+    if (live) {
+      for (uint32_t k = (uint32_t)warp; k < g; k += 8) {
+        uint4 v[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v[b] = ldg128(src + b * blk + (size_t)k * jb.row_bytes);
+        uint32_t o[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t gv[4];  // exact grid values of the pair, per block
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const uint32_t w2 = b == 0 ? (j == 0 ? v[0].x : j == 1 ? v[0].y : j == 2 ? v[0].z : v[0].w)
+                              : b == 1 ? (j == 0 ? v[1].x : j == 1 ? v[1].y : j == 2 ? v[1].z : v[1].w)
+                              : b == 2 ? (j == 0 ? v[2].x : j == 1 ? v[2].y : j == 2 ? v[2].z : v[2].w)
+                                       : (j == 0 ? v[3].x : j == 1 ? v[3].y : j == 2 ? v[3].z : v[3].w);
+            const T2 n = slow ? ieee_quot2<DT>(from_u32<T2>(w2), S[b][j]) : fast_quot2<DT>(from_u32<T2>(w2), S[b][j], R[b][j]);
+            gv[b] = as_u32(grid.grid_steps(n, w2));
+          }
+          uint32_t clo[4], chi[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            clo[b] = fp_code_of<DT>((uint16_t)(gv[b] & 0xFFFFu), p.qc.exp_bits, p.qc.mant_bits);
+            chi[b] = fp_code_of<DT>((uint16_t)(gv[b] >> 16), p.qc.exp_bits, p.qc.mant_bits);
+          }
+          uint16_t dlo[4], dhi[4];
+          double_approx_decode4<DT>(clo, p.qc, dlo);
+          double_approx_decode4<DT>(chi, p.qc, dhi);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const T2 dec = from_u32<T2>((uint32_t)dlo[b] | ((uint32_t)dhi[b] << 16));
+            o[b][j] = as_u32(__hmul2(dec, from_u32<T2>(S2[b][j])));  // decoded * scales   quant_linear.py:606
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) stg128(dst + b * blk + (size_t)k * jb.row_bytes, make_uint4(o[b][0], o[b][1], o[b][2], o[b][3]));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-tensor granularity, pass 1
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {

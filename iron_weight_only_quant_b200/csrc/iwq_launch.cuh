@@ -68,7 +68,21 @@ cudaError_t launch_row(const LaunchParams& p, bool sym, int consumers, const Lau
 template <int DT, int KIND>
 cudaError_t launch_col(const LaunchParams& p, bool sym, const LaunchTuning& tune, cudaStream_t st);
 
+template <int DT>
+cudaError_t launch_col_double(const LaunchParams& p, cudaStream_t st);
+
 #ifdef IWQ_INSTANTIATE
+
+template <int DT>
+cudaError_t launch_col_double(const LaunchParams& p, cudaStream_t st) {
+  auto k = col_double_kernel<DT>;
+  const size_t smem = 32768 + p.lut_smem_bytes;
+  int grid = 0;
+  cudaError_t e = persistent_grid(k, 256, smem, 0, p.total_units, &grid);
+  if (e != cudaSuccess) return e;
+  k<<<grid, 256, smem, st>>>(p);
+  return cudaGetLastError();
+}
 
 template <int DT, int KIND, bool SYM>
 static cudaError_t launch_col_one(LaunchParams p, const LaunchTuning& tune, cudaStream_t st) {

@@ -614,6 +614,66 @@ struct BfpApply {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// double-approximate decode of FOUR codes       fp_decode_aligned_double_approx, quant_linear.py:288-363
+// (align_subnorm_exp_as_one=True, handle_max_outlier=True: the driver's arguments, :511-523 etc.)
+// The reference keeps sign / exponent / mantissa in torch.int8 tensors, so `1 << (shift-1)`, `val + offset`
+// and the left shift wrap modulo 256; wrap8() reproduces that, garbage included.
+// Returns the four decoded values as D bit patterns.
+// ------------------------------------------------------------------------------------------------
+IWQ_HD int wrap8(int x) { return (int)(int8_t)(uint8_t)(x & 0xFF); }
+
+IWQ_HD int rounding_rshift8(int val, int shift) {  // _rounding_rshift (:112-123) on int8 tensors
+  const int off = shift > 0 ? wrap8(shift - 1 < 31 ? (1 << (shift - 1)) : 0) : 0;
+  const int v = wrap8(val + off);
+  return shift >= 31 ? (v < 0 ? -1 : 0) : (v >> shift);
+}
+
+template <int DT>
+IWQ_HD void double_approx_decode4(const uint32_t (&code)[4], const QuantConsts& c, uint16_t (&out)[4]) {
+  const int E = c.exp_bits, M = c.mant_bits, bias = (1 << (E - 1)) - 1, tp = c.tail_pad;
+  int ae[4], mp[4];
+  int cnt = 0, gmax = 0;
+  bool has_max = false;
+  const int max_exp = (1 << E) - 1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ef = (int)((code[i] >> M) & (uint32_t)max_exp), mf = (int)(code[i] & ((1u << M) - 1u));
+    ae[i] = ef == 0 ? 1 : ef;                                                            // :315
+    const int full = ((ef == 0 ? 0 : 1) << M) | mf;                                      // :316-317
+    mp[i] = tp >= 0 ? wrap8(full << tp) : rounding_rshift8(full, -tp);                   // :318-321
+    const bool outl = ae[i] < c.hi_start || ae[i] > c.hi_field;                          // :334
+    cnt += outl ? 1 : 0;
+    gmax = ae[i] > gmax ? ae[i] : gmax;
+    has_max = has_max || (ae[i] == max_exp && outl);                                     // :342
+  }
+  int target = cnt <= 1 ? c.hi_field : gmax;                                             // :338
+  if (has_max) target = max_exp;                                                         // :343
+  const int cap = tp >= 0 ? (((1 << (M + 1)) - 1) << tp) : (((1 << (M + 1)) - 1) >> (-tp));  // :351-355
+  const float hi_unb = rD<DT>((float)(target - bias));                                   // (target - bias).to(dtype)
+  const float p2 = rD<DT>(exp2f(hi_unb));                                                // torch.pow(2.0 (dtype), .)
+  const float den = ldexpf(1.0f, M + tp);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int shift = target - ae[i];                                                    // :345
+    int al;
+    if (shift >= 0) {
+      al = rounding_rshift8(mp[i], shift);                                               // :348
+    } else {
+      const int ls = -shift;
+      al = wrap8(ls < 31 ? (mp[i] << ls) : 0);                                           // :349 (int8 wrap)
+      al = al < cap ? al : cap;                                                          // :356
+    }
+    float v = rD<DT>(rD<DT>((float)al) / den);                                           // mant.to(dtype) / 2^(M+tail)  :358
+    v = rD<DT>(v * p2);
+    const uint32_t sign = (code[i] >> (E + M)) & 1u;
+    uint16_t b = DType<DT>::from_f32(v);
+    if (sign) b ^= 0x8000u;                                                              // torch.where(sign == 1, -value, value)
+    if (code[i] == 0) b = 0;                                                             // zero_mask
+    out[i] = b;
+  }
+}
+
 // minifloat code of a grid value (for optional code emission): sign | exponent field | mantissa,
 // zero -> 0 unless the sign survived (quirk Q4).                     quant_linear.py:156-161
 template <int DT>

@@ -17,8 +17,10 @@ no `torch.cuda.empty_cache()` per layer (:954, :162).
 
 Also implemented: weight_format='bfp' (block floating point, :648-723); quant_dim=1 (segments along the
 output dimension, :478-483, :640-647) for every scheme; the single aligned ("approximate") decode
-(_fp_decode_aligned, :237-285, driver :470-632).
-Not implemented yet (raise NotImplementedError): double_approximate (:288-363).
+(_fp_decode_aligned, :237-285, driver :470-632) for both quant_dim; the double-approximate decode
+(fp_decode_aligned_double_approx, :288-363) for quant_dim=1 with (out_features / group) % 4 == 0 -- the
+configuration every script of the reference uses.
+Not implemented (raise NotImplementedError): double_approximate with quant_dim=0.
 """
 from __future__ import annotations
 

@@ -55,6 +55,52 @@ static int run(const iwq_config_t* cfg, const QuantConsts& c, int kind, const ui
     if (cols % 2) return IWQ_ERR_UNSUPPORTED;
     const int64_t n_rb = rows / g;
     std::vector<uint16_t> col(g);
+    if (c.approx == 2) {
+      // double-approximate decode: four consecutive row blocks of a column form the code neighbourhoods,
+      // mirrored from col_double_kernel
+      if (n_rb % 4) return IWQ_ERR_UNSUPPORTED;
+      FpQ q1;
+      q1.S = 1.f; q1.r = 1.f; q1.mid = 0.f; q1.mid_h = 0.f; q1.bad = false; q1.slow_div = false;
+      FpTable<DT, true> grid;
+      grid.setup2(q1, q1, c, steps.data());
+      for (int64_t rb4 = 0; rb4 < n_rb / 4; ++rb4) {
+        for (int64_t cc = 0; cc < cols; cc += 2) {
+          FpQ qs[4][2];
+          for (int b = 0; b < 4; ++b)
+            for (int h = 0; h < 2; ++h) {
+              for (int64_t k = 0; k < g; ++k) col[k] = w[((rb4 * 4 + b) * g + k) * cols + cc + h];
+              float mx, mn;
+              seg_range<DT>(col.data(), g, true, &mx, &mn);
+              qs[b][h] = fp_segment_params<DT>(mx, mn, c);
+              if (scales) scales[(cc + h) * n_rb + rb4 * 4 + b] = DType<DT>::from_f32(qs[b][h].S);
+            }
+          for (int64_t k = 0; k < g; ++k) {
+            uint32_t clo[4], chi[4];
+            int64_t idx[4];
+            for (int b = 0; b < 4; ++b) {
+              idx[b] = ((rb4 * 4 + b) * g + k) * cols + cc;
+              const uint32_t w2 = (uint32_t)w[idx[b]] | ((uint32_t)w[idx[b] + 1] << 16);
+              const bool slow = qs[b][0].slow_div || qs[b][1].slow_div;
+              const float2 S = make_float2(qs[b][0].S, qs[b][1].S), R = make_float2(qs[b][0].r, qs[b][1].r);
+              const T2 n = slow ? ieee_quot2<DT>(from_u32<T2>(w2), S) : fast_quot2<DT>(from_u32<T2>(w2), S, R);
+              const uint32_t gv = as_u32(grid.grid_steps(n, w2));
+              clo[b] = fp_code_of<DT>((uint16_t)(gv & 0xFFFFu), c.exp_bits, c.mant_bits);
+              chi[b] = fp_code_of<DT>((uint16_t)(gv >> 16), c.exp_bits, c.mant_bits);
+            }
+            uint16_t dlo[4], dhi[4];
+            double_approx_decode4<DT>(clo, c, dlo);
+            double_approx_decode4<DT>(chi, c, dhi);
+            for (int b = 0; b < 4; ++b) {
+              const T2 dec = from_u32<T2>((uint32_t)dlo[b] | ((uint32_t)dhi[b] << 16));
+              const uint32_t o = as_u32(__hmul2(dec, DType<DT>::from_f32x2(qs[b][0].S, qs[b][1].S)));
+              out[idx[b]] = (uint16_t)(o & 0xFFFF);
+              out[idx[b] + 1] = (uint16_t)(o >> 16);
+            }
+          }
+        }
+      }
+      return 0;
+    }
     for (int64_t rb = 0; rb < n_rb; ++rb) {
       for (int64_t cc = 0; cc < cols; cc += 2) {
         float mxv[2], mnv[2];

@@ -372,9 +372,7 @@ def test_wrapper_gates_and_errors():
     with pytest.raises(ValueError):
         quant_wrapper.quantize_model(model, _Args(w_format="bfp", w_group_size=-1))  # quant_wrapper.py:19-20
     with pytest.raises(NotImplementedError):
-        quant_wrapper.quantize_model(model, _Args(w_format="fp4", approximate=True))  # not built yet: fails loudly
-    with pytest.raises(NotImplementedError):
-        quant_wrapper.quantize_model(model, _Args(quant_dim=1))
+        quant_wrapper.quantize_model(model, _Args(w_format="int", approximate=True))  # quant_linear.py:601
     with pytest.raises(NotImplementedError):
         quant_wrapper.quantize_model(model, _Args(gptq=True, w_format="fp4"))  # quant_wrapper.py:24-25
 
@@ -585,8 +583,8 @@ def test_single_approximate_matches_reference_golden(golden, dt, case):
         with pytest.raises(NotImplementedError):
             _from_linear(w, dt, w_group_size=32, weight_format="int", approximate=True)  # quant_linear.py:601
         if not (wf == "fp4" and E == 1):
-            with pytest.raises(NotImplementedError):
-                _from_linear(w, dt, w_group_size=128, weight_format=wf, approximate=True, double_approximate=True, quant_dim=1, **kw)
+            with pytest.raises(NotImplementedError):  # double-approximate exists for quant_dim = 1 only
+                _from_linear(w, dt, w_group_size=32, weight_format=wf, approximate=True, double_approximate=True, quant_dim=0, **kw)
     finally:
         quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
 
@@ -613,3 +611,30 @@ def test_quant_dim1_vs_oracle_larger(dt):
     cfg = _lib.make_config(TDT[dt], _lib.SCHEME_FP_CODEC, 128, exp_bits=4, mant_bits=3, symmetric=True, quant_dim=1, approx=1, hi_align_start=12, hi_align_exp_field=15, tail_pad_bits=1)
     _lib.fake_quant_(wd, wd, cfg, 512, 768)
     assert_bits(bits(wd), ref["out"], dt, "approx e4m3 d1")
+
+
+DOUBLE_APPROX = [("e2m1_d", "fp4", 2, 1, 0, 2, 1), ("e2m3_d", "fp6", 2, 3, 0, 2, -1), ("e3m2_d", "fp6", 3, 2, 4, 6, 0), ("e4m3_d", "fp8", 4, 3, 13, 15, -1), ("e4m3_d0", "fp8", 4, 3, 12, 15, 0)]
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("case", DOUBLE_APPROX, ids=[c[0] for c in DOUBLE_APPROX])
+def test_double_approximate_matches_reference_golden(golden, dt, case):
+    """--approximate --double_approximate --quant_dim 1 (scripts/opt-6.7b/scripts_4.sh): the reference's 4-code
+    neighbourhood decode, int8 overflow included."""
+    name, wf, E, M, hs, hf, tp = case
+    g = golden("golden_dim1_approx")
+    w = tensor_of(g[f"w_{dt}"], dt)
+    quant_linear.configure_fp_formats(**{f"{wf}_exp_bits": E, f"{wf}_mantissa_bits": M})
+    try:
+        kw = {f"{wf}_hi_align_start": hs, f"{wf}_hi_align_exp_field": hf, f"{wf}_tail_pad_bits": tp}
+        ql = _from_linear(w, dt, w_bit=4, w_group_size=128, symmetric=True, weight_format=wf, approximate=True, double_approximate=True, quant_dim=1, **kw)
+        key = f"{dt}_approx_{name}_g128_d1"
+        assert_bits(bits(ql.weight.data), g[key + "_out"], dt, key)
+        assert np.array_equal(bits(ql.scales.reshape(-1)), g[key + "_scales"]), key + " scales"
+        # larger, against the oracle: 16 row blocks, ragged column tile
+        wl = seeded(2048, 264, dt, 5 + E)
+        ref = O.along_output_dim(O.fp_approx_fake_quant, bits(wl), dt, E, M, 128, hs, hf, tp, True)
+        ql = _from_linear(wl.to(DEV), dt, w_bit=4, w_group_size=128, symmetric=True, weight_format=wf, approximate=True, double_approximate=True, quant_dim=1, **kw)
+        assert_bits(bits(ql.weight.data), ref["out"], dt, key + " large")
+    finally:
+        quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)

@@ -210,3 +210,18 @@ def test_single_approximate_math_matches_reference(emu, golden, dt, case):
     assert_bits_equal(out, g[f"{dt}_approx_{name}_g32_d0_out"], dt, "quant_dim 0")
     out, _, _ = run_emu(emu, w, d, SCHEME_FP_CODEC, 128, E=E, M=M, sym=True, approx=1, hs=hs, hf=hf, tp=tp, quant_dim=1)
     assert_bits_equal(out, g[f"{dt}_approx_{name}_g128_d1_out"], dt, "quant_dim 1")
+
+
+DOUBLE_APPROX = [("e2m1_d", 2, 1, 0, 2, 1), ("e2m3_d", 2, 3, 0, 2, -1), ("e3m2_d", 3, 2, 4, 6, 0), ("e4m3_d", 4, 3, 13, 15, -1), ("e4m3_d0", 4, 3, 12, 15, 0)]
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("case", DOUBLE_APPROX, ids=[c[0] for c in DOUBLE_APPROX])
+def test_double_approximate_math_matches_reference(emu, golden, dt, case):
+    """fp_decode_aligned_double_approx incl. the reference's int8 overflow, quant_dim = 1 (what its scripts run)"""
+    name, E, M, hs, hf, tp = case
+    g = golden("golden_dim1_approx")
+    w = g[f"w_{dt}"]
+    d = F16 if dt == "f16" else BF16
+    out, _, _ = run_emu(emu, w, d, SCHEME_FP_CODEC, 128, E=E, M=M, sym=True, approx=2, hs=hs, hf=hf, tp=tp, quant_dim=1)
+    assert_bits_equal(out, g[f"{dt}_approx_{name}_g128_d1_out"], dt, name)
