@@ -153,6 +153,9 @@ static inline int build_quant_consts(const iwq_config_t* cfg, QuantConsts* c, in
     int llo = emin - M - 1;  // 2^(emin-M-1) is half the smallest step: it and everything below rounds to 0
     if (llo + DB < 1) llo = 1 - DB;
     c->lut_lo_bits = (uint16_t)((llo + DB) << MB);
+    // fp16: the table starts at bit pattern 0, which saves the kernel a clamp and a subtract per pair
+    // (FpTable::kFromZero); bf16 has 8 exponent bits, a table from 0 would be far too large
+    if (dt == IWQ_F16) c->lut_lo_bits = 0;
   }
   c->fmax_bits = (uint16_t)(((emax + DB) << MB) | (((1 << M) - 1) << (MB - M)));
   c->lut_shift = (uint16_t)(MB - M - 1);

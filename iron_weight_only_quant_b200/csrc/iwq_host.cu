@@ -74,7 +74,7 @@ static int get_fp_lut(const iwq_config_t* cfg, const QuantConsts& qc, cudaStream
     *out = it->second;
     return IWQ_OK;
   }
-  if (qc.lut_n > 1024) return fail(IWQ_ERR_UNSUPPORTED, "minifloat step table too large");
+  if (qc.lut_n > 4096) return fail(IWQ_ERR_UNSUPPORTED, "minifloat step table too large");
   std::vector<FpStep> host(qc.lut_n);
   if (!build_step_table(cfg->dtype, qc, host.data()))
     return fail(IWQ_ERR_UNSUPPORTED, "minifloat format changes value more than once inside a half-step interval");

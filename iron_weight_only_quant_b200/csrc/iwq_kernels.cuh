@@ -196,6 +196,7 @@ struct PreparedInt {  // KIND_INT_FAST / KIND_INT_WIDE
     zero = q.z;
     bad = q.bad;
   }
+  template <bool SYM>
   __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts&, const FpStep*, bool want_codes, uint2* codes8) const {
     T2 d[4];
     uint4 o;
@@ -232,6 +233,7 @@ struct Prepared<DT, KIND_INT_GENERIC> {
     zero = q.z;
     bad = q.bad;
   }
+  template <bool SYM>
   __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts& c, const FpStep*, bool want_codes, uint2* codes8) const {
     const uint32_t in[4] = {v.x, v.y, v.z, v.w};
     uint32_t out[4], cb[8];
@@ -262,19 +264,20 @@ struct Prepared<DT, KIND_FP> {
     zero = q.mid;
     bad = q.bad;
   }
-  template <bool SLOW>
+  template <bool SLOW, bool SYM>
   __device__ __forceinline__ uint4 apply_t(const uint4& v, T2 (&g)[4]) const {
     uint4 o;
-    o.x = f.template apply<SLOW>(v.x, &g[0]);
-    o.y = f.template apply<SLOW>(v.y, &g[1]);
-    o.z = f.template apply<SLOW>(v.z, &g[2]);
-    o.w = f.template apply<SLOW>(v.w, &g[3]);
+    o.x = f.template apply<SLOW, SYM ? 0 : 1>(v.x, &g[0]);
+    o.y = f.template apply<SLOW, SYM ? 0 : 1>(v.y, &g[1]);
+    o.z = f.template apply<SLOW, SYM ? 0 : 1>(v.z, &g[2]);
+    o.w = f.template apply<SLOW, SYM ? 0 : 1>(v.w, &g[3]);
     return o;
   }
+  template <bool SYM>
   __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts& c, const FpStep*, bool want_codes, uint2* codes8) const {
     T2 g[4];
     // one (segment-uniform) branch per vector: IEEE division only for degenerate scales
-    const uint4 o = f.slow_div ? apply_t<true>(v, g) : apply_t<false>(v, g);
+    const uint4 o = f.slow_div ? apply_t<true, SYM>(v, g) : apply_t<false, SYM>(v, g);
     if (want_codes) {
       uint32_t cb[8];
 #pragma unroll
@@ -300,6 +303,7 @@ struct Prepared<DT, KIND_BFP> {
     zero = 0.f;
     bad = false;
   }
+  template <bool SYM>
   __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts&, const FpStep*, bool want_codes, uint2* codes8) const {
     if (want_codes) *codes8 = make_uint2(0u, 0u);  // the reference keeps no BFP codes (quant_linear.py:712-715)
     return make_uint4(f.apply(v.x), f.apply(v.y), f.apply(v.z), f.apply(v.w));
@@ -388,7 +392,7 @@ __device__ __forceinline__ void consume_tile(uint4 (&v)[kVPT], const TileCtx& t,
       prep.setup(mx, mn, p.qc, SYM, tbl);
     }
     uint2 codes8;
-    const uint4 o = prep.apply(v[it], p.qc, tbl, want_codes, &codes8);
+    const uint4 o = prep.template apply<SYM>(v[it], p.qc, tbl, want_codes, &codes8);
     if (idx < t.n_vec) {
       stg128(t.dst + (size_t)idx * 16, o);
       if (want_codes) *reinterpret_cast<uint2*>(t.codes + (t.vec0 + idx) * 8) = codes8;
@@ -515,10 +519,9 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
   } else {
     uint32_t pk = range_max<DT>(range_max<DT>(vec_range<DT, SYM>(v[0]), vec_range<DT, SYM>(v[1])),
                                 range_max<DT>(vec_range<DT, SYM>(v[2]), vec_range<DT, SYM>(v[3])));
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      if (o < lps) pk = range_max<DT>(pk, __shfl_xor_sync(0xFFFFFFFFu, pk, o));
-    }
+    // log2(lps) butterfly rounds; lps is launch-uniform, so this is a short uniform loop (no divergence handling)
+#pragma unroll 1
+    for (int o = lps >> 1; o > 0; o >>= 1) pk = range_max<DT>(pk, __shfl_xor_sync(0xFFFFFFFFu, pk, o));
     float mx, mn;
     range_unpack<DT>(pk, &mx, &mn);
     prep.setup(mx, mn, p.qc, SYM, s_tbl);
@@ -528,7 +531,7 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
   for (int k = 0; k < 4; ++k) {
     const uint32_t j = (k + rot) & 3u;
     uint2 codes8;
-    const uint4 o = prep.apply(v[k], p.qc, s_tbl, want_codes, &codes8);
+    const uint4 o = prep.template apply<SYM>(v[k], p.qc, s_tbl, want_codes, &codes8);
     sts128(lbase + j * 16, o);
     if (want_codes && lane_vec + j < t.n_vec) *reinterpret_cast<uint2*>(t.codes + (t.vec0 + lane_vec + j) * 8) = codes8;
   }
@@ -740,7 +743,7 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
       prep.setup(mx, mn, p.qc, SYM, s_tbl);
       for (uint32_t i = tid; i < t.n_vec; i += n_cons) {
         uint2 codes8;
-        const uint4 o = prep.apply(lds128(sdata + (size_t)i * 16), p.qc, s_tbl, want_codes, &codes8);
+        const uint4 o = prep.template apply<SYM>(lds128(sdata + (size_t)i * 16), p.qc, s_tbl, want_codes, &codes8);
         stg128(t.dst + (size_t)i * 16, o);
         if (want_codes) *reinterpret_cast<uint2*>(t.codes + (size_t)i * 8) = codes8;
       }
@@ -785,6 +788,7 @@ struct PreparedPairInt {
     *sa = qa.s; *za = qa.z; *sb = qb.s; *zb = qb.z;
     *bad = qa.bad || qb.bad;
   }
+  template <bool SYM>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const {
     typename DType<DT>::T2 d;
     return f.apply(w2, &d);
@@ -805,6 +809,7 @@ struct PreparedPair<DT, KIND_INT_GENERIC> {
     *sa = qa.s; *za = qa.z; *sb = qb.s; *zb = qb.z;
     *bad = qa.bad || qb.bad;
   }
+  template <bool SYM>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts& c) const {
     float k;
     const uint32_t lo = int_generic_elem<DT>((uint16_t)(w2 & 0xFFFFu), qa, c, &k);
@@ -823,9 +828,10 @@ struct PreparedPair<DT, KIND_FP> {
     *sa = qa.S; *za = qa.mid; *sb = qb.S; *zb = qb.mid;
     *bad = qa.bad || qb.bad;
   }
+  template <bool SYM>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const {
     typename DType<DT>::T2 v;
-    return f.slow_div ? f.template apply<true>(w2, &v) : f.template apply<false>(w2, &v);
+    return f.slow_div ? f.template apply<true, SYM ? 0 : 1>(w2, &v) : f.template apply<false, SYM ? 0 : 1>(w2, &v);
   }
 };
 
@@ -838,6 +844,7 @@ struct PreparedPair<DT, KIND_BFP> {
     *sa = 0.f; *za = 0.f; *sb = 0.f; *zb = 0.f;
     *bad = false;
   }
+  template <bool SYM>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const { return f.apply(w2); }
 };
 
@@ -966,15 +973,15 @@ __global__ void __launch_bounds__(256) col_kernel(const __grid_constant__ Launch
         const uint4 v0 = ldg128(src + (size_t)k * jb.row_bytes);
         const uint4 v1 = ldg128(src + (size_t)(k + 8) * jb.row_bytes);
         uint4 o0, o1;
-        o0.x = prep[0].apply(v0.x, p.qc); o0.y = prep[1].apply(v0.y, p.qc); o0.z = prep[2].apply(v0.z, p.qc); o0.w = prep[3].apply(v0.w, p.qc);
-        o1.x = prep[0].apply(v1.x, p.qc); o1.y = prep[1].apply(v1.y, p.qc); o1.z = prep[2].apply(v1.z, p.qc); o1.w = prep[3].apply(v1.w, p.qc);
+        o0.x = prep[0].template apply<SYM>(v0.x, p.qc); o0.y = prep[1].template apply<SYM>(v0.y, p.qc); o0.z = prep[2].template apply<SYM>(v0.z, p.qc); o0.w = prep[3].template apply<SYM>(v0.w, p.qc);
+        o1.x = prep[0].template apply<SYM>(v1.x, p.qc); o1.y = prep[1].template apply<SYM>(v1.y, p.qc); o1.z = prep[2].template apply<SYM>(v1.z, p.qc); o1.w = prep[3].template apply<SYM>(v1.w, p.qc);
         stg128(dst + (size_t)k * jb.row_bytes, o0);
         stg128(dst + (size_t)(k + 8) * jb.row_bytes, o1);
       }
       for (; k < g; k += 8) {
         const uint4 v0 = ldg128(src + (size_t)k * jb.row_bytes);
         uint4 o0;
-        o0.x = prep[0].apply(v0.x, p.qc); o0.y = prep[1].apply(v0.y, p.qc); o0.z = prep[2].apply(v0.z, p.qc); o0.w = prep[3].apply(v0.w, p.qc);
+        o0.x = prep[0].template apply<SYM>(v0.x, p.qc); o0.y = prep[1].template apply<SYM>(v0.y, p.qc); o0.z = prep[2].template apply<SYM>(v0.z, p.qc); o0.w = prep[3].template apply<SYM>(v0.w, p.qc);
         stg128(dst + (size_t)k * jb.row_bytes, o0);
       }
     }

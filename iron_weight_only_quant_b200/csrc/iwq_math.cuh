@@ -483,45 +483,59 @@ struct FpTable {
     return from_u32<T2>(vb | sgn);
   }
 
-  // Same function as grid(), evaluated through the step table: one 8-byte shared-memory load per element
-  // (intervals are few, so lanes mostly share entries and bank conflicts are rare), a packed compare and a
-  // select.  No per-binade constants, no table walk.
+  // Same function as grid(), evaluated through the step table: one 8-byte shared-memory load per element, a
+  // packed compare and a select.  No per-binade constants, no table walk.  The kernel is bound by the ALU pipe
+  // (LOP3 / SHF / PRMT / HMNMX2 / HSET2 issue at half rate), so the sequence is written to minimise those:
+  //   * fp16: the table starts at bit pattern 0 (kFromZero), so there is no lower clamp and no offset subtract;
+  //   * |n| is a source modifier of the min, the sign comes from n + (+0.0) (an FMA-pipe HADD2 that turns the
+  //     -0.0 of an underflowed quotient into +0.0: sign = (n < 0), quant_linear.py:130) and one LOP3;
+  //   * the three packed constants are gathered with one PRMT each.
+  static constexpr bool kFromZero = (DT == IWQ_F16);
   IWQ_HD T2 grid_steps(T2 n2, uint32_t sign_src) const {
-    const uint32_t nb = as_u32(n2);
-    T2 a = from_u32<T2>(nb & 0x7FFF7FFFu);
-    a = __hmin2(a, fmax2);
-    a = __hmax2(a, lutlo2);
-    const uint32_t d = as_u32(a) - lo2;  // per-half pattern offset; no borrow (a >= lo in both halves)
-    const uint32_t i0 = (d & 0xFFFFu) >> sh;
+    T2 a = __hmin2(__habs2(n2), fmax2);
+    uint32_t d = as_u32(a);
+    if (!kFromZero) {
+      a = __hmax2(a, lutlo2);
+      d = as_u32(a) - lo2;  // per-half pattern offset; no borrow (a >= lo in both halves)
+    }
+    const uint32_t i0 = (d << 16) >> (16u + sh);
     const uint32_t i1 = d >> (16u + sh);
     uint2 e0, e1;
 #ifdef __CUDA_ARCH__
     asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(e0.x), "=r"(e0.y) : "r"(steps_saddr + i0 * 8u));
     asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(e1.x), "=r"(e1.y) : "r"(steps_saddr + i1 * 8u));
+    const uint32_t thr = __byte_perm(e0.x, e1.x, 0x5410);
+    const uint32_t below = __byte_perm(e0.x, e1.x, 0x7632);
+    const uint32_t above = __byte_perm(e0.y, e1.y, 0x5410);
 #else
     e0 = *reinterpret_cast<const uint2*>(steps + i0);
     e1 = *reinterpret_cast<const uint2*>(steps + i1);
-#endif
     const uint32_t thr = (e0.x & 0xFFFFu) | (e1.x << 16);
     const uint32_t below = (e0.x >> 16) | (e1.x & 0xFFFF0000u);
     const uint32_t above = (e0.y & 0xFFFFu) | (e1.y << 16);
+#endif
     const uint32_t m = __hge2_mask(a, from_u32<T2>(thr));
     const uint32_t vb = (below & ~m) | (above & m);
-    const uint32_t sgn = rne ? (sign_src & 0x80008000u) : (__hlt2_mask(n2, from_u32<T2>(0u)) & 0x80008000u);
-    return from_u32<T2>(vb | sgn);
+    const uint32_t ss = rne ? sign_src : as_u32(__hadd2(n2, from_u32<T2>(0u)));
+    return from_u32<T2>(vb | (ss & 0x80008000u));
   }
 
-  template <bool SLOW>
+  // ASYM: 1 / 0 fixes the asymmetric (mid/span) form at compile time (the kernels pass their SYM template
+  // constant); -1 reads the runtime flag (test emulator).
+  template <bool SLOW, int ASYM = -1>
   IWQ_HD uint32_t apply(uint32_t w2, T2* v2) const {
+    const bool as = ASYM < 0 ? asym : (ASYM != 0);
     T2 w = from_u32<T2>(w2);
-    if (asym) w = __hsub2(w, mid2);                                   // weight - zeros            :755
+    if (as) w = __hsub2(w, mid2);                                     // weight - zeros            :755
     T2 n = SLOW ? ieee_quot2<DT>(w, S) : fast_quot2<DT>(w, S, r);     // / scales
     T2 v = grid_steps(n, w2);
     // a NaN quotient (only possible when S is 0/inf/NaN, i.e. the slow path) must stay NaN: the clamp removed it
     if (SLOW) v = from_u32<T2>(as_u32(v) | __hneu2_mask(n, n));
     *v2 = v;
-    T2 o = __hmul2(v, S2);                                            // decoded.to(D) * scales    :774
-    if (asym) o = __hadd2(o, midh2);                                  // + zeros.half().to(D)      :776
+    // _rn forms: the product is rounded to D before the add (two ATen ops); plain __hmul2 + __hadd2 may be
+    // contracted into one HFMA2 by ptxas once `as` is a compile-time constant
+    T2 o = __hmul2_rn(v, S2);                                         // decoded.to(D) * scales    :774
+    if (as) o = __hadd2_rn(o, midh2);                                 // + zeros.half().to(D)      :776
     return as_u32(o);
   }
 };
