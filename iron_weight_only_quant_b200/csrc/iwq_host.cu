@@ -43,6 +43,10 @@ struct Knobs {
   int row_smem_kb = env_int("IWQ_ROW_SMEM_KB", 0);  // per-CTA ring budget; 0 = automatic
   int variant = env_int("IWQ_VARIANT", -1);          // -1: use cfg->variant
   int row_warps = env_int("IWQ_ROW_WARPS", 0);       // consumer warps of the row kernels; 0 = automatic
+  int col_tile = env_int("IWQ_COL_TILE", 0);         // quant_dim = 1: columns per tile (64/128/256), -1 = two-sweep kernel
+  int col_ctas = env_int("IWQ_COL_CTAS", 0);
+  int col_mode = env_int("IWQ_COL_MODE", 0);         // 0: warp-private cp.async ring (col_async_kernel), 1: register-resident
+  int col_stages = env_int("IWQ_COL_STAGES", 0);     // ring depth of col_async_kernel (1..4); 0 = automatic
 };
 static const Knobs& knobs() {
   static Knobs k;
@@ -399,9 +403,37 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
   return IWQ_OK;
 }
 
+// Tile shape for quant_dim = 1 segments of `g` rows.  lpr lanes cover a strip row (16 * lpr bytes).
+// Default (col_async_kernel): tile = 32 * lpr columns (4 warps), *rpl = 0, ring of *stages x g * 16 * lpr bytes
+// per warp.  IWQ_COL_MODE=1 (col_reg_kernel): tile = 64 * lpr columns (8 warps), *rpl = g * lpr / 32 vectors per
+// lane held in registers.  Returns 0 for the two-sweep col_kernel (other group sizes, per-channel columns).
+static uint32_t col_tile_for(int64_t g, int* rpl, int* stages) {
+  if (knobs().col_tile < 0) return 0;
+  if (g != 32 && g != 64 && g != 128 && g != 256 && g != 512) return 0;
+  uint32_t lpr = g <= 128 ? 4 : g == 256 ? 2 : 1;
+  if (knobs().col_tile == 128 && g <= 128) lpr = 2;
+  if (knobs().col_tile == 64 && g <= 256) lpr = 1;
+  if (knobs().col_mode == 1) {
+    const int64_t r = g * lpr / 32;
+    if (r != 4 && r != 8 && r != 16) return 0;
+    *rpl = (int)r;
+    return 64u * lpr;
+  }
+  *rpl = 0;
+  // measured on B200 (profiles/r01_col_kernel_notes.md): a single stage with 4..6 CTAs per SM beats a deeper
+  // per-warp ring with fewer resident warps
+  int st = knobs().col_stages > 0 ? knobs().col_stages : 1;
+  if (st > 4) st = 4;
+  *stages = st;
+  return 32u * lpr;
+}
+
 static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, LaunchParams& p, int kind, void* workspace, size_t ws_bytes, cudaStream_t st) {
   std::vector<Job> jobs;
   uint64_t units = 0;
+  int rpl = 0, stages = 0;
+  const uint32_t ctile = (cfg->group > 0 && p.qc.approx != 2) ? col_tile_for(cfg->group, &rpl, &stages) : 0u;
+  const uint32_t unit_cols = ctile ? ctile : (uint32_t)kColTile;
   for (int i = 0; i < n; ++i) {
     int rc = check_matrix(&ms[i]);
     if (rc) return rc;
@@ -425,7 +457,7 @@ static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, Launc
       if (row_blocks % 4 != 0) return fail(IWQ_ERR_UNSUPPORTED, "double-approximate decode needs (rows / group) % 4 == 0");
       row_blocks /= 4;
     }
-    units += row_blocks * (uint64_t)((cols + kColTile - 1) / kColTile);
+    units += row_blocks * (uint64_t)((cols + unit_cols - 1) / unit_cols);
     if (units >= 0xFFFFFFFFull) return fail(IWQ_ERR_INVALID, "too much work for one launch");
     jobs.push_back(j);
   }
@@ -434,11 +466,20 @@ static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, Launc
   p.single = jobs[0];
   p.jobs = nullptr;
   p.col_group = cfg->group > 0 ? (uint32_t)cfg->group : 0u;
+  p.col_tile = ctile;
+  p.col_rpl = (uint32_t)rpl;
+  if (ctile && rpl == 0) {
+    p.stage_bytes = (uint32_t)cfg->group * (ctile / 2);  // g rows x 16 * lpr bytes, lpr = ctile / 32
+    p.n_stages = stages;
+  }
   int rc = upload_jobs(jobs, workspace, ws_bytes, &p, st);
   if (rc) return rc;
   LaunchTuning tune;
   tune.stages = 0;
-  tune.ctas_per_sm = 0;
+  tune.ctas_per_sm = knobs().col_ctas;
+  // the light INT / BFP element stages run best with 4 CTAs (16 warps) per SM at group >= 128; the minifloat
+  // stage (two table lookups per pair) wants every warp it can get
+  if (tune.ctas_per_sm == 0 && ctile && rpl == 0 && kind != KIND_FP && cfg->group >= 128) tune.ctas_per_sm = 4;
   cudaError_t e;
   if (p.qc.approx == 2)
     e = cfg->dtype == IWQ_F16 ? launch_col_double<IWQ_F16>(p, st) : launch_col_double<IWQ_BF16>(p, st);

@@ -63,6 +63,8 @@ struct LaunchParams {
   const FpStep* lut;       // KIND_FP: device step table (qc.lut_n entries), copied into shared memory by every CTA
   uint32_t lut_smem_bytes; // bytes reserved for it in front of the ring (multiple of 1024; 0 for INT kinds)
   uint32_t col_group;      // quant_dim = 1: rows per segment (0: the whole column, i.e. per-channel)
+  uint32_t col_tile;       // col_reg_kernel: columns per tile (64 / 128 / 256), 0 = col_kernel
+  uint32_t col_rpl;        // col_reg_kernel: vectors (rows) per lane = col_group * (col_tile / 64) / 32
   QuantConsts qc;
 };
 
@@ -986,6 +988,306 @@ __global__ void __launch_bounds__(256) col_kernel(const __grid_constant__ Launch
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// col_reg_kernel (default for quant_dim = 1 with group 32 .. 512): the whole segment lives in REGISTERS.
+//
+// A tile is `g` rows x C columns (C = 256 / 128 / 64).  Warp w owns the strip of C/8 columns [w*C/8, ...) for
+// all rows, so a segment never leaves the warp: no shared memory, no barrier.  Inside the warp lpr = C/64 lanes
+// cover one row of the strip (one 16-byte vector = 8 columns per lane) and the 32/lpr lane groups take the rows
+// r, r + 32/lpr, ...: RPL = g * lpr / 32 vectors per lane, all loaded up front (RPL 128-bit loads in flight per
+// lane: 8 KB per warp at RPL = 16, which is what hides the HBM latency), reduced element-wise (HMNMX2) and with
+// log2(32/lpr) butterfly rounds, quantised in registers and stored.  Every byte crosses HBM exactly once each way.
+// (A 1-D TMA staged variant was measured first: one bulk copy per 256..512-byte row piece makes the kernel
+// TMA-issue-bound at ~3.7 TB/s, see profiles/.)
+// ------------------------------------------------------------------------------------------------
+template <int DT, bool SYM>
+__device__ __forceinline__ void col_range_update(uint32_t (&mx)[4], uint32_t (&mn)[4], const uint4& v) {
+  using T2 = typename DType<DT>::T2;
+  const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (SYM) {
+      mx[j] = as_u32(__hmax2_nan(from_u32<T2>(mx[j]), __habs2(from_u32<T2>(w4[j]))));
+    } else {
+      mx[j] = as_u32(__hmax2_nan(from_u32<T2>(mx[j]), from_u32<T2>(w4[j])));
+      mn[j] = as_u32(__hmin2_nan(from_u32<T2>(mn[j]), from_u32<T2>(w4[j])));
+    }
+  }
+}
+
+template <int DT, int KIND, bool SYM, int RPL>
+__global__ void __launch_bounds__(256, 2) col_reg_kernel(const __grid_constant__ LaunchParams p) {
+  using T2 = typename DType<DT>::T2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const FpStep* s_tbl = nullptr;
+  if (KIND == KIND_FP) {
+    s_tbl = load_fp_lut(p, smem);
+    __syncthreads();
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t C = p.col_tile, g = p.col_group;
+  const uint32_t lpr = C >> 6;                 // lanes per strip row: 4 / 2 / 1
+  const uint32_t rps = 32u / lpr;              // rows per warp-wide access
+  const uint32_t sub = (uint32_t)lane & (lpr - 1u), rph = (uint32_t)lane / lpr;
+  const uint32_t tcol = (uint32_t)warp * (C >> 3) + sub * 8u;  // this lane's first column inside the tile
+  const uint32_t ident_max = SYM ? 0u : (DT == IWQ_F16 ? 0xFC00FC00u : 0xFF80FF80u);  // {0,0} | {-inf,-inf}
+  const uint32_t ident_min = DT == IWQ_F16 ? 0x7C007C00u : 0x7F807F80u;                // {+inf,+inf}
+  int cur = -1;
+  Job jb;
+  for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+    advance_job(p, tile, &cur, &jb);
+    const uint32_t cols = jb.row_bytes >> 1;
+    const uint32_t rows = (uint32_t)(jb.bytes / jb.row_bytes);
+    const uint32_t n_ct = (cols + C - 1) / C;
+    const uint32_t local = tile - jb.first_unit;
+    const uint32_t rb = local / n_ct, ct = local - rb * n_ct;
+    const uint32_t col = ct * C + tcol;
+    const bool live = col < cols;  // cols is a multiple of 8 (checked on the host)
+    const size_t off = ((size_t)rb * g + rph) * jb.row_bytes + (size_t)col * 2;
+    const size_t step = (size_t)rps * jb.row_bytes;
+    const uint8_t* src = jb.src + off;
+    uint8_t* dst = jb.dst + off;
+
+    uint4 v[RPL];
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) v[i] = live ? ldg128(src + (size_t)i * step) : make_uint4(0u, 0u, 0u, 0u);
+
+    // ---- per-column range: this lane's rows, then across the lane groups ----
+    uint32_t mx[4] = {ident_max, ident_max, ident_max, ident_max};
+    uint32_t mn[4] = {ident_min, ident_min, ident_min, ident_min};
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) col_range_update<DT, SYM>(mx, mn, v[i]);
+#pragma unroll 1
+    for (uint32_t o = lpr; o < 32u; o <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mx[j] = as_u32(__hmax2_nan(from_u32<T2>(mx[j]), from_u32<T2>(__shfl_xor_sync(0xFFFFFFFFu, mx[j], o))));
+        if (!SYM) mn[j] = as_u32(__hmin2_nan(from_u32<T2>(mn[j]), from_u32<T2>(__shfl_xor_sync(0xFFFFFFFFu, mn[j], o))));
+      }
+    }
+
+    // ---- per-column parameters: 4 packed pairs per lane ----
+    PreparedPair<DT, KIND> prep[4];
+    bool any_bad = false;
+    const size_t n_rb = rows / g;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float mxa = DType<DT>::to_f32((uint16_t)(mx[j] & 0xFFFFu)), mxb = DType<DT>::to_f32((uint16_t)(mx[j] >> 16));
+      const float mna = DType<DT>::to_f32((uint16_t)(mn[j] & 0xFFFFu)), mnb = DType<DT>::to_f32((uint16_t)(mn[j] >> 16));
+      float sa, za, sb, zb;
+      bool bad;
+      prep[j].setup2(mxa, SYM ? -mxa : mna, mxb, SYM ? -mxb : mnb, p.qc, SYM, s_tbl, &sa, &za, &sb, &zb, &bad);
+      any_bad |= bad;
+      if (live && rph == 0) {
+        // segment order of the reference for quant_dim = 1: column-major over (column, row block)
+        const size_t ga = (size_t)(col + 2 * j) * n_rb + rb, gb = ga + n_rb;
+        if (jb.scales) {
+          reinterpret_cast<uint16_t*>(jb.scales)[ga] = DType<DT>::from_f32(sa);
+          reinterpret_cast<uint16_t*>(jb.scales)[gb] = DType<DT>::from_f32(sb);
+        }
+        if (jb.zeros) {
+          reinterpret_cast<uint16_t*>(jb.zeros)[ga] = DType<DT>::from_f32(za);
+          reinterpret_cast<uint16_t*>(jb.zeros)[gb] = DType<DT>::from_f32(zb);
+        }
+      }
+    }
+    if (live && any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
+
+    // ---- element stage on the registers, store in place ----
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      uint4 o;
+      o.x = prep[0].template apply<SYM>(v[i].x, p.qc);
+      o.y = prep[1].template apply<SYM>(v[i].y, p.qc);
+      o.z = prep[2].template apply<SYM>(v[i].z, p.qc);
+      o.w = prep[3].template apply<SYM>(v[i].w, p.qc);
+      if (live) stg128(dst + (size_t)i * step, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// col_async_kernel (default for quant_dim = 1 with group 32 .. 512): like col_reg_kernel a warp owns a column
+// strip (16*lpr bytes per row) of the tile for all `g` rows, but the strip is parked in a WARP-PRIVATE
+// shared-memory ring filled with 16-byte cp.async copies issued by the warp itself, which frees the 64 data
+// registers of col_reg_kernel: twice the resident warps, and with n_stages >= 2 the copies of the warp's next
+// tile are in flight while it reduces and quantises the current one.  Nothing but __syncwarp() couples the lanes:
+// no barrier, no mbarrier.  The strip is stored densely ([row][16*lpr bytes]), so a warp-wide LDS.128 reads 512
+// contiguous bytes.  blockDim.x = 128 (4 warps): tile = g rows x 32*lpr columns; shared memory = LUT + 4 warps x
+// n_stages x g*16*lpr bytes.
+// (Measured alternatives, profiles/r01_col_kernel_notes.md: 1-D TMA row pieces are TMA-issue-bound; a CTA-wide
+// row-coalesced cp.async ring with two barriers per tile leaves only 8 warps per SM and is compute-latency-bound.)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {  // n = groups that may stay in flight (0..3)
+  if (n <= 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+  else if (n == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+  else if (n == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+  else asm volatile("cp.async.wait_group 3;" ::: "memory");
+}
+
+struct ColTile {        // per-lane view of one tile
+  uint8_t* dst;         // this lane's first output vector (row rph of the row block, its 8 columns)
+  uint8_t* scales;
+  uint8_t* zeros;
+  size_t step;          // bytes between the lane's consecutive rows = rps * row_bytes
+  size_t seg0;          // segment index of the lane's first column: col * n_rb + rb
+  uint32_t n_rb;
+  bool live;
+};
+
+constexpr int kColAsyncWarps = 4;
+
+template <int DT, int KIND, bool SYM>
+__global__ void __launch_bounds__(kColAsyncWarps * 32) col_async_kernel(const __grid_constant__ LaunchParams p) {
+  using T2 = typename DType<DT>::T2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const FpStep* s_tbl = nullptr;
+  if (KIND == KIND_FP) {
+    s_tbl = load_fp_lut(p, smem);
+    __syncthreads();
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t C = p.col_tile, g = p.col_group;
+  const int n_stages = p.n_stages;
+  const uint32_t lpr = C >> 5;                 // lanes per strip row: 4 / 2 / 1   (C = 32 * lpr columns per 4-warp tile)
+  const uint32_t rps = 32u / lpr;              // rows per warp-wide access
+  const uint32_t sub = (uint32_t)lane & (lpr - 1u), rph = (uint32_t)lane / lpr;
+  const uint32_t tcol = (uint32_t)warp * (8u * lpr) + sub * 8u;  // this lane's first column inside the tile
+  const uint32_t n_it = g / rps;               // vectors per lane per tile
+  const uint32_t stage_bytes = p.stage_bytes;  // g * 16 * lpr
+  uint8_t* ring = smem + p.lut_smem_bytes + (size_t)warp * n_stages * stage_bytes + (size_t)lane * 16u;  // + it * 512
+  const uint32_t ident_max = SYM ? 0u : (DT == IWQ_F16 ? 0xFC00FC00u : 0xFF80FF80u);  // {0,0} | {-inf,-inf}
+  const uint32_t ident_min = DT == IWQ_F16 ? 0x7C007C00u : 0x7F807F80u;                // {+inf,+inf}
+  int cur_l = -1, cur_c = -1;  // job cursors: copy issue runs n_stages - 1 tiles ahead of the arithmetic
+  Job jb_l, jb_c;
+
+  auto describe = [&](uint32_t tile, int* cur, Job* jb, const uint8_t** src) -> ColTile {
+    ColTile t;
+    advance_job(p, tile, cur, jb);
+    const uint32_t cols = jb->row_bytes >> 1;
+    const uint32_t rows = (uint32_t)(jb->bytes / jb->row_bytes);
+    const uint32_t n_ct = (cols + C - 1) / C;
+    const uint32_t local = tile - jb->first_unit;
+    const uint32_t rb = local / n_ct, ct = local - rb * n_ct;
+    const uint32_t col = ct * C + tcol;
+    t.live = col < cols;
+    const size_t off = ((size_t)rb * g + rph) * jb->row_bytes + (size_t)col * 2;
+    t.step = (size_t)rps * jb->row_bytes;
+    t.dst = jb->dst + off;
+    t.scales = jb->scales;
+    t.zeros = jb->zeros;
+    t.n_rb = rows / g;
+    t.seg0 = (size_t)col * t.n_rb + rb;
+    *src = jb->src + off;
+    return t;
+  };
+  auto issue = [&](uint32_t tile, int st) {
+    if (tile < p.total_units) {
+      const uint8_t* src;
+      const ColTile t = describe(tile, &cur_l, &jb_l, &src);
+      if (t.live) {
+        uint8_t* sd = ring + (size_t)st * stage_bytes;
+        for (uint32_t i = 0; i < n_it; ++i) cp_async_16(sd + (size_t)i * 512u, src + (size_t)i * t.step);
+      }
+    }
+    cp_async_commit();  // (possibly empty) group: keeps the group count per tile uniform
+  };
+
+  for (int s = 0; s < n_stages - 1; ++s) issue(blockIdx.x + (uint32_t)s * gridDim.x, s);
+  int st = 0;
+  for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+    {
+      int ps = st + n_stages - 1;
+      if (ps >= n_stages) ps -= n_stages;
+      issue(tile + (uint32_t)(n_stages - 1) * gridDim.x, ps);  // n_stages == 1: the current tile itself
+    }
+    cp_async_wait_dyn(n_stages - 1);
+    __syncwarp();  // every lane's copies of the current tile have landed
+    const uint8_t* unused;
+    const ColTile t = describe(tile, &cur_c, &jb_c, &unused);
+    const uint8_t* sd = ring + (size_t)st * stage_bytes;
+
+    // ---- sweep 1: per-column range over this lane's rows, then across the lane groups ----
+    uint32_t mx[4] = {ident_max, ident_max, ident_max, ident_max};
+    uint32_t mn[4] = {ident_min, ident_min, ident_min, ident_min};
+    {
+      uint32_t i = 0;
+      for (; i + 4 <= n_it; i += 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = lds128(sd + (size_t)(i + u) * 512u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) col_range_update<DT, SYM>(mx, mn, v[u]);
+      }
+      for (; i < n_it; ++i) col_range_update<DT, SYM>(mx, mn, lds128(sd + (size_t)i * 512u));
+    }
+#pragma unroll 1
+    for (uint32_t o = lpr; o < 32u; o <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mx[j] = as_u32(__hmax2_nan(from_u32<T2>(mx[j]), from_u32<T2>(__shfl_xor_sync(0xFFFFFFFFu, mx[j], o))));
+        if (!SYM) mn[j] = as_u32(__hmin2_nan(from_u32<T2>(mn[j]), from_u32<T2>(__shfl_xor_sync(0xFFFFFFFFu, mn[j], o))));
+      }
+    }
+
+    // ---- per-column parameters: 4 packed pairs per lane ----
+    PreparedPair<DT, KIND> prep[4];
+    bool any_bad = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float mxa = DType<DT>::to_f32((uint16_t)(mx[j] & 0xFFFFu)), mxb = DType<DT>::to_f32((uint16_t)(mx[j] >> 16));
+      const float mna = DType<DT>::to_f32((uint16_t)(mn[j] & 0xFFFFu)), mnb = DType<DT>::to_f32((uint16_t)(mn[j] >> 16));
+      float sa, za, sb, zb;
+      bool bad;
+      prep[j].setup2(mxa, SYM ? -mxa : mna, mxb, SYM ? -mxb : mnb, p.qc, SYM, s_tbl, &sa, &za, &sb, &zb, &bad);
+      any_bad |= bad;
+      if (t.live && rph == 0) {
+        // segment order of the reference for quant_dim = 1: column-major over (column, row block)
+        const size_t ga = t.seg0 + (size_t)(2 * j) * t.n_rb, gb = ga + t.n_rb;
+        if (t.scales) {
+          reinterpret_cast<uint16_t*>(t.scales)[ga] = DType<DT>::from_f32(sa);
+          reinterpret_cast<uint16_t*>(t.scales)[gb] = DType<DT>::from_f32(sb);
+        }
+        if (t.zeros) {
+          reinterpret_cast<uint16_t*>(t.zeros)[ga] = DType<DT>::from_f32(za);
+          reinterpret_cast<uint16_t*>(t.zeros)[gb] = DType<DT>::from_f32(zb);
+        }
+      }
+    }
+    if (t.live && any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
+
+    // ---- sweep 2: quantise from shared memory, store from registers ----
+    if (t.live) {
+      uint32_t i = 0;
+      for (; i + 2 <= n_it; i += 2) {
+        const uint4 v0 = lds128(sd + (size_t)i * 512u);
+        const uint4 v1 = lds128(sd + (size_t)(i + 1) * 512u);
+        uint4 o0, o1;
+        o0.x = prep[0].template apply<SYM>(v0.x, p.qc); o0.y = prep[1].template apply<SYM>(v0.y, p.qc);
+        o0.z = prep[2].template apply<SYM>(v0.z, p.qc); o0.w = prep[3].template apply<SYM>(v0.w, p.qc);
+        o1.x = prep[0].template apply<SYM>(v1.x, p.qc); o1.y = prep[1].template apply<SYM>(v1.y, p.qc);
+        o1.z = prep[2].template apply<SYM>(v1.z, p.qc); o1.w = prep[3].template apply<SYM>(v1.w, p.qc);
+        stg128(t.dst + (size_t)i * t.step, o0);
+        stg128(t.dst + (size_t)(i + 1) * t.step, o1);
+      }
+      for (; i < n_it; ++i) {
+        const uint4 v0 = lds128(sd + (size_t)i * 512u);
+        uint4 o0;
+        o0.x = prep[0].template apply<SYM>(v0.x, p.qc); o0.y = prep[1].template apply<SYM>(v0.y, p.qc);
+        o0.z = prep[2].template apply<SYM>(v0.z, p.qc); o0.w = prep[3].template apply<SYM>(v0.w, p.qc);
+        stg128(t.dst + (size_t)i * t.step, o0);
+      }
+    }
+    __syncwarp();  // the stage may be refilled by the next iteration's copies
+    if (++st == n_stages) st = 0;
+  }
+  cp_async_wait_dyn(0);
 }
 
 // ------------------------------------------------------------------------------------------------

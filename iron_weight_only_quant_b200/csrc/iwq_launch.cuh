@@ -86,6 +86,35 @@ cudaError_t launch_col_double(const LaunchParams& p, cudaStream_t st) {
 
 template <int DT, int KIND, bool SYM>
 static cudaError_t launch_col_one(LaunchParams p, const LaunchTuning& tune, cudaStream_t st) {
+  if (p.col_tile != 0 && p.col_rpl == 0) {  // warp-private cp.async ring (group 32 .. 512)
+    auto k = col_async_kernel<DT, KIND, SYM>;
+    const size_t smem = p.lut_smem_bytes + (size_t)kColAsyncWarps * p.n_stages * p.stage_bytes;
+    int grid = 0;
+    cudaError_t e = persistent_grid(k, kColAsyncWarps * 32, smem, tune.ctas_per_sm, p.total_units, &grid);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kColAsyncWarps * 32, smem, st>>>(p);
+    return cudaGetLastError();
+  }
+  if (p.col_tile != 0) {  // register-resident variant (group 32 .. 512)
+    const size_t smem = p.lut_smem_bytes;
+    int grid = 0;
+    cudaError_t e;
+#define IWQ_COL_REG(RPL)                                                                  \
+  do {                                                                                    \
+    auto k = col_reg_kernel<DT, KIND, SYM, RPL>;                                          \
+    e = persistent_grid(k, 256, smem, tune.ctas_per_sm, p.total_units, &grid);            \
+    if (e == cudaSuccess) {                                                               \
+      k<<<grid, 256, smem, st>>>(p);                                                      \
+      e = cudaGetLastError();                                                             \
+    }                                                                                     \
+  } while (0)
+    if (p.col_rpl == 16) IWQ_COL_REG(16);
+    else if (p.col_rpl == 8) IWQ_COL_REG(8);
+    else if (p.col_rpl == 4) IWQ_COL_REG(4);
+    else e = cudaErrorInvalidValue;
+#undef IWQ_COL_REG
+    return e;
+  }
   auto k = col_kernel<DT, KIND, SYM>;
   const size_t smem = 16384 + p.lut_smem_bytes;
   int grid = 0;

@@ -592,7 +592,8 @@ def test_single_approximate_matches_reference_golden(golden, dt, case):
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
 def test_quant_dim1_vs_oracle_larger(dt):
     """column-group kernel on shapes with several row blocks, a ragged last column tile and whole-column segments"""
-    for rows, cols, grp, nb, sym in [(1024, 520, 128, 4, False), (512, 1032, 64, 4, True), (384, 264, -2, 8, False), (2048, 256, 256, 3, False)]:
+    for rows, cols, grp, nb, sym in [(1024, 520, 128, 4, False), (512, 1032, 64, 4, True), (384, 264, -2, 8, False), (2048, 256, 256, 3, False),
+                                     (256, 72, 32, 4, True), (1024, 136, 512, 4, False), (2048, 64, 1024, 4, False), (96, 40, 8, 5, False)]:
         w = seeded(rows, cols, dt, rows + cols + 1)
         ref = O.along_output_dim(O.int_fake_quant, bits(w), dt, nb, not sym, grp)
         G = _lib.num_segments(rows, cols, grp, 1)

@@ -35,6 +35,9 @@ CONFIGS = {
     "bfp4g128": dict(scheme=_lib.SCHEME_BFP, group=128, bits=4, symmetric=True),
     "bfp6g64": dict(scheme=_lib.SCHEME_BFP, group=64, bits=6, symmetric=True),
     "int4g128_d1": dict(scheme=_lib.SCHEME_INT, group=128, bits=4, symmetric=False, quant_dim=1),
+    "int4g128sym_d1": dict(scheme=_lib.SCHEME_INT, group=128, bits=4, symmetric=True, quant_dim=1),
+    "int4g64_d1": dict(scheme=_lib.SCHEME_INT, group=64, bits=4, symmetric=False, quant_dim=1),
+    "int4g256_d1": dict(scheme=_lib.SCHEME_INT, group=256, bits=4, symmetric=False, quant_dim=1),
     "fp4e2m1g128_d1": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=2, mant_bits=1, symmetric=True, quant_dim=1),
     "fp4e2m1g128_d1_approx": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=2, mant_bits=1, symmetric=True, quant_dim=1, approx=1, hi_align_start=1, hi_align_exp_field=1, tail_pad_bits=0),
     "fp4e2m1g128_d1_double": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=2, mant_bits=1, symmetric=True, quant_dim=1, approx=2, hi_align_start=0, hi_align_exp_field=2, tail_pad_bits=1),
@@ -51,15 +54,19 @@ def main():
     ap.add_argument("--dtype", default="f16")
     ap.add_argument("--configs", default="int4g128,int4g128sym,int4g32,int8pc,int4pt,fp4e2m1g128,fp8e4m3g128")
     ap.add_argument("--no-emit", action="store_true", help="do not emit scales/zeros")
+    ap.add_argument("--shape", default="", help="rows,cols[,count]: use `count` matrices of this shape instead of a model's layers")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     dt = torch.float16 if args.dtype == "f16" else torch.bfloat16
     m = shapes.MODELS[args.model]
     mats = m.matrices(range(args.layers if args.layers > 0 else m.n_layers))
+    if args.shape:
+        f = [int(x) for x in args.shape.split(",")]
+        mats = [(f[0], f[1])] * (f[2] if len(f) > 2 else 1)
     ws = [(torch.randn(o, k, device=dev, dtype=torch.float32) * 0.02).to(dt) for o, k in mats]
     n = sum(w.numel() for w in ws)
     knobs = {k: os.environ[k] for k in os.environ if k.startswith("IWQ_")}
-    res = {"knobs": knobs, "model": args.model, "layers": args.layers if args.layers > 0 else m.n_layers, "dtype": args.dtype, "weights": n, "results": {}}
+    res = {"knobs": knobs, "model": args.shape or args.model, "layers": args.layers if args.layers > 0 else m.n_layers, "dtype": args.dtype, "weights": n, "results": {}}
 
     def timeit(fn):
         for _ in range(3):
