@@ -103,6 +103,7 @@ static inline int build_quant_consts(const iwq_config_t* cfg, QuantConsts* c, in
     c->hi_field = cfg->hi_align_exp_field;
     c->tail_pad = cfg->tail_pad_bits;
     if (c->tail_pad < -8 || c->tail_pad > 8) return fail(IWQ_ERR_INVALID, "tail_pad_bits out of range");
+    if (c->approx == 2 && (c->hi_field < 0 || c->hi_field > 31)) return fail(IWQ_ERR_UNSUPPORTED, "double-approximate decode: hi_align_exp_field must be in [0, 31]");
   }
   const int MB = dt == IWQ_F16 ? 10 : 7, DB = dt == IWQ_F16 ? 15 : 127;
   const int max_field = dt == IWQ_F16 ? 30 : 254;
@@ -238,6 +239,29 @@ static inline bool build_step_table_t(const QuantConsts& c, FpStep* out) {
 }
 static inline bool build_step_table(int dtype, const QuantConsts& c, FpStep* out) {
   return dtype == IWQ_F16 ? build_step_table_t<IWQ_F16>(c, out) : build_step_table_t<IWQ_BF16>(c, out);
+}
+
+// Tables of the double-approximate decode (see double_approx_info in iwq_math.cuh): the step table with the
+// INFO word of each grid value in place of the value, and val[target << 8 | sign << 7 | code magnitude].
+template <int DT>
+static inline bool build_double_tables_t(const QuantConsts& c, FpStep* steps, uint16_t* val) {
+  if (!build_step_table_t<DT>(c, steps)) return false;  // approx == 2 leaves the values themselves untouched
+  const int E = c.exp_bits, M = c.mant_bits;
+  for (uint32_t i = 0; i < c.lut_n; ++i) {
+    steps[i].below = double_approx_info(fp_code_of<DT>(steps[i].below, E, M), c);
+    steps[i].above = double_approx_info(fp_code_of<DT>(steps[i].above, E, M), c);
+  }
+  for (int t = 0; t < 32; ++t)
+    for (uint32_t k = 0; k < 256; ++k) {
+      const uint32_t mag = k & 0x7Fu, sign = k >> 7;
+      uint16_t v = 0;
+      if (mag < (1u << (E + M))) v = double_approx_elem<DT>(mag | (sign << (E + M)), t, c);
+      val[(t << 8) | k] = v;
+    }
+  return true;
+}
+static inline bool build_double_tables(int dtype, const QuantConsts& c, FpStep* steps, uint16_t* val) {
+  return dtype == IWQ_F16 ? build_double_tables_t<IWQ_F16>(c, steps, val) : build_double_tables_t<IWQ_BF16>(c, steps, val);
 }
 
 }  // namespace iwq

@@ -70,8 +70,9 @@ static int get_fp_lut(const iwq_config_t* cfg, const QuantConsts& qc, cudaStream
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
-  auto key = std::make_tuple(dev, cfg->dtype, cfg->exp_bits, cfg->mant_bits, qc.flavour_rne, qc.approx == 1 ? 1 : 0,
-                             qc.approx == 1 ? qc.hi_start : 0, qc.approx == 1 ? qc.hi_field : 0, qc.approx == 1 ? qc.tail_pad : 0);
+  const bool ap = qc.approx != 0;
+  auto key = std::make_tuple(dev, cfg->dtype, cfg->exp_bits, cfg->mant_bits, qc.flavour_rne, qc.approx, ap ? qc.hi_start : 0,
+                             ap ? qc.hi_field : 0, ap ? qc.tail_pad : 0);
   std::lock_guard<std::mutex> lk(g_lut_mu);
   auto it = g_luts.find(key);
   if (it != g_luts.end()) {
@@ -79,13 +80,18 @@ static int get_fp_lut(const iwq_config_t* cfg, const QuantConsts& qc, cudaStream
     return IWQ_OK;
   }
   if (qc.lut_n > 4096) return fail(IWQ_ERR_UNSUPPORTED, "minifloat step table too large");
-  std::vector<FpStep> host(qc.lut_n);
-  if (!build_step_table(cfg->dtype, qc, host.data()))
-    return fail(IWQ_ERR_UNSUPPORTED, "minifloat format changes value more than once inside a half-step interval");
+  // approx == 2: [step table in info form, padded to 1 KB][value table, 16 KB] (build_double_tables)
+  const size_t step_bytes = ((size_t)qc.lut_n * sizeof(FpStep) + 1023) & ~(size_t)1023;
+  const size_t total = qc.approx == 2 ? step_bytes + kDblValEntries * sizeof(uint16_t) : (size_t)qc.lut_n * sizeof(FpStep);
+  std::vector<uint8_t> host(total, 0);
+  FpStep* hsteps = reinterpret_cast<FpStep*>(host.data());
+  const bool ok = qc.approx == 2 ? build_double_tables(cfg->dtype, qc, hsteps, reinterpret_cast<uint16_t*>(host.data() + step_bytes))
+                                 : build_step_table(cfg->dtype, qc, hsteps);
+  if (!ok) return fail(IWQ_ERR_UNSUPPORTED, "minifloat format changes value more than once inside a half-step interval");
   FpStep* buf = nullptr;
-  e = cudaMalloc((void**)&buf, host.size() * sizeof(FpStep));
+  e = cudaMalloc((void**)&buf, total);
   if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(minifloat step table)");
-  e = cudaMemcpyAsync(buf, host.data(), host.size() * sizeof(FpStep), cudaMemcpyHostToDevice, st);
+  e = cudaMemcpyAsync(buf, host.data(), total, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // one-time: later calls may come on any stream
   if (e != cudaSuccess) {
     cudaFree(buf);
@@ -341,6 +347,7 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
     rc = get_fp_lut(cfg, p.qc, st, &p.lut);
     if (rc) return rc;
     p.lut_smem_bytes = (uint32_t)(((size_t)p.qc.lut_n * sizeof(FpStep) + 1023) & ~(size_t)1023);
+    p.lut_extra_bytes = p.qc.approx == 2 ? (uint32_t)(kDblValEntries * sizeof(uint16_t)) : 0u;
   }
   if (p.qc.approx == 2 && cfg->quant_dim != 1)
     return fail(IWQ_ERR_UNSUPPORTED, "double-approximate decode is implemented for quant_dim = 1 only (what the reference's scripts use)");

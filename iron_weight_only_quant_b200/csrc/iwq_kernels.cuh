@@ -62,6 +62,7 @@ struct LaunchParams {
   int32_t* status;
   const FpStep* lut;       // KIND_FP: device step table (qc.lut_n entries), copied into shared memory by every CTA
   uint32_t lut_smem_bytes; // bytes reserved for it in front of the ring (multiple of 1024; 0 for INT kinds)
+  uint32_t lut_extra_bytes;// double-approximate decode: value table behind the step table (device: lut + lut_smem_bytes)
   uint32_t col_group;      // quant_dim = 1: rows per segment (0: the whole column, i.e. per-channel)
   uint32_t col_tile;       // col_reg_kernel: columns per tile (64 / 128 / 256), 0 = col_kernel
   uint32_t col_rpl;        // col_reg_kernel: vectors (rows) per lane = col_group * (col_tile / 64) / 32
@@ -411,11 +412,16 @@ __device__ __forceinline__ void consume_tile(uint4 (&v)[kVPT], const TileCtx& t,
   if (any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
 }
 
-// Copy the minifloat step table into shared memory (all threads; caller syncs).
+// Copy the minifloat step table (and the value table of the double-approximate decode behind it) into shared
+// memory (all threads; caller syncs).
 __device__ __forceinline__ const FpStep* load_fp_lut(const LaunchParams& p, uint8_t* s_lut) {
   const uint2* g = reinterpret_cast<const uint2*>(p.lut);
   uint2* s = reinterpret_cast<uint2*>(s_lut);
   for (uint32_t i = threadIdx.x; i < p.qc.lut_n; i += blockDim.x) s[i] = g[i];
+  if (p.lut_extra_bytes) {
+    const uint32_t o = p.lut_smem_bytes / 8u, n = p.lut_extra_bytes / 8u;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s[o + i] = g[o + i];
+  }
   return reinterpret_cast<const FpStep*>(s_lut);
 }
 
@@ -1392,8 +1398,11 @@ __global__ void __launch_bounds__(256) col_double_kernel(const __grid_constant__
     }
     if (live && any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
 
-    // ---- sweep 2 ----
+    // ---- sweep 2: packed quantiser -> info words -> packed group logic -> value table ----
     if (live) {
+      const uint32_t hf2 = ((uint32_t)p.qc.hi_field << 8) * 0x00010001u;                    // hi_align_exp_field, ae position
+      const uint32_t maxe2 = ((uint32_t)((1 << p.qc.exp_bits) - 1) << 8) * 0x00010001u;    // all-ones exponent
+      const uint32_t val_saddr = smem_u32(smem + 32768 + p.lut_smem_bytes);
       for (uint32_t k = (uint32_t)warp; k < g; k += 8) {
         uint4 v[4];
 #pragma unroll
@@ -1401,7 +1410,7 @@ __global__ void __launch_bounds__(256) col_double_kernel(const __grid_constant__
         uint32_t o[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint32_t gv[4];  // exact grid values of the pair, per block
+          uint32_t info[4], sg[4];
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             const uint32_t w2 = b == 0 ? (j == 0 ? v[0].x : j == 1 ? v[0].y : j == 2 ? v[0].z : v[0].w)
@@ -1409,20 +1418,26 @@ __global__ void __launch_bounds__(256) col_double_kernel(const __grid_constant__
                               : b == 2 ? (j == 0 ? v[2].x : j == 1 ? v[2].y : j == 2 ? v[2].z : v[2].w)
                                        : (j == 0 ? v[3].x : j == 1 ? v[3].y : j == 2 ? v[3].z : v[3].w);
             const T2 n = slow ? ieee_quot2<DT>(from_u32<T2>(w2), S[b][j]) : fast_quot2<DT>(from_u32<T2>(w2), S[b][j], R[b][j]);
-            gv[b] = as_u32(grid.grid_steps(n, w2));
+            info[b] = grid.steps_select(n);
+            sg[b] = grid.codec_sign(n);
           }
-          uint32_t clo[4], chi[4];
+          // group = the four blocks; low halves and high halves are two independent groups (neighbouring columns)
+          const uint32_t cnt = (info[0] & kDblOutl) + (info[1] & kDblOutl) + (info[2] & kDblOutl) + (info[3] & kDblOutl);  // k * 0x80 per half
+          const uint32_t few = __hle2_mask(from_u32<T2>(cnt), from_u32<T2>(kDblOutl));         // outlier_count <= 1      :338
+          const T2 g01 = __hmax2(from_u32<T2>(info[0] & kDblAe), from_u32<T2>(info[1] & kDblAe));  // positive patterns: float max == integer max
+          const T2 g23 = __hmax2(from_u32<T2>(info[2] & kDblAe), from_u32<T2>(info[3] & kDblAe));
+          const uint32_t gmax = as_u32(__hmax2(g01, g23));
+          uint32_t target = (gmax & ~few) | (hf2 & few);
+          const uint32_t anymax = (info[0] | info[1] | info[2] | info[3]) & kDblMaxOutl;
+          const uint32_t hm = __hne2_mask(from_u32<T2>(anymax), from_u32<T2>(0u));             // has_max_outlier          :342-343
+          target = (target & ~hm) | (maxe2 & hm);
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
-            clo[b] = fp_code_of<DT>((uint16_t)(gv[b] & 0xFFFFu), p.qc.exp_bits, p.qc.mant_bits);
-            chi[b] = fp_code_of<DT>((uint16_t)(gv[b] >> 16), p.qc.exp_bits, p.qc.mant_bits);
-          }
-          uint16_t dlo[4], dhi[4];
-          double_approx_decode4<DT>(clo, p.qc, dlo);
-          double_approx_decode4<DT>(chi, p.qc, dhi);
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const T2 dec = from_u32<T2>((uint32_t)dlo[b] | ((uint32_t)dhi[b] << 16));
+            const uint32_t idx = (info[b] & kDblCodeMask) | target | (sg[b] >> 8);             // target << 8 | sign << 7 | code
+            uint16_t lo, hi;
+            asm("ld.shared.u16 %0, [%1];" : "=h"(lo) : "r"(val_saddr + (idx & 0xFFFFu) * 2u));
+            asm("ld.shared.u16 %0, [%1];" : "=h"(hi) : "r"(val_saddr + (idx >> 16) * 2u));
+            const T2 dec = from_u32<T2>((uint32_t)lo | ((uint32_t)hi << 16));
             o[b][j] = as_u32(__hmul2(dec, from_u32<T2>(S2[b][j])));  // decoded * scales   quant_linear.py:606
           }
         }

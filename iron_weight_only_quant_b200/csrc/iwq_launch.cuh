@@ -76,7 +76,7 @@ cudaError_t launch_col_double(const LaunchParams& p, cudaStream_t st);
 template <int DT>
 cudaError_t launch_col_double(const LaunchParams& p, cudaStream_t st) {
   auto k = col_double_kernel<DT>;
-  const size_t smem = 32768 + p.lut_smem_bytes;
+  const size_t smem = 32768 + p.lut_smem_bytes + p.lut_extra_bytes;
   int grid = 0;
   cudaError_t e = persistent_grid(k, 256, smem, 0, p.total_units, &grid);
   if (e != cudaSuccess) return e;

@@ -491,7 +491,8 @@ struct FpTable {
   //     -0.0 of an underflowed quotient into +0.0: sign = (n < 0), quant_linear.py:130) and one LOP3;
   //   * the three packed constants are gathered with one PRMT each.
   static constexpr bool kFromZero = (DT == IWQ_F16);
-  IWQ_HD T2 grid_steps(T2 n2, uint32_t sign_src) const {
+  // magnitude part: the selected `below` / `above` entries of both halves, packed
+  IWQ_HD uint32_t steps_select(T2 n2) const {
     T2 a = __hmin2(__habs2(n2), fmax2);
     uint32_t d = as_u32(a);
     if (!kFromZero) {
@@ -515,7 +516,13 @@ struct FpTable {
     const uint32_t above = (e0.y & 0xFFFFu) | (e1.y << 16);
 #endif
     const uint32_t m = __hge2_mask(a, from_u32<T2>(thr));
-    const uint32_t vb = (below & ~m) | (above & m);
+    return (below & ~m) | (above & m);
+  }
+  // sign bits of the codec: (n < 0), i.e. the sign of n + (+0.0)
+  IWQ_HD uint32_t codec_sign(T2 n2) const { return as_u32(__hadd2(n2, from_u32<T2>(0u))) & 0x80008000u; }
+
+  IWQ_HD T2 grid_steps(T2 n2, uint32_t sign_src) const {
+    const uint32_t vb = steps_select(n2);
     const uint32_t ss = rne ? sign_src : as_u32(__hadd2(n2, from_u32<T2>(0u)));
     return from_u32<T2>(vb | (ss & 0x80008000u));
   }
@@ -643,49 +650,86 @@ IWQ_HD int rounding_rshift8(int val, int shift) {  // _rounding_rshift (:112-123
   return shift >= 31 ? (v < 0 ? -1 : 0) : (v >> shift);
 }
 
+// per-code part of the decode: aligned exponent (:315) and padded mantissa (:316-321)
+IWQ_HD void double_approx_fields(uint32_t code, const QuantConsts& c, int* ae, int* mp) {
+  const int E = c.exp_bits, M = c.mant_bits, tp = c.tail_pad;
+  const int ef = (int)((code >> M) & ((1u << E) - 1u)), mf = (int)(code & ((1u << M) - 1u));
+  *ae = ef == 0 ? 1 : ef;                                                                // :315
+  const int full = ((ef == 0 ? 0 : 1) << M) | mf;                                        // :316-317
+  *mp = tp >= 0 ? wrap8(full << tp) : rounding_rshift8(full, -tp);                       // :318-321
+}
+
+// value of ONE code once the group's target exponent is known (:345-362); `code` includes the sign bit
 template <int DT>
-IWQ_HD void double_approx_decode4(const uint32_t (&code)[4], const QuantConsts& c, uint16_t (&out)[4]) {
+IWQ_HD uint16_t double_approx_elem(uint32_t code, int target, const QuantConsts& c) {
   const int E = c.exp_bits, M = c.mant_bits, bias = (1 << (E - 1)) - 1, tp = c.tail_pad;
-  int ae[4], mp[4];
-  int cnt = 0, gmax = 0;
-  bool has_max = false;
-  const int max_exp = (1 << E) - 1;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int ef = (int)((code[i] >> M) & (uint32_t)max_exp), mf = (int)(code[i] & ((1u << M) - 1u));
-    ae[i] = ef == 0 ? 1 : ef;                                                            // :315
-    const int full = ((ef == 0 ? 0 : 1) << M) | mf;                                      // :316-317
-    mp[i] = tp >= 0 ? wrap8(full << tp) : rounding_rshift8(full, -tp);                   // :318-321
-    const bool outl = ae[i] < c.hi_start || ae[i] > c.hi_field;                          // :334
-    cnt += outl ? 1 : 0;
-    gmax = ae[i] > gmax ? ae[i] : gmax;
-    has_max = has_max || (ae[i] == max_exp && outl);                                     // :342
-  }
-  int target = cnt <= 1 ? c.hi_field : gmax;                                             // :338
-  if (has_max) target = max_exp;                                                         // :343
+  int ae, mp;
+  double_approx_fields(code, c, &ae, &mp);
   const int cap = tp >= 0 ? (((1 << (M + 1)) - 1) << tp) : (((1 << (M + 1)) - 1) >> (-tp));  // :351-355
   const float hi_unb = rD<DT>((float)(target - bias));                                   // (target - bias).to(dtype)
   const float p2 = rD<DT>(exp2f(hi_unb));                                                // torch.pow(2.0 (dtype), .)
   const float den = ldexpf(1.0f, M + tp);
+  const int shift = target - ae;                                                         // :345
+  int al;
+  if (shift >= 0) {
+    al = rounding_rshift8(mp, shift);                                                    // :348
+  } else {
+    const int ls = -shift;
+    al = wrap8(ls < 31 ? (mp << ls) : 0);                                                // :349 (int8 wrap)
+    al = al < cap ? al : cap;                                                            // :356
+  }
+  float v = rD<DT>(rD<DT>((float)al) / den);                                             // mant.to(dtype) / 2^(M+tail)  :358
+  v = rD<DT>(v * p2);
+  const uint32_t sign = (code >> (E + M)) & 1u;
+  uint16_t b = DType<DT>::from_f32(v);
+  if (sign) b ^= 0x8000u;                                                                // torch.where(sign == 1, -value, value)
+  if (code == 0) b = 0;                                                                  // zero_mask
+  return b;
+}
+
+// the group's target exponent from the four codes (:334-343)
+IWQ_HD int double_approx_target(const uint32_t (&code)[4], const QuantConsts& c) {
+  const int max_exp = (1 << c.exp_bits) - 1;
+  int cnt = 0, gmax = 0;
+  bool has_max = false;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int shift = target - ae[i];                                                    // :345
-    int al;
-    if (shift >= 0) {
-      al = rounding_rshift8(mp[i], shift);                                               // :348
-    } else {
-      const int ls = -shift;
-      al = wrap8(ls < 31 ? (mp[i] << ls) : 0);                                           // :349 (int8 wrap)
-      al = al < cap ? al : cap;                                                          // :356
-    }
-    float v = rD<DT>(rD<DT>((float)al) / den);                                           // mant.to(dtype) / 2^(M+tail)  :358
-    v = rD<DT>(v * p2);
-    const uint32_t sign = (code[i] >> (E + M)) & 1u;
-    uint16_t b = DType<DT>::from_f32(v);
-    if (sign) b ^= 0x8000u;                                                              // torch.where(sign == 1, -value, value)
-    if (code[i] == 0) b = 0;                                                             // zero_mask
-    out[i] = b;
+    int ae, mp;
+    double_approx_fields(code[i], c, &ae, &mp);
+    const bool outl = ae < c.hi_start || ae > c.hi_field;                                // :334
+    cnt += outl ? 1 : 0;
+    gmax = ae > gmax ? ae : gmax;
+    has_max = has_max || (ae == max_exp && outl);                                        // :342
   }
+  int target = cnt <= 1 ? c.hi_field : gmax;                                             // :338
+  if (has_max) target = max_exp;                                                         // :343
+  return target;
+}
+
+template <int DT>
+IWQ_HD void double_approx_decode4(const uint32_t (&code)[4], const QuantConsts& c, uint16_t (&out)[4]) {
+  const int target = double_approx_target(code, c);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = double_approx_elem<DT>(code[i], target, c);
+}
+
+// Device form of the same decode: everything per-code is tabulated (iwq_consts.h: build_double_tables).
+//   * the step table's `below` / `above` hold a 16-bit INFO word of the grid value instead of the value:
+//       code magnitude [0:6] | outlier [7] | aligned exponent [8:12] | outlier-at-max-exponent [13]
+//     so the packed quantiser (steps_select) yields the info of both halves of a pair in one go;
+//   * a value table val[target << 8 | sign << 7 | code magnitude] holds double_approx_elem for every
+//     (target exponent 0..31, 8-bit code): 16 KB in shared memory.
+// The group logic runs packed on the two halves (= two neighbouring columns = two independent groups): the
+// fields are positioned so that sums cannot carry between halves and compare as positive fp16 patterns.
+constexpr uint32_t kDblCodeMask = 0x007F007Fu, kDblOutl = 0x00800080u, kDblAe = 0x1F001F00u, kDblMaxOutl = 0x20002000u;
+constexpr int kDblValEntries = 32 * 256;
+
+IWQ_HD uint16_t double_approx_info(uint32_t mag_code, const QuantConsts& c) {
+  int ae, mp;
+  double_approx_fields(mag_code, c, &ae, &mp);
+  const int max_exp = (1 << c.exp_bits) - 1;
+  const bool outl = ae < c.hi_start || ae > c.hi_field;
+  return (uint16_t)((mag_code & 0x7Fu) | (outl ? 0x80u : 0u) | ((uint32_t)ae << 8) | ((outl && ae == max_exp) ? 0x2000u : 0u));
 }
 
 // minifloat code of a grid value (for optional code emission): sign | exponent field | mantissa,
