@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define IWQ_ABI_VERSION 2
+#define IWQ_ABI_VERSION 3
 
 /* storage dtype of weights, scales and zeros */
 enum { IWQ_F16 = 0, IWQ_BF16 = 1 };
@@ -78,6 +78,10 @@ typedef struct iwq_config {
   int32_t hi_align_start;     /* approx: fp{4,6,8}_hi_align_start                                       */
   int32_t hi_align_exp_field; /* approx: fp{4,6,8}_hi_align_exp_field                                   */
   int32_t tail_pad_bits;      /* approx: fp{4,6,8}_tail_pad_bits (may be negative)                      */
+  int32_t code_bits;          /* layout of iwq_matrix.codes: 0 or 8 = one byte per code; 4 = packed W4 format,
+                                 two codes per byte, element 2i in the low nibble (INT bits <= 4, minifloats
+                                 with 1 + E + M <= 4); no reference counterpart -- the reference discards its
+                                 codes (quant_linear.py:613-625, :771), this is SURVEY section 8f row 4         */
 } iwq_config_t;
 
 typedef struct iwq_matrix {
@@ -85,7 +89,8 @@ typedef struct iwq_matrix {
   void* out;      /* [rows, cols] fake-quantised output; may equal `w`                                */
   void* scales;   /* optional [G] scales in the weight dtype (G = rows*cols/group | rows | 1)         */
   void* zeros;    /* optional [G]: INT asym zero points / FP asym mid points, weight dtype            */
-  void* codes;    /* optional [rows, cols] uint8: INT code (two's complement for sym) / minifloat code*/
+  void* codes;    /* optional [rows, cols] uint8 (or [rows, cols/2] when cfg.code_bits == 4): INT code
+                     (two's complement for sym) / minifloat code; quant_dim = 0 only                 */
   int64_t rows;
   int64_t cols;
 } iwq_matrix_t;

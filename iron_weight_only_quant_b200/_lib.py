@@ -40,7 +40,7 @@ EXPORTS = (
 class Config(ctypes.Structure):
     """struct iwq_config (include/iwq_b200.h)."""
 
-    _fields_ = [(n, ctypes.c_int32) for n in ("dtype", "scheme", "bits", "exp_bits", "mant_bits", "symmetric", "group", "variant", "quant_dim", "approx", "hi_align_start", "hi_align_exp_field", "tail_pad_bits")]
+    _fields_ = [(n, ctypes.c_int32) for n in ("dtype", "scheme", "bits", "exp_bits", "mant_bits", "symmetric", "group", "variant", "quant_dim", "approx", "hi_align_start", "hi_align_exp_field", "tail_pad_bits", "code_bits")]
 
 
 class Matrix(ctypes.Structure):
@@ -94,7 +94,7 @@ def lib() -> ctypes.CDLL:
         L.iwq_selftest_division.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.iwq_fake_quant_host.restype = ctypes.c_int
         L.iwq_fake_quant_host.argtypes = [ctypes.POINTER(Config), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32)]
-        if L.iwq_abi_version() != 2:
+        if L.iwq_abi_version() != 3:
             raise RuntimeError("libiwq_b200.so ABI version mismatch")
         _lib = L
     return _lib
@@ -124,10 +124,10 @@ def dtype_code(dt: torch.dtype) -> int:
     raise TypeError(f"iron_weight_only_quant_b200 computes in fp16/bf16 storage only, got {dt} (no CPU/fp32 fallback)")
 
 
-def make_config(dtype: torch.dtype, scheme: int, group: int, *, bits: int = 0, exp_bits: int = 0, mant_bits: int = 0, symmetric: bool = False, variant: int = 0, quant_dim: int = 0, approx: int = 0, hi_align_start: int = 0, hi_align_exp_field: int = 0, tail_pad_bits: int = 0) -> Config:
+def make_config(dtype: torch.dtype, scheme: int, group: int, *, bits: int = 0, exp_bits: int = 0, mant_bits: int = 0, symmetric: bool = False, variant: int = 0, quant_dim: int = 0, approx: int = 0, hi_align_start: int = 0, hi_align_exp_field: int = 0, tail_pad_bits: int = 0, code_bits: int = 0) -> Config:
     return Config(
         dtype=dtype_code(dtype), scheme=scheme, bits=int(bits), exp_bits=int(exp_bits), mant_bits=int(mant_bits), symmetric=int(bool(symmetric)), group=int(group), variant=int(variant),
-        quant_dim=int(quant_dim), approx=int(approx), hi_align_start=int(hi_align_start), hi_align_exp_field=int(hi_align_exp_field), tail_pad_bits=int(tail_pad_bits),
+        quant_dim=int(quant_dim), approx=int(approx), hi_align_start=int(hi_align_start), hi_align_exp_field=int(hi_align_exp_field), tail_pad_bits=int(tail_pad_bits), code_bits=int(code_bits),
     )
 
 

@@ -51,6 +51,13 @@ static inline int build_quant_consts(const iwq_config_t* cfg, QuantConsts* c, in
   c->exp_bits = cfg->exp_bits;
   c->mant_bits = cfg->mant_bits;
   c->symmetric = cfg->symmetric ? 1 : 0;
+  if (cfg->code_bits != 0 && cfg->code_bits != 8 && cfg->code_bits != 4) return fail(IWQ_ERR_INVALID, "code_bits must be 0, 8 or 4");
+  c->code_nibbles = cfg->code_bits == 4 ? 1 : 0;
+  if (c->code_nibbles) {
+    const bool fits = cfg->scheme == IWQ_SCHEME_INT ? (cfg->bits >= 1 && cfg->bits <= 4)
+                    : (cfg->scheme == IWQ_SCHEME_FP_CODEC || cfg->scheme == IWQ_SCHEME_FP_RNE) ? (1 + cfg->exp_bits + cfg->mant_bits <= 4) : false;
+    if (!fits) return fail(IWQ_ERR_INVALID, "code_bits = 4 needs codes of at most 4 bits (INT bits <= 4, minifloat 1 + E + M <= 4)");
+  }
   if (cfg->scheme == IWQ_SCHEME_INT) {
     const int b = cfg->bits;
     if (b < 1 || b > 15) return fail(IWQ_ERR_INVALID, "INT bits must be in [1, 15]");

@@ -445,6 +445,7 @@ static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, Launc
     int rc = check_matrix(&ms[i]);
     if (rc) return rc;
     const int64_t rows = ms[i].rows, cols = ms[i].cols;
+    if (ms[i].codes) return fail(IWQ_ERR_UNSUPPORTED, "code emission is implemented for quant_dim = 0 only");
     int64_t g;
     if (cfg->group > 0) {
       if (rows % cfg->group != 0) return fail(IWQ_ERR_INDIVISIBLE, "rows is not divisible by the group size (quant_dim = 1)");

@@ -182,6 +182,20 @@ __device__ __forceinline__ void pack_codes(const uint32_t (&cb)[8], uint2* codes
   codes8->y = cb[4] | (cb[5] << 8) | (cb[6] << 16) | (cb[7] << 24);
 }
 
+// store the 8 codes of one 16-byte vector: 8 bytes, or 4 bytes in the packed W4 layout (low nibble = even element)
+__device__ __forceinline__ void store_codes(uint8_t* codes, uint64_t vec, const uint2& c8, bool nibbles) {
+  if (!nibbles) {
+    *reinterpret_cast<uint2*>(codes + vec * 8) = c8;
+  } else {
+    uint32_t a = c8.x & 0x0F0F0F0Fu, b = c8.y & 0x0F0F0F0Fu;
+    a = (a | (a >> 4)) & 0x00FF00FFu;
+    b = (b | (b >> 4)) & 0x00FF00FFu;
+    a = (a | (a >> 8)) & 0xFFFFu;
+    b = (b | (b >> 8)) & 0xFFFFu;
+    *reinterpret_cast<uint32_t*>(codes + vec * 4) = a | (b << 16);
+  }
+}
+
 template <int DT, int KIND>
 struct Prepared;
 
@@ -398,7 +412,7 @@ __device__ __forceinline__ void consume_tile(uint4 (&v)[kVPT], const TileCtx& t,
     const uint4 o = prep.template apply<SYM>(v[it], p.qc, tbl, want_codes, &codes8);
     if (idx < t.n_vec) {
       stg128(t.dst + (size_t)idx * 16, o);
-      if (want_codes) *reinterpret_cast<uint2*>(t.codes + (t.vec0 + idx) * 8) = codes8;
+      if (want_codes) store_codes(t.codes, t.vec0 + idx, codes8, p.qc.code_nibbles != 0);
       any_bad |= prep.bad;
       // segment parameters: one lane per segment; per-tensor (GIVEN) has a single segment per matrix
       const bool owner = GIVEN ? (t.vec0 + idx == 0) : ((lane & (lps - 1)) == 0 && (it & (vpl - 1)) == 0);
@@ -541,7 +555,7 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
     uint2 codes8;
     const uint4 o = prep.template apply<SYM>(v[k], p.qc, s_tbl, want_codes, &codes8);
     sts128(lbase + j * 16, o);
-    if (want_codes && lane_vec + j < t.n_vec) *reinterpret_cast<uint2*>(t.codes + (t.vec0 + lane_vec + j) * 8) = codes8;
+    if (want_codes && lane_vec + j < t.n_vec) store_codes(t.codes, t.vec0 + lane_vec + j, codes8, p.qc.code_nibbles != 0);
   }
   if (FAST || lane_vec < t.n_vec) {
     const bool owner = GIVEN ? (t.vec0 + lane_vec == 0) : ((lane & (lps - 1)) == 0);
@@ -711,7 +725,7 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
         t.dst = jb.dst + r * jb.row_bytes;
         t.scales = jb.scales;
         t.zeros = jb.zeros;
-        t.codes = jb.codes ? jb.codes + r * (jb.row_bytes >> 1) : nullptr;
+        t.codes = jb.codes ? jb.codes + ((r * (jb.row_bytes >> 1)) >> (p.qc.code_nibbles ? 1 : 0)) : nullptr;
         t.row = r;
         t.n_vec = jb.row_bytes >> 4;
         t.pad = 0;
@@ -753,7 +767,7 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
         uint2 codes8;
         const uint4 o = prep.template apply<SYM>(lds128(sdata + (size_t)i * 16), p.qc, s_tbl, want_codes, &codes8);
         stg128(t.dst + (size_t)i * 16, o);
-        if (want_codes) *reinterpret_cast<uint2*>(t.codes + (size_t)i * 8) = codes8;
+        if (want_codes) store_codes(t.codes, i, codes8, p.qc.code_nibbles != 0);
       }
       if (tid == 0) {
         if (t.scales) reinterpret_cast<uint16_t*>(t.scales)[t.row] = DType<DT>::from_f32(prep.scale);

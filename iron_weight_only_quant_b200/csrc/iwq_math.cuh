@@ -245,6 +245,7 @@ struct QuantConsts {
   int32_t bfp_target;      // BFP: mantissa bits kept incl. the leading one = min(w_bit-1, 11)   quant_linear.py:673
   int32_t bfp_sd;          // BFP: 11 - bfp_target (rounding right shift)                          quant_linear.py:674
   int32_t bfp_round_mant;  // BFP on bf16 with more than 8 mantissa bits: `mant_rounded.to(bf16)` rounds (:707)
+  int32_t code_nibbles;    // 1: emitted codes are packed two per byte (iwq_config.code_bits == 4)
   uint16_t lut_lo_bits;    // D bits of 2^(emin-M-1): everything at or below it quantises to 0 (exact tie -> even)
   uint16_t lut_shift;      // log2 of the interval width W = 2^(mantissa_bits(D) - M - 1) bit patterns (half a grid step)
   uint32_t lut_n;          // number of FpStep intervals covering bit patterns lut_lo_bits .. fmax_bits

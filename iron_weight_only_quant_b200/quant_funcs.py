@@ -79,3 +79,33 @@ def quantize_activation_per_tensor_absmax(t, n_bits=8):
     t = t.view(-1, t_shape[-1])
     t = pseudo_quantize_tensor(t, n_bits=n_bits, zero_point=True, q_group_size=-1, per_tensor=True, inplace=False)
     return t.reshape(t_shape)
+
+
+@torch.no_grad()
+def quantize_to_packed_w4(tensor, n_bits=4, zero_point=True, q_group_size=128):
+    """NOT in the reference (which computes its codes only to throw them away: quant_funcs.py:44-46,
+    quant_linear.py:613-625) -- SURVEY section 8f row 4: the same fused pass that fake-quantises also emits the
+    integer codes in a packed W4 layout, two per byte with element 2i in the low nibble (two's complement nibbles
+    for the symmetric form), plus the scales and zero points `pseudo_quantize_tensor` drops.
+
+    Returns {"codes": uint8 [rows, cols/2], "scales": [G, 1], "zeros": [G, 1] or None, "dequantized": tensor},
+    G = rows*cols/q_group_size (q_group_size > 0) or rows (q_group_size = -2).  The codes are the reference's
+    `clamp(round(w / s) + z)` values bit for bit (checked in tests/test_gpu_parity.py).
+    """
+    if not tensor.is_cuda:
+        raise RuntimeError("quantize_to_packed_w4: tensor must be on a CUDA device (no CPU fallback in iron_weight_only_quant_b200)")
+    assert tensor.dim() == 2 and n_bits <= 4
+    rows, cols = (int(x) for x in tensor.shape)
+    assert cols % 2 == 0
+    group = int(q_group_size) if q_group_size > 0 else _lib.GROUP_PER_CHANNEL
+    if q_group_size > 0:
+        assert cols % q_group_size == 0
+    src = tensor if tensor.is_contiguous() else tensor.contiguous()
+    G = _lib.num_segments(rows, cols, group)
+    out = torch.empty_like(src)
+    codes = torch.empty(rows, cols // 2, dtype=torch.uint8, device=src.device)
+    scales = torch.empty(G, 1, dtype=src.dtype, device=src.device)
+    zeros = torch.empty(G, 1, dtype=src.dtype, device=src.device) if zero_point else None
+    cfg = _lib.make_config(src.dtype, _lib.SCHEME_INT, group, bits=n_bits, symmetric=not zero_point, code_bits=4)
+    _lib.fake_quant_(src, out, cfg, rows, cols, scales=scales, zeros=zeros, codes=codes, track_status=False)
+    return {"codes": codes, "scales": scales, "zeros": zeros, "dequantized": out}

@@ -224,6 +224,45 @@ def test_int_vs_oracle_all_outputs(dt, variant):
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_packed_w4_codes_vs_oracle(dt):
+    """code_bits = 4: two codes per byte, element 2i in the low nibble; same codes as the
+    unpacked emission / the oracle, for INT (asym, sym two's complement) and FP4, all kernels that emit codes."""
+    def pack(c):
+        c = (c.astype(np.int64) & 0xF).astype(np.uint8).reshape(c.shape[0], -1, 2)
+        return c[:, :, 0] | (c[:, :, 1] << 4)
+
+    for rows, cols, grp, variant in [(256, 2048, 128, 0), (64, 1024, 32, 0), (48, 768, -2, 0), (30, 11008, -2, 0), (16, 512, 16, 2), (128, 1024, 128, 1), (8, 4096, -1, 0), (3, 200, 8, 0)]:
+        w = seeded(rows, cols, dt, rows * 7 + cols)
+        wd = w.to(DEV)
+        for nb, sym in [(4, False), (4, True), (3, False), (2, True)]:
+            ref = O.int_fake_quant(bits(w), dt, nb, not sym, grp)
+            codes = torch.zeros(rows, cols // 2, dtype=torch.uint8, device=DEV)
+            cfg = _lib.make_config(TDT[dt], _lib.SCHEME_INT, grp, bits=nb, symmetric=sym, variant=variant, code_bits=4)
+            out = torch.empty_like(wd)
+            _lib.fake_quant_(wd, out, cfg, rows, cols, codes=codes)
+            tag = f"{dt} [{rows},{cols}] g{grp} b{nb} sym={sym} v{variant}"
+            assert_bits(bits(out), ref["out"], dt, tag)
+            assert np.array_equal(codes.cpu().numpy(), pack(ref["codes"])), tag + " packed codes"
+    # FP4 E2M1 / E1M2: packed minifloat codes == the unpacked emission
+    w = seeded(64, 1024, dt, 5).to(DEV)
+    for E, M in [(2, 1), (1, 2)]:
+        c8 = torch.zeros(64, 1024, dtype=torch.uint8, device=DEV)
+        c4 = torch.zeros(64, 512, dtype=torch.uint8, device=DEV)
+        for cb, buf in [(8, c8), (4, c4)]:
+            cfg = _lib.make_config(TDT[dt], _lib.SCHEME_FP_CODEC, 128, exp_bits=E, mant_bits=M, symmetric=True, code_bits=cb)
+            _lib.fake_quant_(w, torch.empty_like(w), cfg, 64, 1024, codes=buf)
+        assert np.array_equal(c4.cpu().numpy(), pack(c8.cpu().numpy())), f"{dt} fp4 e{E}m{M} packed codes"
+    with pytest.raises(ValueError):  # 8-bit codes do not fit a nibble
+        _lib.fake_quant_(w, torch.empty_like(w), _lib.make_config(TDT[dt], _lib.SCHEME_INT, 128, bits=8, code_bits=4), 64, 1024, codes=c4)
+    # the Python-level export: packed codes + scales + zero points reproduce the fake-quant weight exactly
+    pk = quant_funcs.quantize_to_packed_w4(w, n_bits=4, zero_point=True, q_group_size=128)
+    fq = quant_funcs.pseudo_quantize_tensor(w, n_bits=4, zero_point=True, q_group_size=128)
+    q = torch.stack([pk["codes"] & 0xF, pk["codes"] >> 4], dim=-1).reshape(64, 1024).to(torch.float32)
+    deq = ((q.reshape(-1, 128) - pk["zeros"].float()) * pk["scales"].float()).reshape(64, 1024)
+    assert torch.equal(deq.to(TDT[dt]), fq)
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
 def test_per_channel_row_kernel_vs_oracle(dt):
     """per-channel goes through row_tma_kernel for every row length that is not a power of two <= 1024."""
     for rows, cols in [(64, 768), (96, 3072), (40, 4096), (33, 11008), (7, 28672), (130, 1024), (50, 1032)]:

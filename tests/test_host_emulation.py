@@ -23,7 +23,7 @@ FORMATS = {"e2m1": (2, 1), "e1m2": (1, 2), "e3m2": (3, 2), "e2m3": (2, 3), "e4m3
 
 
 class Cfg(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int32) for n in ("dtype", "scheme", "bits", "exp_bits", "mant_bits", "symmetric", "group", "variant", "quant_dim", "approx", "hi_align_start", "hi_align_exp_field", "tail_pad_bits")]
+    _fields_ = [(n, ctypes.c_int32) for n in ("dtype", "scheme", "bits", "exp_bits", "mant_bits", "symmetric", "group", "variant", "quant_dim", "approx", "hi_align_start", "hi_align_exp_field", "tail_pad_bits", "code_bits")]
 
 
 @pytest.fixture(scope="module")
