@@ -213,14 +213,15 @@ struct PreparedInt {  // KIND_INT_FAST / KIND_INT_WIDE
     zero = q.z;
     bad = q.bad;
   }
-  template <bool SYM>
+  __device__ __forceinline__ bool slow() const { return f.slow_div; }
+  template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts&, const FpStep*, bool want_codes, uint2* codes8) const {
     T2 d[4];
     uint4 o;
-    o.x = f.apply(v.x, &d[0]);
-    o.y = f.apply(v.y, &d[1]);
-    o.z = f.apply(v.z, &d[2]);
-    o.w = f.apply(v.w, &d[3]);
+    o.x = f.template apply<SLOW>(v.x, &d[0]);
+    o.y = f.template apply<SLOW>(v.y, &d[1]);
+    o.z = f.template apply<SLOW>(v.z, &d[2]);
+    o.w = f.template apply<SLOW>(v.w, &d[3]);
     if (want_codes) {
       uint32_t cb[8];
 #pragma unroll
@@ -250,7 +251,8 @@ struct Prepared<DT, KIND_INT_GENERIC> {
     zero = q.z;
     bad = q.bad;
   }
-  template <bool SYM>
+  __device__ __forceinline__ bool slow() const { return false; }
+  template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts& c, const FpStep*, bool want_codes, uint2* codes8) const {
     const uint32_t in[4] = {v.x, v.y, v.z, v.w};
     uint32_t out[4], cb[8];
@@ -290,11 +292,12 @@ struct Prepared<DT, KIND_FP> {
     o.w = f.template apply<SLOW, SYM ? 0 : 1>(v.w, &g[3]);
     return o;
   }
-  template <bool SYM>
+  __device__ __forceinline__ bool slow() const { return f.slow_div; }
+  template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts& c, const FpStep*, bool want_codes, uint2* codes8) const {
     T2 g[4];
-    // one (segment-uniform) branch per vector: IEEE division only for degenerate scales
-    const uint4 o = f.slow_div ? apply_t<true, SYM>(v, g) : apply_t<false, SYM>(v, g);
+    // IEEE division only for degenerate scales: a segment-uniform branch, per vector (SLOW < 0) or hoisted by the caller
+    const uint4 o = SLOW < 0 ? (f.slow_div ? apply_t<true, SYM>(v, g) : apply_t<false, SYM>(v, g)) : (SLOW ? apply_t<true, SYM>(v, g) : apply_t<false, SYM>(v, g));
     if (want_codes) {
       uint32_t cb[8];
 #pragma unroll
@@ -320,7 +323,8 @@ struct Prepared<DT, KIND_BFP> {
     zero = 0.f;
     bad = false;
   }
-  template <bool SYM>
+  __device__ __forceinline__ bool slow() const { return false; }
+  template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint4 apply(const uint4& v, const QuantConsts&, const FpStep*, bool want_codes, uint2* codes8) const {
     if (want_codes) *codes8 = make_uint2(0u, 0u);  // the reference keeps no BFP codes (quant_linear.py:712-715)
     return make_uint4(f.apply(v.x), f.apply(v.y), f.apply(v.z), f.apply(v.w));
@@ -549,13 +553,27 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
     prep.setup(mx, mn, p.qc, SYM, s_tbl);
   }
   const bool want_codes = !FAST && t.codes != nullptr;
+  if (FAST && !prep.slow()) {
+    // the hot path: no code emission, reciprocal+FMA quotient; one segment-uniform branch per lane-tile keeps the
+    // IEEE-division variant (degenerate scales only) out of the instruction stream
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint32_t j = (k + rot) & 3u;
-    uint2 codes8;
-    const uint4 o = prep.template apply<SYM>(v[k], p.qc, s_tbl, want_codes, &codes8);
-    sts128(lbase + j * 16, o);
-    if (want_codes && lane_vec + j < t.n_vec) store_codes(t.codes, t.vec0 + lane_vec + j, codes8, p.qc.code_nibbles != 0);
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t j = (k + rot) & 3u;
+      uint2 codes8;
+      sts128(lbase + j * 16, prep.template apply<SYM, 0>(v[k], p.qc, s_tbl, false, &codes8));
+    }
+  } else {
+    // rolled loop (code size): the inputs are re-read from the stage, which still holds them (each pass overwrites
+    // only its own slot), so v[] is never indexed dynamically and stays in registers on the hot path
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t j = (k + rot) & 3u;
+      uint2 codes8;
+      const uint4 vv = (FAST || lane_vec + j < t.n_vec) ? lds128(lbase + j * 16) : make_uint4(0u, 0u, 0u, 0u);
+      const uint4 o = prep.template apply<SYM>(vv, p.qc, s_tbl, want_codes, &codes8);
+      sts128(lbase + j * 16, o);
+      if (want_codes && lane_vec + j < t.n_vec) store_codes(t.codes, t.vec0 + lane_vec + j, codes8, p.qc.code_nibbles != 0);
+    }
   }
   if (FAST || lane_vec < t.n_vec) {
     const bool owner = GIVEN ? (t.vec0 + lane_vec == 0) : ((lane & (lps - 1)) == 0);

@@ -349,10 +349,13 @@ struct IntFast {
     }
   }
 
-  // returns the dequantised pair; *d2 receives clamp(rint(x), lo, hi) (for code emission)
+  // returns the dequantised pair; *d2 receives clamp(rint(x), lo, hi) (for code emission).
+  // SLOW: 1 / 0 fixes the division form at compile time (callers that hoisted the segment-uniform branch), -1 decides here
+  template <int SLOW = -1>
   IWQ_HD uint32_t apply(uint32_t w2, T2* d2) const {
     T2 w = from_u32<T2>(w2);
-    T2 x = slow_div ? ieee_quot2<DT>(w, s) : fast_quot2<DT>(w, s, r);
+    const bool sl = SLOW < 0 ? slow_div : (SLOW != 0);
+    T2 x = sl ? ieee_quot2<DT>(w, s) : fast_quot2<DT>(w, s, r);
     T2 q = rint2(x);
     q = __hmin2_nan(__hmax2_nan(q, lo2), hi2);
     *d2 = q;
