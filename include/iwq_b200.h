@@ -139,6 +139,19 @@ int iwq_selftest_division(int dtype, unsigned long long* mismatches, void* strea
 int iwq_fake_quant_host(const iwq_config_t* cfg, const void* host_w, void* host_out, int64_t rows, int64_t cols, int device,
                         size_t chunk_bytes, int32_t* host_status);
 
+/* The same for `n` host matrices in ONE pipeline: chunks of consecutive matrices follow each other through the
+ * staging ring, which is drained once at the end instead of once per matrix (a [1024, 8192] matrix alone is a
+ * single chunk, i.e. no H2D/D2H overlap at all).  This is what a caller holding a whole state dict in pinned
+ * memory uses; replaces the per-module loop of quantize_model (quant_wrapper.py:52-82) for host-resident weights. */
+typedef struct iwq_host_matrix {
+  const void* host_w; /* [rows, cols] 16-bit weights in host memory (pinned for full speed) */
+  void* host_out;     /* may equal host_w                                                    */
+  int64_t rows;
+  int64_t cols;
+} iwq_host_matrix_t;
+int iwq_fake_quant_host_batched(const iwq_config_t* cfg, const iwq_host_matrix_t* ms, int n, int device, size_t chunk_bytes,
+                                int32_t* host_status);
+
 #ifdef __cplusplus
 }
 #endif

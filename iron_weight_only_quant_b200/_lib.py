@@ -34,6 +34,7 @@ EXPORTS = (
     "iwq_fp_roundtrip",
     "iwq_selftest_division",
     "iwq_fake_quant_host",
+    "iwq_fake_quant_host_batched",
 )
 
 
@@ -55,6 +56,12 @@ class Matrix(ctypes.Structure):
         ("rows", ctypes.c_int64),
         ("cols", ctypes.c_int64),
     ]
+
+
+class HostMatrix(ctypes.Structure):
+    """struct iwq_host_matrix (include/iwq_b200.h)."""
+
+    _fields_ = [("host_w", ctypes.c_void_p), ("host_out", ctypes.c_void_p), ("rows", ctypes.c_int64), ("cols", ctypes.c_int64)]
 
 
 _lib = None
@@ -94,6 +101,8 @@ def lib() -> ctypes.CDLL:
         L.iwq_selftest_division.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.iwq_fake_quant_host.restype = ctypes.c_int
         L.iwq_fake_quant_host.argtypes = [ctypes.POINTER(Config), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32)]
+        L.iwq_fake_quant_host_batched.restype = ctypes.c_int
+        L.iwq_fake_quant_host_batched.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(HostMatrix), ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32)]
         if L.iwq_abi_version() != 3:
             raise RuntimeError("libiwq_b200.so ABI version mismatch")
         _lib = L
@@ -225,3 +234,18 @@ def read_and_clear_status(device: torch.device) -> int:
     if v:
         status.zero_()
     return v
+
+
+def fake_quant_host_(tensors: Sequence[torch.Tensor], cfg: Config, device: int = 0, chunk_bytes: int = 32 << 20) -> int:
+    """Fake-quantise 2-D HOST tensors (pinned for full speed) in place through one H2D -> kernel -> D2H chunk
+    pipeline on `device` (iwq_fake_quant_host_batched); synchronises; returns the status word (STATUS_NAN ...)."""
+    ms = []
+    for t in tensors:
+        if t.is_cuda or t.dim() != 2 or not t.is_contiguous():
+            raise ValueError("fake_quant_host_: expected contiguous 2-D host tensors")
+        dtype_code(t.dtype)
+        ms.append(HostMatrix(t.data_ptr(), t.data_ptr(), t.shape[0], t.shape[1]))
+    arr = (HostMatrix * len(ms))(*ms)
+    st = ctypes.c_int32(0)
+    check(lib().iwq_fake_quant_host_batched(ctypes.byref(cfg), arr, len(ms), int(device), int(chunk_bytes), ctypes.byref(st)))
+    return int(st.value)

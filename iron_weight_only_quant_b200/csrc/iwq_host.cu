@@ -502,10 +502,10 @@ static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, Launc
 // ------------------------------------------------------------------------------------------------
 struct HostPipe {
   int device = -1;
-  static constexpr int kBuf = 3;
-  void* buf[kBuf] = {nullptr, nullptr, nullptr};
+  static constexpr int kBuf = 4;
+  void* buf[kBuf] = {nullptr, nullptr, nullptr, nullptr};
   size_t cap = 0;
-  cudaStream_t stream[kBuf] = {nullptr, nullptr, nullptr};
+  cudaStream_t stream[kBuf] = {nullptr, nullptr, nullptr, nullptr};
   int32_t* status = nullptr;
   int32_t* status_host = nullptr;
 };
@@ -617,48 +617,63 @@ int iwq_selftest_division(int dtype, unsigned long long* mismatches, void* strea
   return IWQ_OK;
 }
 
-int iwq_fake_quant_host(const iwq_config_t* cfg, const void* host_w, void* host_out, int64_t rows, int64_t cols, int device,
-                        size_t chunk_bytes, int32_t* host_status) {
-  if (!cfg || !host_w || !host_out) return fail(IWQ_ERR_INVALID, "null argument");
+// One chunk pipeline over ALL matrices of the call: chunk i goes through staging buffer / stream i % kBuf
+// (H2D -> kernel -> D2H in stream order), so the H2D of later chunks overlaps the D2H of earlier ones on the two
+// copy engines and the ring is drained only once, at the end of the call -- not once per matrix.
+static int host_pipeline(const iwq_config_t* cfg, const iwq_host_matrix_t* ms, int n, int device, size_t chunk_bytes, int32_t* host_status) {
+  if (!cfg || !ms || n < 1) return fail(IWQ_ERR_INVALID, "null argument");
   if (cfg->group == IWQ_GROUP_PER_TENSOR) return fail(IWQ_ERR_UNSUPPORTED, "host pipeline: per-tensor granularity needs the whole matrix on the device");
-  if (rows <= 0 || cols <= 0) return fail(IWQ_ERR_INVALID, "rows and cols must be positive");
+  if (cfg->quant_dim != 0) return fail(IWQ_ERR_UNSUPPORTED, "host pipeline: quant_dim = 1 needs whole columns on the device");
   if (device < 0 || device >= 16) return fail(IWQ_ERR_INVALID, "device ordinal out of range");
-  if (cfg->group > 0 && cols % cfg->group != 0) return fail(IWQ_ERR_INDIVISIBLE, "cols is not divisible by the group size");
-  const size_t row_bytes = (size_t)cols * 2;
-  if (chunk_bytes == 0) chunk_bytes = 64ull << 20;
-  int64_t chunk_rows = (int64_t)(chunk_bytes / row_bytes);
-  if (chunk_rows < 1) chunk_rows = 1;
-  // keep chunk starts 16-byte aligned: rows are, as soon as cols % 8 == 0; otherwise align to 8 rows
-  if (row_bytes % 16 != 0) chunk_rows = (chunk_rows + 7) / 8 * 8;
-  if (chunk_rows > rows) chunk_rows = rows;
+  if (chunk_bytes == 0) chunk_bytes = 32ull << 20;
+  size_t max_chunk = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!ms[i].host_w || !ms[i].host_out) return fail(IWQ_ERR_INVALID, "null host pointer");
+    if (ms[i].rows <= 0 || ms[i].cols <= 0) return fail(IWQ_ERR_INVALID, "rows and cols must be positive");
+    if (cfg->group > 0 && ms[i].cols % cfg->group != 0) return fail(IWQ_ERR_INDIVISIBLE, "cols is not divisible by the group size");
+    const size_t row_bytes = (size_t)ms[i].cols * 2;
+    int64_t chunk_rows = (int64_t)(chunk_bytes / row_bytes);
+    if (chunk_rows < 1) chunk_rows = 1;
+    if (row_bytes % 16 != 0) chunk_rows = (chunk_rows + 7) / 8 * 8;  // keep chunk starts 16-byte aligned
+    if (chunk_rows > ms[i].rows) chunk_rows = ms[i].rows;
+    if ((size_t)chunk_rows * row_bytes > max_chunk) max_chunk = (size_t)chunk_rows * row_bytes;
+  }
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
   std::lock_guard<std::mutex> lk(g_pipe_mu);
   HostPipe* hp = &g_pipes[device];
-  int rc = pipe_prepare(hp, device, (size_t)chunk_rows * row_bytes);
+  int rc = pipe_prepare(hp, device, max_chunk);
   if (rc) return rc;
   e = cudaMemsetAsync(hp->status, 0, sizeof(int32_t), hp->stream[0]);
   if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
   e = cudaStreamSynchronize(hp->stream[0]);
   if (e != cudaSuccess) return fail_cuda(e, "cudaStreamSynchronize");
-  int i = 0;
-  for (int64_t r0 = 0; r0 < rows; r0 += chunk_rows, ++i) {
-    const int64_t nr = rows - r0 < chunk_rows ? rows - r0 : chunk_rows;
-    const size_t bytes = (size_t)nr * row_bytes;
-    const int b = i % HostPipe::kBuf;
-    cudaStream_t st = hp->stream[b];
-    e = cudaMemcpyAsync(hp->buf[b], (const uint8_t*)host_w + (size_t)r0 * row_bytes, bytes, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(H2D)");
-    iwq_matrix_t m;
-    memset(&m, 0, sizeof(m));
-    m.w = hp->buf[b];
-    m.out = hp->buf[b];
-    m.rows = nr;
-    m.cols = cols;
-    rc = run_batched(cfg, &m, 1, nullptr, 0, nullptr, nullptr, hp->status, st, false);
-    if (rc) return rc;
-    e = cudaMemcpyAsync((uint8_t*)host_out + (size_t)r0 * row_bytes, hp->buf[b], bytes, cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(D2H)");
+  int ci = 0;
+  for (int i = 0; i < n; ++i) {
+    const int64_t rows = ms[i].rows, cols = ms[i].cols;
+    const size_t row_bytes = (size_t)cols * 2;
+    int64_t chunk_rows = (int64_t)(chunk_bytes / row_bytes);
+    if (chunk_rows < 1) chunk_rows = 1;
+    if (row_bytes % 16 != 0) chunk_rows = (chunk_rows + 7) / 8 * 8;
+    if (chunk_rows > rows) chunk_rows = rows;
+    for (int64_t r0 = 0; r0 < rows; r0 += chunk_rows, ++ci) {
+      const int64_t nr = rows - r0 < chunk_rows ? rows - r0 : chunk_rows;
+      const size_t bytes = (size_t)nr * row_bytes;
+      const int b = ci % HostPipe::kBuf;
+      cudaStream_t st = hp->stream[b];
+      e = cudaMemcpyAsync(hp->buf[b], (const uint8_t*)ms[i].host_w + (size_t)r0 * row_bytes, bytes, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(H2D)");
+      iwq_matrix_t m;
+      memset(&m, 0, sizeof(m));
+      m.w = hp->buf[b];
+      m.out = hp->buf[b];
+      m.rows = nr;
+      m.cols = cols;
+      rc = run_batched(cfg, &m, 1, nullptr, 0, nullptr, nullptr, hp->status, st, false);
+      if (rc) return rc;
+      e = cudaMemcpyAsync((uint8_t*)ms[i].host_out + (size_t)r0 * row_bytes, hp->buf[b], bytes, cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(D2H)");
+    }
   }
   for (int b = 0; b < HostPipe::kBuf; ++b) {
     e = cudaStreamSynchronize(hp->stream[b]);
@@ -668,6 +683,21 @@ int iwq_fake_quant_host(const iwq_config_t* cfg, const void* host_w, void* host_
   if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpy(status)");
   if (host_status) *host_status = *hp->status_host;
   return IWQ_OK;
+}
+
+int iwq_fake_quant_host(const iwq_config_t* cfg, const void* host_w, void* host_out, int64_t rows, int64_t cols, int device,
+                        size_t chunk_bytes, int32_t* host_status) {
+  iwq_host_matrix_t m;
+  m.host_w = host_w;
+  m.host_out = host_out;
+  m.rows = rows;
+  m.cols = cols;
+  return host_pipeline(cfg, &m, 1, device, chunk_bytes, host_status);
+}
+
+int iwq_fake_quant_host_batched(const iwq_config_t* cfg, const iwq_host_matrix_t* ms, int n, int device, size_t chunk_bytes,
+                                int32_t* host_status) {
+  return host_pipeline(cfg, ms, n, device, chunk_bytes, host_status);
 }
 
 }  // extern "C"

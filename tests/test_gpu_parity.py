@@ -460,6 +460,17 @@ def test_host_buffer_pipeline():
     rc = _lib.lib().iwq_fake_quant_host(ctypes.byref(cfg), buf.data_ptr(), buf.data_ptr(), 300, 3072, 0, 1 << 20, ctypes.byref(st))
     _lib.check(rc)
     assert np.array_equal(bits(buf), O.int_fake_quant(bits(w2), "f16", 8, False, -2)["out"])
+    # several host matrices through ONE pipeline (iwq_fake_quant_host_batched): ragged chunking, shapes mixed
+    cfg = _lib.make_config(torch.float16, _lib.SCHEME_INT, 128, bits=4, symmetric=False)
+    shapes_ = [(700, 1024), (3, 256), (129, 2048), (64, 128), (1000, 512)]
+    ws = [seeded(r, c, "f16", 100 + i) for i, (r, c) in enumerate(shapes_)]
+    hs = [x.clone().pin_memory() for x in ws]
+    assert _lib.fake_quant_host_(hs, cfg, device=0, chunk_bytes=192 * 1024) == 0
+    for x, h in zip(ws, hs):
+        assert np.array_equal(bits(h), O.int_fake_quant(bits(x), "f16", 4, True, 128)["out"])
+    nan = hs[2].clone().pin_memory()
+    nan[5, 7] = float("nan")
+    assert _lib.fake_quant_host_([hs[0], nan], cfg) & _lib.STATUS_NAN
 
 
 # ------------------------------------------------------------------------------------------------
