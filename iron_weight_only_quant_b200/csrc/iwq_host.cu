@@ -45,6 +45,7 @@ struct Knobs {
   int row_warps = env_int("IWQ_ROW_WARPS", 0);       // consumer warps of the row kernels; 0 = automatic
   int col_tile = env_int("IWQ_COL_TILE", 0);         // quant_dim = 1: columns per tile (64/128/256), -1 = two-sweep kernel
   int col_ctas = env_int("IWQ_COL_CTAS", 0);
+  int wide_seg4 = env_int("IWQ_WIDE_SEG4", 1);       // 1: segments of 2048/4096/8192 elements go through seg4_tma_kernel
   int col_mode = env_int("IWQ_COL_MODE", 0);         // 0: warp-private cp.async ring (col_async_kernel), 1: register-resident
   int col_stages = env_int("IWQ_COL_STAGES", 0);     // ring depth of col_async_kernel (1..4); 0 = automatic
 };
@@ -52,6 +53,8 @@ static const Knobs& knobs() {
   static Knobs k;
   return k;
 }
+
+static int effective_variant(const iwq_config_t* cfg) { return knobs().variant >= 0 ? knobs().variant : cfg->variant; }
 
 static int build_consts(const iwq_config_t* cfg, QuantConsts* c, int* kind) {
   std::string msg;
@@ -175,7 +178,14 @@ struct Plan {
   int stages, consumers;   // row path
 };
 
-static bool seg_shape(uint64_t seg_elems, int* lps, int* vpl) {
+static bool seg_shape(uint64_t seg_elems, int* lps, int* vpl, bool seg4_ok) {
+  // seg4 kernel only: segments of 2048 / 4096 elements span 2 / 4 warps of a 16 KB tile (8192 works too, but the
+  // row kernel is faster there: 6073 vs 5924 GB/s on the 70B shapes; IWQ_WIDE_SEG4=2 enables it)
+  if (seg4_ok && (seg_elems == 2048 || seg_elems == 4096 || (seg_elems == 8192 && knobs().wide_seg4 >= 2))) {
+    *lps = (int)(seg_elems / 32);
+    *vpl = 1;
+    return true;
+  }
   // group = 8 * lps * vpl with lps in {1,2,4,8,16,32}; vpl in {1,2,4} only once lps == 32
   if (seg_elems < 8 || seg_elems > 1024 || (seg_elems & (seg_elems - 1))) return false;
   uint64_t vecs = seg_elems / 8;
@@ -219,7 +229,8 @@ static int make_plan(const iwq_config_t* cfg, int64_t cols, uint32_t lut_bytes, 
     pl->vpl = 1;
     return IWQ_OK;
   }
-  if (seg_shape(seg, &pl->lps, &pl->vpl)) {
+  const int v = effective_variant(cfg);
+  if (seg_shape(seg, &pl->lps, &pl->vpl, (v < 1 || v > 2) && knobs().wide_seg4 != 0)) {
     pl->path = PATH_SEG;
     return IWQ_OK;
   }
@@ -263,7 +274,6 @@ static Job make_job(const iwq_matrix_t* m, uint32_t first_unit) {
   return j;
 }
 
-static int effective_variant(const iwq_config_t* cfg) { return knobs().variant >= 0 ? knobs().variant : cfg->variant; }
 
 // Fill LaunchParams for `n` matrices; `jobs_host` receives the table (uploaded by the caller when n > 1).
 static int fill_params(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, const Plan& pl, LaunchParams* p, std::vector<Job>* jobs_host) {

@@ -445,7 +445,7 @@ __device__ __forceinline__ const FpStep* load_fp_lut(const LaunchParams& p, uint
 
 // ------------------------------------------------------------------------------------------------
 // seg_tma_kernel: TMA bulk-copy ring -> consumer warps
-// shared memory: [0,64) full barriers | [64,128) empty barriers | [128,640) TileCtx[8] | [640,960) FP table | [1024,...) stages
+// shared memory: [0,64) full barriers | [64,128) empty barriers | [128,640) TileCtx[8] | [640,896) seg4 range slots [stage][warp] | [1024,...) LUT, stages
 // ------------------------------------------------------------------------------------------------
 template <int DT, int KIND, bool SYM, bool GIVEN>
 __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_constant__ LaunchParams p) {
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_c
 // FAST = full 16 KB tile and no code emission: no per-vector predicates at all.
 template <int DT, int KIND, bool SYM, bool GIVEN, bool FAST>
 __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParams& p, const FpStep* s_tbl, uint8_t* lbase, uint32_t lane_vec,
-                                             uint32_t rot, int lane, int lps) {
+                                             uint32_t rot, int lane, int lps, int warp, uint32_t* xchg) {
   uint4 v[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -547,7 +547,17 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
                                 range_max<DT>(vec_range<DT, SYM>(v[2]), vec_range<DT, SYM>(v[3])));
     // log2(lps) butterfly rounds; lps is launch-uniform, so this is a short uniform loop (no divergence handling)
 #pragma unroll 1
-    for (int o = lps >> 1; o > 0; o >>= 1) pk = range_max<DT>(pk, __shfl_xor_sync(0xFFFFFFFFu, pk, o));
+    for (int o = (lps > 32 ? 32 : lps) >> 1; o > 0; o >>= 1) pk = range_max<DT>(pk, __shfl_xor_sync(0xFFFFFFFFu, pk, o));
+    if (lps > 32) {
+      // segment = wps consecutive warps (per-channel rows / groups of 2048, 4096 or 8192 elements): exchange the warp
+      // ranges through this stage's slots; a named barrier couples just the warps of the segment
+      const int wps = lps >> 5, w0 = warp & ~(wps - 1);
+      if (lane == 0) xchg[warp] = pk;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + w0 / wps), "r"(wps * 32) : "memory");
+      pk = xchg[w0];
+#pragma unroll 1
+      for (int w = 1; w < wps; ++w) pk = range_max<DT>(pk, xchg[w0 + w]);
+    }
     float mx, mn;
     range_unpack<DT>(pk, &mx, &mn);
     prep.setup(mx, mn, p.qc, SYM, s_tbl);
@@ -576,7 +586,7 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
     }
   }
   if (FAST || lane_vec < t.n_vec) {
-    const bool owner = GIVEN ? (t.vec0 + lane_vec == 0) : ((lane & (lps - 1)) == 0);
+    const bool owner = GIVEN ? (t.vec0 + lane_vec == 0) : (lps > 32 ? ((lane_vec & (uint32_t)(4 * lps - 1)) == 0) : ((lane & (lps - 1)) == 0));
     if (owner) {
       const uint64_t g = GIVEN ? 0 : (t.vec0 + lane_vec) / (uint32_t)(4 * lps);
       if (t.scales) reinterpret_cast<uint16_t*>(t.scales)[g] = DType<DT>::from_f32(prep.scale);
@@ -639,10 +649,11 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) seg4_tma_kernel(const __gr
     mbar_wait(&full[stage], phase);
     const TileCtx t = ctx[stage];
     uint8_t* lbase = data + (size_t)stage * kTileBytes + (size_t)lane_vec * 16;
+    uint32_t* xchg = reinterpret_cast<uint32_t*>(smem + 640) + stage * kConsumerWarps;  // [stage][warp] range slots
     if (t.n_vec == (uint32_t)(kTileBytes / 16) && t.codes == nullptr)
-      seg4_consume<DT, KIND, SYM, GIVEN, true>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps);
+      seg4_consume<DT, KIND, SYM, GIVEN, true>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps, warp, xchg);
     else
-      seg4_consume<DT, KIND, SYM, GIVEN, false>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps);
+      seg4_consume<DT, KIND, SYM, GIVEN, false>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps, warp, xchg);
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -1524,7 +1535,14 @@ __global__ void __launch_bounds__(kConsumers) minmax_kernel(const __grid_constan
     acc = ident;
   };
 
-  for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+  // every CTA takes a CONTIGUOUS run of tiles: it streams one contiguous region of memory and crosses only the
+  // few matrix boundaries inside it, so the block reduction + atomics (flush) run once per (CTA, matrix) instead
+  // of once per tile -- with the small shards of the 8-GPU per-tensor configuration (4..16 MB per matrix) a
+  // strided assignment flushed on nearly every tile
+  const uint32_t per = (p.total_units + gridDim.x - 1) / gridDim.x;
+  const uint32_t t_begin = blockIdx.x * per;
+  const uint32_t t_end = t_begin + per < p.total_units ? t_begin + per : p.total_units;
+  for (uint32_t tile = t_begin; tile < t_end; ++tile) {
     advance_job(p, tile, &cur, &jb);
     if (cur != acc_job) {
       if (acc_job >= 0) flush(acc_job);  // block-uniform: every thread sees the same tile sequence

@@ -265,7 +265,8 @@ def test_packed_w4_codes_vs_oracle(dt):
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
 def test_per_channel_row_kernel_vs_oracle(dt):
     """per-channel goes through row_tma_kernel for every row length that is not a power of two <= 1024."""
-    for rows, cols in [(64, 768), (96, 3072), (40, 4096), (33, 11008), (7, 28672), (130, 1024), (50, 1032)]:
+    # 2048 / 4096-element rows take seg4_tma_kernel with 2 / 4 warps per segment (ragged last tiles included)
+    for rows, cols in [(64, 768), (96, 3072), (40, 4096), (33, 11008), (7, 28672), (130, 1024), (50, 1032), (7, 2048), (9, 4096), (5, 8192), (1, 4096)]:
         w = seeded(rows, cols, dt, rows + cols)
         wb = bits(w)
         for nb, sym in [(8, False), (4, True), (4, False)]:
@@ -282,7 +283,7 @@ def test_per_channel_row_kernel_vs_oracle(dt):
 
 def test_odd_group_sizes_and_ragged_tiles():
     """group sizes outside the shuffle path (96, 192, 2048) and matrices that do not fill a 16 KB tile."""
-    for rows, cols, grp in [(8, 192, 96), (16, 384, 192), (4, 4096, 2048), (1, 8, 8), (3, 40, 8), (5, 8200, 8), (1, 128, 128), (1025, 136, 136)]:
+    for rows, cols, grp in [(8, 192, 96), (16, 384, 192), (4, 4096, 2048), (3, 8192, 4096), (3, 16384, 8192), (1, 8, 8), (3, 40, 8), (5, 8200, 8), (1, 128, 128), (1025, 136, 136)]:
         w = seeded(rows, cols, "f16", cols)
         out, scales, zeros, _ = run_int(w.to(DEV), 4, False, grp, want_codes=False)
         ref = O.int_fake_quant(bits(w), "f16", 4, True, grp)
