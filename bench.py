@@ -247,6 +247,12 @@ def run_ours(args):
 
     # ---- end to end: pinned host weights through the host-buffer C-ABI entry point --------------------
     layer_shapes = mats_shape[: len(mats_shape) // LAYERS_PER_RANK]
+    # place this rank's pinned buffers on its GPU's NUMA node (first touch after the affinity change)
+    from iron_weight_only_quant_b200 import hostmem
+
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+    phys = int(visible.split(",")[local]) if visible and visible.split(",")[local].strip().isdigit() else local
+    numa_cpus = hostmem.bind_to_gpu_numa(phys)
     host = [torch.empty(o, k, dtype=torch.float16).pin_memory() for o, k in layer_shapes]
     for h, w in zip(host, weights):
         h.copy_(w)  # quantised values: content is irrelevant for timing
@@ -309,7 +315,7 @@ def run_ours(args):
             "weights_per_s": n_weights * world / (ms_per_step * 1e-3),
             "llama2_70b_full_model_ms": ms_per_step * (8.0 / world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel": "seg4_tma_kernel<f16,INT_FAST,asym>", "bytes_per_launch": nbytes, "kernel_ms": kernel_ms},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_weights * 2, "d2h_bytes_per_step": n_weights * 2, "steps": e2e_steps, "api": "iwq_fake_quant_host_batched (pinned host buffers, one 4-deep H2D/kernel/D2H chunk ring over all 70 matrices)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_weights * 2, "d2h_bytes_per_step": n_weights * 2, "steps": e2e_steps, "api": "iwq_fake_quant_host_batched (pinned host buffers, one 4-deep H2D/kernel/D2H chunk ring over all 70 matrices)", "numa_bound_cpus": len(numa_cpus)},
             "gpu_launches": args.steps,
             "clocks": clocks,
             "nan_status": status,
