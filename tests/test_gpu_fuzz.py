@@ -1,0 +1,123 @@
+"""Seeded randomised parity sweep of the CUDA path against the numpy oracle: random shapes, granularities, bit
+widths, formats, dtypes and both segment directions, on inputs that mix a normal bulk with the adversarial values
+the reference's arithmetic is sensitive to (constant / all-positive / all-negative segments, +-max, subnormals,
+exact .5 ties after scaling, outliers x100, signed zeros).  Bit-exact throughout.
+
+Run on the B200 box:  python -m pytest tests/test_gpu_fuzz.py -m gpu -q
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fakequant_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from iron_weight_only_quant_b200 import _lib
+
+DEV = "cuda:0"
+TDT = {"f16": torch.float16, "bf16": torch.bfloat16}
+
+
+def bits(t):
+    return t.detach().contiguous().cpu().view(torch.int16).numpy().view(np.uint16).copy()
+
+
+def adversarial(rng: np.random.Generator, rows: int, cols: int, dt: str) -> torch.Tensor:
+    w = rng.standard_normal((rows, cols)).astype(np.float32) * 0.02
+    flat = w.reshape(-1, 8)
+    n = flat.shape[0]
+    for kind in range(8):
+        idx = rng.integers(0, n, size=max(1, n // 40))
+        if kind == 0:
+            flat[idx] = 0.0131                      # constant runs
+        elif kind == 1:
+            flat[idx] = np.abs(flat[idx]) + 0.001   # all positive
+        elif kind == 2:
+            flat[idx] = -np.abs(flat[idx]) - 0.001  # all negative
+        elif kind == 3:
+            # large magnitudes of one sign per run (max - min stays finite: overflow to inf is a documented
+            # divergence of NaN patterns)
+            flat[idx, 0] = 30000.0  # (beyond the fp16 range, bf16 BFP differs from the reference: DESIGN.md section 2)
+        elif kind == 4:
+            flat[idx] *= 1e-5                       # fp16 subnormals / tiny bf16
+        elif kind == 5:
+            flat[idx, 3] *= 100.0                   # outliers
+        elif kind == 6:
+            flat[idx, 1] = -0.0
+            flat[idx, 2] = 0.0
+        else:
+            small = np.abs(flat[idx]) < 1.0
+            flat[idx] = np.where(small, np.round(flat[idx] * 64.0) / 64.0 + 1.0 / 128.0, flat[idx])  # exact ties after power-of-two scaling
+    return torch.from_numpy(w).to(TDT[dt])
+
+
+def same(a, b, dt, msg):
+    top = 0x7C00 if dt == "f16" else 0x7F80
+    na, nb = (a & 0x7FFF) > top, (b & 0x7FFF) > top
+    assert np.array_equal(na, nb), f"NaN pattern differs: {msg}: {int(na.sum())} vs {int(nb.sum())} NaNs; first at {np.argwhere(na != nb)[:4].tolist()}"
+    bad = np.where(na, 0, a) != np.where(nb, 0, b)
+    assert not bad.any(), f"{msg}: {int(bad.sum())} of {a.size} differ; first at {np.argwhere(bad)[:4].tolist()}"
+
+
+FP_FORMATS = [(2, 1), (1, 2), (3, 2), (2, 3), (4, 3)]
+
+
+def make_case(seed: int, case: int):
+    """Deterministic in (seed, case) alone, so that a failure can be replayed on the CPU emulator."""
+    rng = np.random.default_rng([1000 + seed, case])
+    dt = ["f16", "bf16"][int(rng.integers(0, 2))]
+    scheme = ["int", "int", "fp", "bfp"][int(rng.integers(0, 4))]
+    qdim = int(rng.integers(0, 2))
+    grp = int(rng.choice([32, 64, 128, 256, -2] if scheme != "bfp" else [32, 64, 128, 256]))
+    g_abs = grp if grp > 0 else 8
+    # the grouped dimension is a multiple of the group, the other a multiple of 8 (16-byte vectors)
+    a = g_abs * int(rng.integers(1, 5))
+    b = 8 * int(rng.integers(1, 70))
+    rows, cols = (a, b) if qdim == 1 else (b, a)
+    if qdim == 0 and grp == -2:
+        cols = int(rng.choice([768, 1032, 2048, 4096, 5120, 11008]))
+        rows = int(rng.integers(1, 20))
+    w = adversarial(rng, rows, cols, dt)
+    sym = bool(rng.integers(0, 2))
+    if scheme == "int":
+        nb = int(rng.choice([2, 3, 4, 5, 6, 8]))
+        kw = dict(scheme=_lib.SCHEME_INT, bits=nb, symmetric=sym)
+        fn, args = O.int_fake_quant, (dt, nb, not sym, grp)
+        tag = f"seed{seed}/{case} {dt} int{nb} sym={sym} g{grp} d{qdim} [{rows},{cols}]"
+    elif scheme == "fp":
+        E, M = FP_FORMATS[int(rng.integers(0, len(FP_FORMATS)))]
+        kw = dict(scheme=_lib.SCHEME_FP_CODEC, exp_bits=E, mant_bits=M, symmetric=sym)
+        fn, args = O.fp_codec_fake_quant, (dt, E, M, sym, grp)
+        tag = f"seed{seed}/{case} {dt} e{E}m{M} sym={sym} g{grp} d{qdim} [{rows},{cols}]"
+    else:
+        nb = int(rng.choice([4, 5, 6, 8]))
+        kw = dict(scheme=_lib.SCHEME_BFP, bits=nb, symmetric=True)
+        fn, args = O.bfp_fake_quant, (dt, nb, grp)
+        tag = f"seed{seed}/{case} {dt} bfp{nb} g{grp} d{qdim} [{rows},{cols}]"
+    return dict(dt=dt, scheme=scheme, qdim=qdim, grp=grp, rows=rows, cols=cols, w=w, sym=sym, kw=kw, fn=fn, args=args, tag=tag)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_configurations_match_oracle(seed):
+    for case in range(14):
+        c = make_case(seed, case)
+        dt, rows, cols, grp, qdim, scheme, tag = c["dt"], c["rows"], c["cols"], c["grp"], c["qdim"], c["scheme"], c["tag"]
+        wb = bits(c["w"])
+        G = _lib.num_segments(rows, cols, grp, qdim)
+        scales = torch.zeros(G, dtype=TDT[dt], device=DEV)
+        zeros = torch.zeros(G, dtype=TDT[dt], device=DEV)
+        wd = c["w"].to(DEV)
+        out = torch.empty_like(wd)
+        kw = dict(c["kw"])
+        cfg = _lib.make_config(TDT[dt], kw.pop("scheme"), grp, quant_dim=qdim, **kw)
+        ref = O.along_output_dim(c["fn"], wb, *c["args"]) if qdim == 1 else c["fn"](wb, *c["args"])
+        emit_z = scheme != "bfp" and not c["sym"]
+        _lib.fake_quant_(wd, out, cfg, rows, cols, scales=None if scheme == "bfp" else scales, zeros=zeros if emit_z else None, track_status=False)
+        same(bits(out), ref["out"], dt, tag)
+        if scheme != "bfp":
+            same(bits(scales), ref["scales"], dt, tag + " scales")
+        if emit_z and "zeros" in ref:
+            # the sign of a zero zero-point is a documented divergence: compare values
+            assert np.array_equal(O.from_bits(bits(zeros), dt), O.from_bits(ref["zeros"], dt), equal_nan=True), tag + " zeros"
