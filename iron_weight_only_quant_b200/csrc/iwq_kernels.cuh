@@ -563,7 +563,7 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
       // ranges through this stage's slots; a named barrier couples just the warps of the segment
       const int wps = lps >> 5, w0 = warp & ~(wps - 1);
       if (lane == 0) xchg[warp] = pk;
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + w0 / wps), "r"(wps * 32) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + (w0 >> (__ffs(wps) - 1))), "r"(wps * 32) : "memory");
       pk = xchg[w0];
 #pragma unroll 1
       for (int w = 1; w < wps; ++w) pk = range_max<DT>(pk, xchg[w0 + w]);

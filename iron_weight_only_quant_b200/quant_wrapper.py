@@ -31,41 +31,83 @@ def _set_submodule(model, name: str, new):
     setattr(parent, path[-1], new)  # quant_wrapper.py:76-80
 
 
-def quantize_linears_batched(shells):
-    """Fake-quantise the weights of already-built QuantLinear shells with as few launches as possible.
+class _Batcher:
+    """Streams QuantLinear shells into batched launches.
 
-    `shells`: list of QuantLinear whose `.weight` aliases the original storage.  Groups them by
-    (device, dtype[, cols for per-channel]) and issues one batched launch per group; per-tensor
-    granularity uses one min/max launch and one apply launch per group.
+    Shells are grouped by (device, dtype[, cols for per-channel]); a group is flushed -- ONE launch for all its
+    matrices (two for per-tensor granularity) -- as soon as it holds `threshold` bytes of weights.  The threshold
+    starts small and doubles after every flush (128 MB -> 2 GB), so the GPU starts working after the first module
+    has been prepared and then always has a launch queued while Python prepares the next modules: the walker's
+    host time (~50 us per module) overlaps the GPU time instead of preceding it.
     """
-    groups = defaultdict(list)
-    for ql in shells:
+
+    FIRST, LAST = 128 << 20, 2 << 30
+
+    def __init__(self):
+        self.groups = defaultdict(list)
+        self.bytes = defaultdict(int)
+        self.threshold = defaultdict(lambda: self.FIRST)
+
+    def add(self, ql):
         plan = ql._plan()
         if plan is None:  # w_bit >= 16: leave untouched (quant_linear.py:887-892)
             ql.quantized.fill_(False)
-            continue
+            return
         cfg, G, wants_zeros = plan
         w = ql.weight.data
         if not w.is_cuda:
             raise RuntimeError("quantize_model: weights must be on CUDA devices (no CPU fallback in iron_weight_only_quant_b200)")
         if not w.is_contiguous() or w.data_ptr() % 16 != 0:
             ql.quantize_weight()  # rare: strided / misaligned storage goes through the single-matrix call
-            continue
+            return
         rows, cols = w.shape
         key = (w.device, w.dtype, cols if (ql.w_group_size == _lib.GROUP_PER_CHANNEL and cfg.quant_dim == 0) else 0)
-        scales, zeros = ql._alloc_qparams(G, wants_zeros)
-        groups[key].append((ql, cfg, _lib.matrix_desc(w, w, rows, cols, scales, zeros), scales, zeros))
-    for (device, _, _), items in groups.items():
+        self.groups[key].append((ql, cfg, w, rows, cols, G, wants_zeros))
+        self.bytes[key] += w.numel() * 2
+        if self.bytes[key] >= self.threshold[key]:
+            self.flush(key)
+            self.threshold[key] = min(self.threshold[key] * 2, self.LAST)
+
+    def flush(self, key):
+        items = self.groups.pop(key, [])
+        self.bytes.pop(key, None)
+        if not items:
+            return
+        device, dtype, _ = key
         cfg = items[0][1]
-        mats = [it[2] for it in items]
+        # one allocation for all scales (and one for all zero points) of the launch, handed out as views
+        n_seg = sum(it[5] for it in items)
+        wants_zeros = items[0][6]
+        pool_s = torch.empty(n_seg, 1, dtype=dtype, device=device) if n_seg else None
+        pool_z = torch.empty(n_seg, 1, dtype=dtype, device=device) if (n_seg and wants_zeros) else None
+        mats, outs, off = [], [], 0
+        for ql, _, w, rows, cols, G, _ in items:
+            scales = pool_s[off : off + G] if G else None
+            zeros = pool_z[off : off + G] if (G and pool_z is not None) else None
+            off += G
+            mats.append(_lib.matrix_desc(w, w, rows, cols, scales, zeros))
+            outs.append((ql, scales, zeros))
         if cfg.group == _lib.GROUP_PER_TENSOR:
             rng = torch.empty(2 * len(mats), dtype=torch.float32, device=device)
             _lib.minmax_(mats, cfg, device, rng)
             _lib.fake_quant_with_range_(mats, cfg, device, rng, track_status=False)
         else:
             _lib.fake_quant_batched_(mats, cfg, device, track_status=False)
-        for ql, _, _, scales, zeros in items:
+        for ql, scales, zeros in outs:
             ql._finish(scales, zeros)
+
+    def flush_all(self):
+        for key in list(self.groups):
+            self.flush(key)
+
+
+def quantize_linears_batched(shells):
+    """Fake-quantise the weights of already-built QuantLinear shells with as few launches as possible
+    (`shells`: QuantLinear modules whose `.weight` aliases the original storage)."""
+    b = _Batcher()
+    for ql in shells:
+        b.add(ql)
+    b.flush_all()
 
 
 def quantize_model(model, args, quant_mix_gate=False):
@@ -86,7 +128,8 @@ def quantize_model(model, args, quant_mix_gate=False):
             )
 
         shells, names = [], []
-        for name, module in model.named_modules():
+        batcher = _Batcher()
+        for name, module in list(model.named_modules()):
             if _is_target(name, module):
                 ql = QuantLinear._shell_from_linear(
                     module,
@@ -108,9 +151,10 @@ def quantize_model(model, args, quant_mix_gate=False):
                     fp4_hi_align_exp_field=getattr(args, "fp4_hi_align_exp_field", 1),
                     fp4_tail_pad_bits=getattr(args, "fp4_tail_pad_bits", 0),
                 )
+                batcher.add(ql)  # launches as soon as enough weights are queued; the GPU works while we walk on
                 shells.append(ql)
                 names.append(name)
-        quantize_linears_batched(shells)
+        batcher.flush_all()
         for name, ql in zip(names, shells):
             _set_submodule(model, name, ql)
     return model
