@@ -121,3 +121,59 @@ def test_random_configurations_match_oracle(seed):
         if emit_z and "zeros" in ref:
             # the sign of a zero zero-point is a documented divergence: compare values
             assert np.array_equal(O.from_bits(bits(zeros), dt), O.from_bits(ref["zeros"], dt), equal_nan=True), tag + " zeros"
+
+
+def _guarded(nbytes: int, guard: int = 4096):
+    """uint8 arena with `guard` canary bytes on both sides of an `nbytes` payload (16-byte aligned payload)."""
+    pad = (16 - nbytes % 16) % 16
+    arena = torch.full((guard + nbytes + pad + guard,), 0xA5, dtype=torch.uint8, device=DEV)
+    return arena, arena[guard : guard + nbytes]
+
+
+def _canaries_intact(arena, nbytes: int, guard: int = 4096) -> bool:
+    return bool((arena[:guard] == 0xA5).all().item()) and bool((arena[guard + nbytes + (16 - nbytes % 16) % 16 :] == 0xA5).all().item())
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_no_out_of_bounds_writes(dt):
+    """compute-sanitizer is not available on the GPU pool, so: every output (weights, scales, zero points, codes)
+    sits between canary zones; ragged tiles, odd row counts and every kernel family must leave them untouched."""
+    esz = 2
+    cases = [
+        # rows, cols, group, quant_dim, scheme kwargs
+        (3, 200, 8, 0, dict(scheme="int", bits=4)), (1025, 136, 136, 0, dict(scheme="int", bits=4)), (7, 4096, -2, 0, dict(scheme="int", bits=8)),
+        (5, 11008, -2, 0, dict(scheme="int", bits=4)), (9, 2048, 2048, 0, dict(scheme="int", bits=4)), (129, 384, 128, 0, dict(scheme="fp", E=2, M=1)),
+        (65, 1024, -1, 0, dict(scheme="int", bits=4)), (384, 264, -2, 1, dict(scheme="int", bits=4)), (256, 520, 128, 1, dict(scheme="int", bits=4)),
+        (512, 72, 32, 1, dict(scheme="fp", E=4, M=3)), (512, 264, 128, 1, dict(scheme="fp", E=2, M=1, approx=2)), (33, 512, 64, 0, dict(scheme="bfp", bits=6)),
+    ]
+    for rows, cols, grp, qd, kw in cases:
+        n = rows * cols
+        G = _lib.num_segments(rows, cols, grp, qd)
+        g = torch.Generator().manual_seed(rows + cols)
+        w = (torch.randn(rows, cols, generator=g) * 0.02).to(TDT[dt])
+        a_w, p_w = _guarded(n * esz)
+        a_s, p_s = _guarded(G * esz)
+        a_z, p_z = _guarded(G * esz)
+        a_c, p_c = _guarded(n)
+        wv = p_w.view(TDT[dt]).view(rows, cols)
+        wv.copy_(w.to(DEV))
+        sym = kw.get("sym", False)
+        if kw["scheme"] == "int":
+            cfg = _lib.make_config(TDT[dt], _lib.SCHEME_INT, grp, bits=kw["bits"], symmetric=sym, quant_dim=qd)
+        elif kw["scheme"] == "fp":
+            ap = kw.get("approx", 0)
+            cfg = _lib.make_config(TDT[dt], _lib.SCHEME_FP_CODEC, grp, exp_bits=kw["E"], mant_bits=kw["M"], symmetric=bool(ap) or sym, quant_dim=qd, approx=ap, hi_align_start=0, hi_align_exp_field=2, tail_pad_bits=1)
+        else:
+            cfg = _lib.make_config(TDT[dt], _lib.SCHEME_BFP, grp, bits=kw["bits"], symmetric=True, quant_dim=qd)
+        emits_q = kw["scheme"] != "bfp"
+        emits_z = emits_q and not cfg.symmetric
+        want_codes = qd == 0 and kw["scheme"] == "int"
+        _lib.fake_quant_(wv, wv, cfg, rows, cols, scales=p_s.view(TDT[dt]) if emits_q else None, zeros=p_z.view(TDT[dt]) if emits_z else None, codes=p_c if want_codes else None, track_status=False)
+        torch.cuda.synchronize()
+        tag = f"{dt} [{rows},{cols}] g{grp} d{qd} {kw}"
+        assert _canaries_intact(a_w, n * esz), tag + ": weight canary"
+        assert _canaries_intact(a_s, G * esz), tag + ": scales canary"
+        assert _canaries_intact(a_z, G * esz), tag + ": zeros canary"
+        assert _canaries_intact(a_c, n), tag + ": codes canary"
+        if not emits_z:
+            assert bool((p_z == 0xA5).all().item()), tag + ": zeros written although not requested"
