@@ -802,11 +802,19 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
       const bool want_codes = t.codes != nullptr;
       Prepared<DT, KIND> prep;
       prep.setup(mx, mn, p.qc, SYM, s_tbl);
-      for (uint32_t i = tid; i < t.n_vec; i += n_cons) {
-        uint2 codes8;
-        const uint4 o = prep.template apply<SYM>(lds128(sdata + (size_t)i * 16), p.qc, s_tbl, want_codes, &codes8);
-        stg128(t.dst + (size_t)i * 16, o);
-        if (want_codes) store_codes(t.codes, i, codes8, p.qc.code_nibbles != 0);
+      if (!want_codes && !prep.slow()) {
+        // hot path: the degenerate-scale (IEEE division) variant is selected once per row, not once per pair
+        for (uint32_t i = tid; i < t.n_vec; i += n_cons) {
+          uint2 codes8;
+          stg128(t.dst + (size_t)i * 16, prep.template apply<SYM, 0>(lds128(sdata + (size_t)i * 16), p.qc, s_tbl, false, &codes8));
+        }
+      } else {
+        for (uint32_t i = tid; i < t.n_vec; i += n_cons) {
+          uint2 codes8;
+          const uint4 o = prep.template apply<SYM>(lds128(sdata + (size_t)i * 16), p.qc, s_tbl, want_codes, &codes8);
+          stg128(t.dst + (size_t)i * 16, o);
+          if (want_codes) store_codes(t.codes, i, codes8, p.qc.code_nibbles != 0);
+        }
       }
       if (tid == 0) {
         if (t.scales) reinterpret_cast<uint16_t*>(t.scales)[t.row] = DType<DT>::from_f32(prep.scale);
@@ -849,10 +857,11 @@ struct PreparedPairInt {
     *sa = qa.s; *za = qa.z; *sb = qb.s; *zb = qb.z;
     *bad = qa.bad || qb.bad;
   }
-  template <bool SYM>
+  __device__ __forceinline__ bool slow() const { return f.slow_div; }
+  template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const {
     typename DType<DT>::T2 d;
-    return f.apply(w2, &d);
+    return f.template apply<SLOW>(w2, &d);
   }
 };
 template <int DT>
@@ -870,7 +879,8 @@ struct PreparedPair<DT, KIND_INT_GENERIC> {
     *sa = qa.s; *za = qa.z; *sb = qb.s; *zb = qb.z;
     *bad = qa.bad || qb.bad;
   }
-  template <bool SYM>
+  __device__ __forceinline__ bool slow() const { return false; }
+  template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts& c) const {
     float k;
     const uint32_t lo = int_generic_elem<DT>((uint16_t)(w2 & 0xFFFFu), qa, c, &k);
@@ -889,9 +899,11 @@ struct PreparedPair<DT, KIND_FP> {
     *sa = qa.S; *za = qa.mid; *sb = qb.S; *zb = qb.mid;
     *bad = qa.bad || qb.bad;
   }
-  template <bool SYM>
+  __device__ __forceinline__ bool slow() const { return f.slow_div; }
+  template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const {
     typename DType<DT>::T2 v;
+    if (SLOW == 0) return f.template apply<false, SYM ? 0 : 1>(w2, &v);
     return f.slow_div ? f.template apply<true, SYM ? 0 : 1>(w2, &v) : f.template apply<false, SYM ? 0 : 1>(w2, &v);
   }
 };
@@ -905,7 +917,8 @@ struct PreparedPair<DT, KIND_BFP> {
     *sa = 0.f; *za = 0.f; *sb = 0.f; *zb = 0.f;
     *bad = false;
   }
-  template <bool SYM>
+  __device__ __forceinline__ bool slow() const { return false; }
+  template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const { return f.apply(w2); }
 };
 
@@ -1322,19 +1335,30 @@ __global__ void __launch_bounds__(kColAsyncWarps * 32) col_async_kernel(const __
     if (t.live && any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
 
     // ---- sweep 2: quantise from shared memory, store from registers ----
-    if (t.live) {
+    const bool any_slow = prep[0].slow() || prep[1].slow() || prep[2].slow() || prep[3].slow();
+    if (t.live && !any_slow) {
+      // hot path: reciprocal+FMA quotient fixed at compile time (the IEEE-division variant is for degenerate scales)
       uint32_t i = 0;
       for (; i + 2 <= n_it; i += 2) {
         const uint4 v0 = lds128(sd + (size_t)i * 512u);
         const uint4 v1 = lds128(sd + (size_t)(i + 1) * 512u);
         uint4 o0, o1;
-        o0.x = prep[0].template apply<SYM>(v0.x, p.qc); o0.y = prep[1].template apply<SYM>(v0.y, p.qc);
-        o0.z = prep[2].template apply<SYM>(v0.z, p.qc); o0.w = prep[3].template apply<SYM>(v0.w, p.qc);
-        o1.x = prep[0].template apply<SYM>(v1.x, p.qc); o1.y = prep[1].template apply<SYM>(v1.y, p.qc);
-        o1.z = prep[2].template apply<SYM>(v1.z, p.qc); o1.w = prep[3].template apply<SYM>(v1.w, p.qc);
+        o0.x = prep[0].template apply<SYM, 0>(v0.x, p.qc); o0.y = prep[1].template apply<SYM, 0>(v0.y, p.qc);
+        o0.z = prep[2].template apply<SYM, 0>(v0.z, p.qc); o0.w = prep[3].template apply<SYM, 0>(v0.w, p.qc);
+        o1.x = prep[0].template apply<SYM, 0>(v1.x, p.qc); o1.y = prep[1].template apply<SYM, 0>(v1.y, p.qc);
+        o1.z = prep[2].template apply<SYM, 0>(v1.z, p.qc); o1.w = prep[3].template apply<SYM, 0>(v1.w, p.qc);
         stg128(t.dst + (size_t)i * t.step, o0);
         stg128(t.dst + (size_t)(i + 1) * t.step, o1);
       }
+      for (; i < n_it; ++i) {
+        const uint4 v0 = lds128(sd + (size_t)i * 512u);
+        uint4 o0;
+        o0.x = prep[0].template apply<SYM, 0>(v0.x, p.qc); o0.y = prep[1].template apply<SYM, 0>(v0.y, p.qc);
+        o0.z = prep[2].template apply<SYM, 0>(v0.z, p.qc); o0.w = prep[3].template apply<SYM, 0>(v0.w, p.qc);
+        stg128(t.dst + (size_t)i * t.step, o0);
+      }
+    } else if (t.live) {
+      uint32_t i = 0;
       for (; i < n_it; ++i) {
         const uint4 v0 = lds128(sd + (size_t)i * 512u);
         uint4 o0;
