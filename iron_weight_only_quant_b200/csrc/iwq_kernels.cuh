@@ -21,6 +21,8 @@
 
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "iwq_consts.h"
 #include "iwq_math.cuh"
 
@@ -1384,7 +1386,7 @@ __global__ void __launch_bounds__(kColAsyncWarps * 32) col_async_kernel(const __
 // integer work (~100 ops per 4 elements): correctness first, it is the research path of the reference.
 // ------------------------------------------------------------------------------------------------
 template <int DT>
-__global__ void __launch_bounds__(256) col_double_kernel(const __grid_constant__ LaunchParams p) {
+__global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constant__ LaunchParams p) {
   using D = DType<DT>;
   using T2 = typename D::T2;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -1480,6 +1482,8 @@ __global__ void __launch_bounds__(256) col_double_kernel(const __grid_constant__
       const uint32_t hf2 = ((uint32_t)p.qc.hi_field << 8) * 0x00010001u;                    // hi_align_exp_field, ae position
       const uint32_t maxe2 = ((uint32_t)((1 << p.qc.exp_bits) - 1) << 8) * 0x00010001u;    // all-ones exponent
       const uint32_t val_saddr = smem_u32(smem + 32768 + p.lut_smem_bytes);
+      auto sweep2 = [&](auto slow_c) {
+      constexpr bool kSlow = decltype(slow_c)::value;  // IEEE division only for degenerate scales: chosen once per tile
       for (uint32_t k = (uint32_t)warp; k < g; k += 8) {
         uint4 v[4];
 #pragma unroll
@@ -1494,7 +1498,7 @@ __global__ void __launch_bounds__(256) col_double_kernel(const __grid_constant__
                               : b == 1 ? (j == 0 ? v[1].x : j == 1 ? v[1].y : j == 2 ? v[1].z : v[1].w)
                               : b == 2 ? (j == 0 ? v[2].x : j == 1 ? v[2].y : j == 2 ? v[2].z : v[2].w)
                                        : (j == 0 ? v[3].x : j == 1 ? v[3].y : j == 2 ? v[3].z : v[3].w);
-            const T2 n = slow ? ieee_quot2<DT>(from_u32<T2>(w2), S[b][j]) : fast_quot2<DT>(from_u32<T2>(w2), S[b][j], R[b][j]);
+            const T2 n = kSlow ? ieee_quot2<DT>(from_u32<T2>(w2), S[b][j]) : fast_quot2<DT>(from_u32<T2>(w2), S[b][j], R[b][j]);
             info[b] = grid.steps_select(n);
             sg[b] = grid.codec_sign(n);
           }
@@ -1521,6 +1525,8 @@ __global__ void __launch_bounds__(256) col_double_kernel(const __grid_constant__
 #pragma unroll
         for (int b = 0; b < 4; ++b) stg128(dst + b * blk + (size_t)k * jb.row_bytes, make_uint4(o[b][0], o[b][1], o[b][2], o[b][3]));
       }
+      };
+      if (slow) sweep2(std::true_type{}); else sweep2(std::false_type{});
     }
   }
 }
