@@ -528,6 +528,9 @@ def test_quantize_model_on_hf_architectures(family):
         n_lin = 2 * 6
     model = model.half().to(DEV).eval()
     before = {n: bits(m.weight.data) for n, m in model.named_modules() if isinstance(m, torch.nn.Linear)}
+    import copy
+
+    twin = copy.deepcopy(model)  # same architecture, weights to be overwritten with the ORACLE's fake-quant output
     args = _Args(w_bit=4, w_group_size=128, w_symmetric=False)
     quant_wrapper.quantize_model(model, args)
     q = {n: m for n, m in model.named_modules() if isinstance(m, quant_linear.QuantLinear)}
@@ -539,8 +542,16 @@ def test_quantize_model_on_hf_architectures(family):
         assert_bits(bits(m.scales.reshape(-1)), ref["scales"], "f16", n + " scales")
     ids = torch.randint(0, 512, (2, 16), device=DEV)
     with torch.no_grad():
-        out = model(ids)
+        out = model(ids, labels=ids)
     assert out.logits.shape == (2, 16, 512) and torch.isfinite(out.logits).all()
+    # "PPL delta" (north star): the model quantised by the CUDA path and the twin carrying the oracle's weights give
+    # the SAME loss and logits bit for bit -- with identical weights perplexity cannot differ, on any dataset
+    for n, m in twin.named_modules():
+        if isinstance(m, torch.nn.Linear) and "lm_head" not in n:
+            m.weight.data.copy_(tensor_of(O.int_fake_quant(before[n], "f16", 4, True, 128)["out"], "f16"))
+    with torch.no_grad():
+        ref_out = twin(ids, labels=ids)
+    assert torch.equal(out.logits, ref_out.logits) and float(out.loss) == float(ref_out.loss)
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
