@@ -56,8 +56,9 @@ enum {
 
 /* status bits OR-ed into the optional device status word by the kernels */
 enum {
-  IWQ_STATUS_NAN = 1 /* some segment produced NaN: the condition of `assert torch.isnan(t).sum()==0`
-                        (quant_funcs.py:40); checked lazily by the host */
+  IWQ_STATUS_NAN = 1,    /* some segment produced NaN: the condition of `assert torch.isnan(t).sum()==0`
+                            (quant_funcs.py:40); checked lazily by the host */
+  IWQ_STATUS_TIMEOUT = 2 /* iwq_fake_quant_per_tensor_fused: a peer's ranges did not arrive within the spin limit */
 };
 
 typedef struct iwq_config {
@@ -122,6 +123,26 @@ int iwq_minmax(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, float* ra
                void* stream);
 int iwq_fake_quant_with_range(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, const float* range, void* workspace,
                               size_t workspace_bytes, int32_t* status, void* stream);
+
+/* The same three steps in ONE launch (pertensor_fused_kernel): range pass, in-kernel exchange of the ranges
+ * through peer-mapped memory (NVLink / NVSwitch P2P stores + system-scope flags; no NCCL call) and apply pass,
+ * software-pipelined over L2-sized batches of matrices so that the apply pass reads the weights from L2
+ * (HBM traffic 4 B/weight instead of 6).  `peers` == NULL: single GPU (world 1), scratch comes from `workspace`.
+ * Otherwise every rank of the group calls this with its own shards and the same `n`, shapes and config:
+ *   slot_ptrs[r] / flag_ptrs[r] = rank r's exchange buffers AS MAPPED ON THIS GPU (e.g. torch symmetric memory),
+ *   slots: float[2][world][2 * n] (double-buffered by epoch parity), flags: uint32[world][n] (>= one per batch),
+ *   zero-initialised once; `epoch` must be non-zero and different from the previous call's on these buffers.
+ * `workspace`: device memory of at least iwq_fused_workspace_bytes(n).  Status: IWQ_STATUS_NAN / IWQ_STATUS_TIMEOUT. */
+typedef struct iwq_peers {
+  int32_t world, rank;
+  void* const* slot_ptrs; /* host array [world] of device pointers */
+  void* const* flag_ptrs; /* host array [world] of device pointers */
+  uint32_t epoch;
+  uint32_t spin_limit;    /* 0 = default (about one second) */
+} iwq_peers_t;
+size_t iwq_fused_workspace_bytes(int n);
+int iwq_fake_quant_per_tensor_fused(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, void* workspace, size_t workspace_bytes,
+                                    const iwq_peers_t* peers, int32_t* status, void* stream);
 
 /* ---- element-wise pieces, exposed for exhaustive parity tests ---------------------------------- */
 /* decode(encode(x)) of the quant_linear minifloat codec on `n` 16-bit values (quant_linear.py:126-163,

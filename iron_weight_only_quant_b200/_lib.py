@@ -20,6 +20,7 @@ IWQ_F16, IWQ_BF16 = 0, 1
 SCHEME_INT, SCHEME_FP_CODEC, SCHEME_FP_RNE, SCHEME_BFP = 0, 1, 2, 3
 GROUP_PER_TENSOR, GROUP_PER_CHANNEL = -1, -2
 STATUS_NAN = 1
+STATUS_TIMEOUT = 2
 
 ERR_INVALID, ERR_INDIVISIBLE, ERR_UNSUPPORTED, ERR_CUDA, ERR_ALIGN, ERR_FP16_RANGE = -1, -2, -3, -4, -5, -6
 
@@ -35,6 +36,8 @@ EXPORTS = (
     "iwq_selftest_division",
     "iwq_fake_quant_host",
     "iwq_fake_quant_host_batched",
+    "iwq_fused_workspace_bytes",
+    "iwq_fake_quant_per_tensor_fused",
 )
 
 
@@ -56,6 +59,12 @@ class Matrix(ctypes.Structure):
         ("rows", ctypes.c_int64),
         ("cols", ctypes.c_int64),
     ]
+
+
+class Peers(ctypes.Structure):
+    """struct iwq_peers (include/iwq_b200.h)."""
+
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("slot_ptrs", ctypes.POINTER(ctypes.c_void_p)), ("flag_ptrs", ctypes.POINTER(ctypes.c_void_p)), ("epoch", ctypes.c_uint32), ("spin_limit", ctypes.c_uint32)]
 
 
 class HostMatrix(ctypes.Structure):
@@ -103,6 +112,10 @@ def lib() -> ctypes.CDLL:
         L.iwq_fake_quant_host.argtypes = [ctypes.POINTER(Config), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32)]
         L.iwq_fake_quant_host_batched.restype = ctypes.c_int
         L.iwq_fake_quant_host_batched.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(HostMatrix), ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32)]
+        L.iwq_fused_workspace_bytes.restype = ctypes.c_size_t
+        L.iwq_fused_workspace_bytes.argtypes = [ctypes.c_int]
+        L.iwq_fake_quant_per_tensor_fused.restype = ctypes.c_int
+        L.iwq_fake_quant_per_tensor_fused.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(Matrix), ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(Peers), ctypes.c_void_p, ctypes.c_void_p]
         if L.iwq_abi_version() != 3:
             raise RuntimeError("libiwq_b200.so ABI version mismatch")
         _lib = L
@@ -249,3 +262,22 @@ def fake_quant_host_(tensors: Sequence[torch.Tensor], cfg: Config, device: int =
     st = ctypes.c_int32(0)
     check(lib().iwq_fake_quant_host_batched(ctypes.byref(cfg), arr, len(ms), int(device), int(chunk_bytes), ctypes.byref(st)))
     return int(st.value)
+
+
+def per_tensor_fused_(mats: Sequence[Matrix], cfg: Config, device: torch.device, peers: Optional[Peers] = None, track_status: bool = True):
+    """ONE launch for per-tensor granularity over many matrices (range pass, in-kernel range exchange with the
+    peers when the matrices are sharded across GPUs, apply pass from L2): iwq_fake_quant_per_tensor_fused."""
+    n = len(mats)
+    arr = (Matrix * n)(*mats)
+    with torch.cuda.device(device):
+        status, _, _ = scratch(device, n)
+        need = lib().iwq_fused_workspace_bytes(n)
+        key = ("fused_ws", device.index if device.index is not None else torch.cuda.current_device())
+        ws = _scratch.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
+            _scratch[key] = ws
+        stream = torch.cuda.current_stream(device).cuda_stream
+        rc = lib().iwq_fake_quant_per_tensor_fused(ctypes.byref(cfg), arr, n, ws.data_ptr(), ws.numel(), ctypes.byref(peers) if peers is not None else None, status.data_ptr() if track_status else None, stream)
+    check(rc)
+    return status

@@ -45,6 +45,8 @@ struct Knobs {
   int row_warps = env_int("IWQ_ROW_WARPS", 0);       // consumer warps of the row kernels; 0 = automatic
   int col_tile = env_int("IWQ_COL_TILE", 0);         // quant_dim = 1: columns per tile (64/128/256), -1 = two-sweep kernel
   int col_ctas = env_int("IWQ_COL_CTAS", 0);
+  int fused_batch_mb = env_int("IWQ_FUSED_BATCH_MB", 16);  // pertensor_fused_kernel: bytes of weights per batch
+  int fused_lookahead = env_int("IWQ_FUSED_LOOKAHEAD", 2); // ... and how many batches the range pass runs ahead
   int wide_seg4 = env_int("IWQ_WIDE_SEG4", 1);       // 1: segments of 2048/4096/8192 elements go through seg4_tma_kernel
   int col_mode = env_int("IWQ_COL_MODE", 0);         // 0: warp-private cp.async ring (col_async_kernel), 1: register-resident
   int col_stages = env_int("IWQ_COL_STAGES", 0);     // ring depth of col_async_kernel (1..4); 0 = automatic
@@ -159,6 +161,24 @@ static cudaError_t dispatch_col(int dt, int kind, const LaunchParams& p, bool sy
     case KIND_FP: return launch_col<IWQ_BF16, KIND_FP>(p, sym, t, st);
     case KIND_BFP: return launch_col<IWQ_BF16, KIND_BFP>(p, sym, t, st);
     default: return launch_col<IWQ_BF16, KIND_INT_GENERIC>(p, sym, t, st);
+  }
+}
+
+static cudaError_t dispatch_fused(int dt, int kind, const LaunchParams& p, const FusedParams& f, bool sym, const LaunchTuning& t, cudaStream_t st, int* grid) {
+  if (dt == IWQ_F16) {
+    switch (kind) {
+      case KIND_INT_FAST: return launch_fused<IWQ_F16, KIND_INT_FAST>(p, f, sym, t, st, grid);
+      case KIND_FP: return launch_fused<IWQ_F16, KIND_FP>(p, f, sym, t, st, grid);
+      case KIND_BFP: return cudaErrorInvalidValue;
+      default: return launch_fused<IWQ_F16, KIND_INT_GENERIC>(p, f, sym, t, st, grid);
+    }
+  }
+  switch (kind) {
+    case KIND_INT_FAST: return launch_fused<IWQ_BF16, KIND_INT_FAST>(p, f, sym, t, st, grid);
+    case KIND_INT_WIDE: return launch_fused<IWQ_BF16, KIND_INT_WIDE>(p, f, sym, t, st, grid);
+    case KIND_FP: return launch_fused<IWQ_BF16, KIND_FP>(p, f, sym, t, st, grid);
+    case KIND_BFP: return cudaErrorInvalidValue;
+    default: return launch_fused<IWQ_BF16, KIND_INT_GENERIC>(p, f, sym, t, st, grid);
   }
 }
 
@@ -582,6 +602,116 @@ int iwq_fake_quant_with_range(const iwq_config_t* cfg, const iwq_matrix_t* ms, i
   if (!cfg || cfg->group != IWQ_GROUP_PER_TENSOR) return fail(IWQ_ERR_INVALID, "iwq_fake_quant_with_range is for per-tensor granularity");
   if (!range) return fail(IWQ_ERR_INVALID, "null range buffer");
   return run_batched(cfg, ms, n, workspace, workspace_bytes, range, nullptr, status, (cudaStream_t)stream, false);
+}
+
+size_t iwq_fused_workspace_bytes(int n) {
+  const size_t m = (size_t)(n < 1 ? 1 : n);
+  // jobs | batch_tile0 | batch_job0 | arrive | local_range | local slots [2][1][2n] | local flags | 2 x 16 peer pointers
+  return m * sizeof(Job) + 2 * (m + 1) * 4 + m * 4 + 2 * m * 4 + 4 * m * 4 + m * 4 + 2 * 16 * 8 + 256;
+}
+
+int iwq_fake_quant_per_tensor_fused(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, void* workspace, size_t workspace_bytes,
+                                    const iwq_peers_t* peers, int32_t* status, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!cfg || !ms || n < 1) return fail(IWQ_ERR_INVALID, "null config/matrices or n < 1");
+  if (cfg->group != IWQ_GROUP_PER_TENSOR || cfg->quant_dim != 0) return fail(IWQ_ERR_INVALID, "iwq_fake_quant_per_tensor_fused is for per-tensor granularity");
+  if (!workspace || workspace_bytes < iwq_fused_workspace_bytes(n)) return fail(IWQ_ERR_INVALID, "workspace too small (see iwq_fused_workspace_bytes)");
+  if ((uintptr_t)workspace & 15) return fail(IWQ_ERR_ALIGN, "workspace must be 16-byte aligned");
+  const int world = peers ? peers->world : 1, rank = peers ? peers->rank : 0;
+  if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(IWQ_ERR_INVALID, "bad world / rank");
+  if (peers && (!peers->slot_ptrs || !peers->flag_ptrs || peers->epoch == 0)) return fail(IWQ_ERR_INVALID, "peers: null pointer arrays or epoch 0");
+  LaunchParams p;
+  memset(&p, 0, sizeof(p));
+  int kind = 0;
+  int rc = build_consts(cfg, &p.qc, &kind);
+  if (rc) return rc;
+  if (kind == KIND_BFP) return fail(IWQ_ERR_INVALID, "BFP needs a positive group size");
+  if (kind == KIND_FP) {
+    rc = get_fp_lut(cfg, p.qc, st, &p.lut);
+    if (rc) return rc;
+    p.lut_smem_bytes = (uint32_t)(((size_t)p.qc.lut_n * sizeof(FpStep) + 1023) & ~(size_t)1023);
+  }
+  Plan pl;
+  memset(&pl, 0, sizeof(pl));
+  pl.path = PATH_SEG;
+  pl.lps = 1;
+  pl.vpl = 1;
+  std::vector<Job> jobs;
+  rc = fill_params(cfg, ms, n, pl, &p, &jobs);
+  if (rc) return rc;
+  if (p.n_stages < 3) p.n_stages = 3;  // the fused kernel parks one stage behind its bulk store across item changes
+  for (int i = 0; i < n; ++i)
+    if (ms[i].codes) return fail(IWQ_ERR_UNSUPPORTED, "the fused per-tensor entry point does not emit codes");
+  p.status = status;
+  // batches of whole matrices
+  const uint64_t batch_bytes = (uint64_t)(knobs().fused_batch_mb > 0 ? knobs().fused_batch_mb : 16) << 20;
+  std::vector<uint32_t> b_tile0, b_job0;
+  uint64_t acc = 0;
+  int in_batch = 0;
+  for (int i = 0; i < n; ++i) {
+    if (acc == 0) {
+      b_tile0.push_back(jobs[i].first_unit);
+      b_job0.push_back((uint32_t)i);
+      in_batch = 0;
+    }
+    acc += jobs[i].bytes;
+    if (acc >= batch_bytes || ++in_batch >= kFusedMaxBatchJobs) acc = 0;
+  }
+  const int nb = (int)b_tile0.size();
+  if (nb > 2048) return fail(IWQ_ERR_UNSUPPORTED, "too many batches for one fused launch (raise IWQ_FUSED_BATCH_MB or split the call)");
+  b_tile0.push_back(p.total_units);
+  b_job0.push_back((uint32_t)n);
+  // one host blob -> one H2D copy: tables, zeroed counters / local flags, -inf ranges, peer pointer arrays
+  const size_t m = (size_t)n;
+  size_t off = 0;
+  auto take = [&](size_t bytes, size_t align) { off = (off + align - 1) / align * align; size_t o = off; off += bytes; return o; };
+  const size_t o_jobs = take(m * sizeof(Job), 16), o_bt = take((m + 1) * 4, 4), o_bj = take((m + 1) * 4, 4), o_arr = take(m * 4, 4);
+  const size_t o_rng = take(2 * m * 4, 4), o_slots = take(4 * m * 4, 16), o_flags = take(m * 4, 4), o_sp = take(16 * 8, 8), o_fp = take(16 * 8, 8);
+  if (off > workspace_bytes) return fail(IWQ_ERR_INVALID, "workspace too small (see iwq_fused_workspace_bytes)");
+  std::vector<uint8_t> blob(off, 0);
+  memcpy(blob.data() + o_jobs, jobs.data(), m * sizeof(Job));
+  memcpy(blob.data() + o_bt, b_tile0.data(), b_tile0.size() * 4);
+  memcpy(blob.data() + o_bj, b_job0.data(), b_job0.size() * 4);
+  for (size_t i = 0; i < 2 * m; ++i) reinterpret_cast<float*>(blob.data() + o_rng)[i] = -INFINITY;
+  uint8_t* ws = (uint8_t*)workspace;
+  FusedParams f;
+  memset(&f, 0, sizeof(f));
+  void** sp = reinterpret_cast<void**>(blob.data() + o_sp);
+  void** fp = reinterpret_cast<void**>(blob.data() + o_fp);
+  if (peers) {
+    for (int r = 0; r < world; ++r) {
+      if (!peers->slot_ptrs[r] || !peers->flag_ptrs[r]) return fail(IWQ_ERR_INVALID, "peers: null buffer pointer");
+      sp[r] = peers->slot_ptrs[r];
+      fp[r] = peers->flag_ptrs[r];
+    }
+    f.epoch = peers->epoch;
+  } else {
+    sp[0] = ws + o_slots;  // zeroed by the blob copy; epoch 1 of a fresh flag array
+    fp[0] = ws + o_flags;
+    f.epoch = 1;
+  }
+  cudaError_t e = cudaMemcpyAsync(workspace, blob.data(), off, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(fused tables)");
+  p.jobs = (const Job*)(ws + o_jobs);
+  f.local_range = (float*)(ws + o_rng);
+  f.arrive = (uint32_t*)(ws + o_arr);
+  f.batch_tile0 = (const uint32_t*)(ws + o_bt);
+  f.batch_job0 = (const uint32_t*)(ws + o_bj);
+  f.peer_slots = (float* const*)(ws + o_sp);
+  f.peer_flags = (uint32_t* const*)(ws + o_fp);
+  f.n_batches = nb;
+  f.world = world;
+  f.rank = rank;
+  f.spin_limit = (peers && peers->spin_limit) ? peers->spin_limit : 2000000u;
+  f.poll_ns = (uint32_t)env_int("IWQ_FUSED_POLL_NS", 200);
+  f.lookahead = knobs().fused_lookahead > 0 ? (knobs().fused_lookahead < kFusedRing ? knobs().fused_lookahead : kFusedRing - 1) : 2;
+  LaunchTuning tune;
+  tune.stages = p.n_stages;
+  tune.ctas_per_sm = knobs().seg_ctas;
+  int grid = 0;
+  e = dispatch_fused(cfg->dtype, kind, p, f, p.qc.symmetric != 0, tune, st, &grid);
+  if (e != cudaSuccess) return fail_cuda(e, "fused per-tensor kernel launch");
+  return IWQ_OK;
 }
 
 int iwq_fp_roundtrip(int dtype, int flavour, int exp_bits, int mant_bits, const void* x, void* y, void* codes, int64_t n, void* stream) {

@@ -110,6 +110,23 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                : "memory");
 }
 
+// the same with an L2 eviction-priority hint (createpolicy): evict_last keeps a tile that will be re-read soon
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+
 // shared::cta -> global bulk store (SASS: UBLKCP), tracked by the thread's bulk async-group
 __device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
@@ -1601,6 +1618,366 @@ __global__ void __launch_bounds__(kConsumers) minmax_kernel(const __grid_constan
     for (int it = 0; it < kVPT; ++it) acc = range_max<DT>(acc, vec_range<DT, SYM>(v[it]));
   }
   if (acc_job >= 0) flush(acc_job);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pertensor_fused_kernel: per-tensor granularity in ONE launch, also when every matrix is row-split across the
+// GPUs of a box (BASELINE config 4) -- range pass, range exchange and apply pass fused.
+//
+//   * the matrices are cut into BATCHES of whole matrices (~24 MB: a few batches fit the 126 MB L2);
+//   * range pass of batch b (the 8 consumer warps of every CTA, 128-bit loads, warp-level reduction, ordered
+//     atomics into this GPU's {max, -min} per matrix); the LAST CTA to finish a batch (arrival counter) publishes
+//     the batch's ranges: it stores them into slot [rank] of EVERY rank's exchange buffer through the peer-mapped
+//     (NVLink / NVSwitch) pointers, fences at system scope and raises flag [rank][b] on every rank -- no NCCL call,
+//     no second launch, a few microseconds per batch, overlapped with the other batches' work;
+//   * the producer lane waits until all ranks' flags for batch b are up (acquire, bounded spin), takes the
+//     maximum over the ranks' slots and streams the batch's tiles through the usual TMA ring; the consumers run
+//     the seg4 element stage with the given range.  The tiles were read by the range pass moments ago, so the
+//     apply pass reads them from L2: HBM sees 2 B/weight of reads + 2 B/weight of writes instead of 4 + 2;
+//   * software pipeline per CTA: range(0), range(1), then for every batch: apply(b), range(b + 2) -- the exchange
+//     latency of a batch hides behind the apply pass of the previous one.
+// All CTAs must be co-resident (persistent grid sized by the occupancy API), as for any arrival-counter scheme.
+// world == 1 runs the same code with the local buffers as the only "peer".
+// ------------------------------------------------------------------------------------------------
+struct FusedParams {
+  float* local_range;            // [2 * n_jobs] {max, -min}, initialised to -inf by the host
+  uint32_t* arrive;              // [n_batches] arrival counters, zero-initialised
+  const uint32_t* batch_tile0;   // [n_batches + 1] first tile of every batch
+  const uint32_t* batch_job0;    // [n_batches + 1] first job of every batch
+  float* const* peer_slots;      // [world] rank r's exchange buffer: float[world][2 * n_jobs], as mapped on THIS GPU
+  uint32_t* const* peer_flags;   // [world] rank r's flag array: uint32[world][n_batches]
+  int32_t n_batches, world, rank;
+  uint32_t epoch;                // value a raised flag carries in this call (flags persist across calls)
+  uint32_t spin_limit;           // bounded wait: afterwards IWQ_STATUS_TIMEOUT is raised instead of hanging
+  int32_t lookahead;             // batches the range pass runs ahead of the apply pass (>= 1)
+  uint32_t poll_ns;              // sleep of the exchange lanes between polls
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float max_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
+
+// The CTA's work list is a fixed interleaving of RANGE and APPLY items over the batches -- R(0), R(1), A(0), R(2),
+// A(1), ... -- walked identically by the producer lane and by the consumers; BOTH kinds of item are tiles streamed
+// through the same TMA ring (a range item is read-only: the consumers reduce it from shared memory and hand the
+// stage straight back), so the range pass runs at the same bandwidth as the apply pass.
+constexpr int kFusedMaxBatchJobs = 16;  // matrices per batch (the host closes a batch earlier if need be)
+constexpr int kFusedRing = 8;           // batches whose reduced ranges may be parked in shared memory (lookahead < kFusedRing)
+
+__device__ __forceinline__ uint32_t fused_first_tile(uint32_t t0) {  // first tile >= t0 with tile % gridDim.x == blockIdx.x
+  return t0 + (blockIdx.x + gridDim.x - t0 % gridDim.x) % gridDim.x;
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking
+  uint32_t ok;
+  asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// The exchange state machine, run by lanes 1..31 of the producer warp (lane 0 issues the TMA copies and must not wait
+// on microsecond-long global / peer loads).  The 31 lanes work in parallel so that a step costs ONE memory latency:
+//   publish: this CTA is the publisher of the batches b == blockIdx.x (mod gridDim.x): once all consumer warps of
+//            the grid have arrived for such a batch, the lanes copy the batch's local ranges into slot [rank] of every
+//            rank's exchange buffer (peer-mapped stores), fence at system scope and raise flag [rank][b] everywhere;
+//   gather : batches in order: lane r + 1 polls rank r's flag; when all are up, lane (job, rank) pairs fetch the
+//            slots, the maximum over the ranks goes into the shared-memory ring s_rng[gather_b % kFusedRing][job].
+struct FusedExchange {
+  int pub_b;      // next batch this CTA has to publish (>= n_batches: none left)
+  int gather_b;   // next batch whose ranges are to be gathered
+  uint32_t spins;
+};
+constexpr uint32_t kXchgMask = 0xFFFFFFFEu;  // lanes 1..31
+
+template <bool SYM>
+__device__ __forceinline__ void fused_exchange_step(const LaunchParams& p, const FusedParams& f, FusedExchange& x, float2* s_rng, float2* s_tmp,
+                                                    const uint32_t* s_bj, int lane) {
+  const int nb = f.n_batches, xl = lane - 1;  // xl: 0..30
+  if (x.pub_b < nb) {
+    uint32_t cnt = 0;
+    if (xl == 0) cnt = ld_acquire_gpu_u32(&f.arrive[x.pub_b]);
+    cnt = __shfl_sync(kXchgMask, cnt, 1);
+    if (cnt == gridDim.x * (uint32_t)kConsumerWarps) {
+      const uint32_t j0 = s_bj[x.pub_b], j1 = s_bj[x.pub_b + 1];
+      const uint32_t nv = 2u * (j1 - j0), total = nv * (uint32_t)f.world;
+      const size_t slot_off = ((size_t)(f.epoch & 1u) * f.world + f.rank) * 2u * p.n_jobs + 2u * j0;  // [parity][source rank][2 * n_jobs]
+      for (uint32_t i = (uint32_t)xl; i < total; i += 31u) {
+        const uint32_t r = i / nv, k = i - r * nv;
+        f.peer_slots[r][slot_off + k] = __ldcg(&f.local_range[2u * j0 + k]);  // peer-mapped store (NVLink), local when r == rank
+      }
+      __threadfence_system();
+      __syncwarp(kXchgMask);
+      if (xl < f.world) st_release_sys_u32(&f.peer_flags[xl][(size_t)f.rank * nb + x.pub_b], f.epoch);
+      x.pub_b += (int)gridDim.x;
+    }
+  }
+  if (x.gather_b < nb) {
+    const uint32_t* my_flags = f.peer_flags[f.rank];
+    bool ok = true;
+    for (int r = xl; r < f.world; r += 31) ok = ok && (ld_acquire_sys_u32(&my_flags[(size_t)r * nb + x.gather_b]) == f.epoch);
+    const bool all = __all_sync(kXchgMask, ok);
+    const bool give_up = !all && (++x.spins > f.spin_limit);  // bounded: do not hang the GPU on a missing peer
+    if (all || give_up) {
+      if (give_up && xl == 0 && p.status) atomicOr(p.status, IWQ_STATUS_TIMEOUT);
+      const float* my_slots = f.peer_slots[f.rank] + (size_t)(f.epoch & 1u) * f.world * 2u * p.n_jobs;
+      const uint32_t j0 = s_bj[x.gather_b], j1 = s_bj[x.gather_b + 1];
+      const uint32_t nj = j1 - j0, total = nj * (uint32_t)f.world;
+      for (uint32_t i = (uint32_t)xl; i < total; i += 31u) {  // (job, rank) pairs in parallel: one latency
+        const uint32_t r = i / nj, j = i - r * nj;
+        const float* src = &my_slots[(size_t)r * 2u * p.n_jobs + 2u * (j0 + j)];
+        s_tmp[j * 16u + r] = make_float2(ld_relaxed_sys_f32(src), SYM ? -INFINITY : ld_relaxed_sys_f32(src + 1));
+      }
+      __syncwarp(kXchgMask);
+      for (uint32_t j = (uint32_t)xl; j < nj; j += 31u) {
+        float mx = -INFINITY, nmn = -INFINITY;
+        for (int r = 0; r < f.world; ++r) {
+          const float2 v = s_tmp[j * 16u + r];
+          mx = max_nan(mx, v.x);
+          nmn = max_nan(nmn, v.y);
+        }
+        s_rng[(x.gather_b % kFusedRing) * kFusedMaxBatchJobs + j] = make_float2(mx, -nmn);
+      }
+      __syncwarp(kXchgMask);
+      ++x.gather_b;
+      x.spins = 0;
+    }
+  }
+}
+
+template <int DT, int KIND, bool SYM>
+__global__ void __launch_bounds__(kConsumers + 32, 3) pertensor_fused_kernel(const __grid_constant__ LaunchParams p, const __grid_constant__ FusedParams f) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + kMaxStages;
+  TileCtx* ctx = reinterpret_cast<TileCtx*>(smem + 128);
+  const FpStep* s_tbl = nullptr;
+  uint8_t* data = smem + kSmemHeader + p.lut_smem_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_stages = p.n_stages;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kConsumerWarps);
+    }
+    fence_mbar_init();
+  }
+  if (KIND == KIND_FP) s_tbl = load_fp_lut(p, smem + kSmemHeader);
+  const int nb = f.n_batches;
+  // batch tables in shared memory: an item is only 1..4 tiles per CTA, two dependent global loads per item and warp
+  // would cost as much as the item itself
+  uint32_t* s_bt = reinterpret_cast<uint32_t*>(data + (size_t)n_stages * kTileBytes + (size_t)(kFusedRing + 16) * kFusedMaxBatchJobs * sizeof(float2));
+  uint32_t* s_bj = s_bt + (nb + 1);
+  for (int i = threadIdx.x; i <= nb; i += blockDim.x) {
+    s_bt[i] = f.batch_tile0[i];
+    s_bj[i] = f.batch_job0[i];
+  }
+  if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(smem + 900) = 0u;
+  __syncthreads();
+  // the schedule, walked identically by the producer lane and the consumers: RANGE items run `lookahead` batches
+  // ahead of the APPLY items -- R(0) .. R(D-1), A(0), R(D), A(1), R(D+1), ... -- so that a batch's publication and
+  // exchange latency (~10 us) hides behind D - 1 batches of work while D + 1 batches stay L2-resident.  BOTH kinds
+  // of item are tiles streamed through the same TMA ring (a range item is read-only: the consumers reduce it from
+  // shared memory and hand the stage straight back).
+  const int D = f.lookahead;
+  int next_r = 0, next_a = 0;
+  auto next_item = [&](int* batch) -> bool {  // returns true for a RANGE item; call while next_a < nb
+    if (next_r < nb && next_r < next_a + D) {
+      *batch = next_r++;
+      return true;
+    }
+    *batch = next_a++;
+    return false;
+  };
+
+  if (warp == kConsumerWarps) {
+    float2* s_rng = reinterpret_cast<float2*>(data + (size_t)n_stages * kTileBytes);  // [kFusedRing][kFusedMaxBatchJobs]
+    volatile uint32_t* s_gathered = reinterpret_cast<volatile uint32_t*>(smem + 900);  // batches whose ranges are in s_rng
+    if (lane >= 1) {
+      // ---------------- exchange lanes 1..31: publish this CTA's batches, gather every batch's ranges ----------------
+      float2* s_tmp = s_rng + kFusedRing * kFusedMaxBatchJobs;  // [kFusedMaxBatchJobs][16 ranks] scratch
+      FusedExchange x;
+      x.pub_b = (int)blockIdx.x;
+      x.gather_b = 0;
+      x.spins = 0;
+      while (x.gather_b < nb || x.pub_b < nb) {
+        const int before = x.gather_b;
+        fused_exchange_step<SYM>(p, f, x, s_rng, s_tmp, s_bj, lane);
+        if (x.gather_b != before) {
+          __threadfence_block();
+          if (lane == 1) *s_gathered = (uint32_t)x.gather_b;
+        } else {
+          __nanosleep(f.poll_ns);
+        }
+      }
+    } else if (lane == 0) {
+      // ---------------- producer lane: TMA issue ----------------
+      int stage = 0;
+      uint32_t phase = 0;
+      // two cursors over the job table (range stream, apply stream), each with the NEXT job's first tile cached in a
+      // register: a range tile is only ~1 us of HBM time per CTA, a dependent global load per tile would cap the rate
+      struct Cursor {
+        int cur;
+        uint32_t next_first;
+        Job jb;
+      } cr, ca;
+      const Job* jobs = job_table(p);
+      auto seek = [&](Cursor& c, uint32_t tile) {
+        if (c.cur >= 0 && tile < c.next_first) return;
+        int j = c.cur < 0 ? 0 : c.cur;
+        if (c.cur < 0 && p.n_jobs > 8) {
+          int lo = 0, hi = p.n_jobs - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (jobs[mid].first_unit <= tile) lo = mid; else hi = mid - 1;
+          }
+          j = lo;
+        }
+        while (j + 1 < p.n_jobs && tile >= jobs[j + 1].first_unit) ++j;
+        c.cur = j;
+        c.jb = jobs[j];
+        c.next_first = j + 1 < p.n_jobs ? jobs[j + 1].first_unit : 0xFFFFFFFFu;
+      };
+      cr.cur = -1;
+      ca.cur = -1;
+      const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+      while (next_a < nb) {
+        int b;
+        const bool is_range = next_item(&b);
+        if (!is_range) {
+          while (*s_gathered <= (uint32_t)b) __nanosleep(64);  // the batch's ranges from every rank (exchange lanes)
+          __threadfence_block();
+        }
+        const uint32_t j0 = s_bj[b];
+        const uint32_t t1 = s_bt[b + 1];
+        for (uint32_t tile = fused_first_tile(s_bt[b]); tile < t1; tile += gridDim.x) {
+          if (is_range) seek(cr, tile); else seek(ca, tile);
+          const int cur = is_range ? cr.cur : ca.cur;
+          const Job& jb = is_range ? cr.jb : ca.jb;
+          mbar_wait(&empty[stage], phase ^ 1u);
+          TileCtx t = make_tile_ctx(p, jb, cur, tile, false);
+          t.pad = is_range ? (1u + (uint32_t)cur) : 0u;  // range item: job index + 1
+          if (!is_range) {
+            const float2 g = s_rng[(b % kFusedRing) * kFusedMaxBatchJobs + ((uint32_t)cur - j0)];
+            t.given_mx = g.x;
+            t.given_mn = g.y;
+          }
+          ctx[stage] = t;
+          const uint32_t bytes = t.n_vec * 16u;
+          mbar_arrive_expect_tx(&full[stage], bytes);
+          // range tiles come back within a few batches: keep them in L2; apply tiles are never read again
+          tma_load_1d_hint(data + (size_t)stage * kTileBytes, jb.src + (t.vec0 << 4), bytes, &full[stage], is_range ? pol_keep : pol_drop);
+          if (++stage == n_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const uint32_t lane_vec = (uint32_t)warp * 128u + (uint32_t)lane * 4u;
+  const uint32_t rot = (uint32_t)lane >> 1;
+  const uint32_t ident = SYM ? 0u : (DT == IWQ_F16 ? 0xFC00FC00u : 0xFF80FF80u);
+  int stage = 0, pending = -1;  // pending: stage whose bulk store may still be reading shared memory
+  bool aged = false;            // ... and at least one further tile has been consumed since that store was issued
+  uint32_t phase = 0;
+  while (next_a < nb) {
+    int b;
+    const bool is_range = next_item(&b);
+    const uint32_t t1 = s_bt[b + 1];
+    uint32_t acc = ident;
+    int acc_job = -1;
+    auto flush = [&](int job) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) acc = range_max<DT>(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
+      if (lane == 0) {
+        float mx, mn;
+        range_unpack<DT>(acc, &mx, &mn);
+        atomic_max_float(&f.local_range[2 * job], mx);
+        if (!SYM) atomic_max_float(&f.local_range[2 * job + 1], -mn);
+      }
+      acc = ident;
+    };
+    for (uint32_t tile = fused_first_tile(s_bt[b]); tile < t1; tile += gridDim.x) {
+      mbar_wait(&full[stage], phase);
+      const TileCtx t = ctx[stage];
+      uint8_t* lbase = data + (size_t)stage * kTileBytes + (size_t)lane_vec * 16;
+      if (is_range) {
+        const int job = (int)t.pad - 1;
+        if (job != acc_job) {
+          if (acc_job >= 0) flush(acc_job);
+          acc_job = job;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // lanes past the end of a ragged tile re-read its first vector: harmless for a max/min
+          const uint32_t jj = ((uint32_t)j + rot) & 3u;
+          const uint4 v = lds128(lane_vec + jj < t.n_vec ? lbase + jj * 16 : data + (size_t)stage * kTileBytes);
+          acc = range_max<DT>(acc, vec_range<DT, SYM>(v));
+        }
+        __syncwarp();
+        if (lane == 0) {
+          if (pending >= 0 && aged) {  // the apply item's store was issued a whole tile ago: it has read its stage by now
+            tma_store_wait_read<0>();
+            mbar_arrive(&empty[pending]);
+          }
+          mbar_arrive(&empty[stage]);
+        }
+        if (pending >= 0 && aged) pending = -1;
+        aged = pending >= 0;
+      } else {
+        if (t.n_vec == (uint32_t)(kTileBytes / 16) && t.codes == nullptr)
+          seg4_consume<DT, KIND, SYM, true, true>(t, p, s_tbl, lbase, lane_vec, rot, lane, 1, warp, nullptr);
+        else
+          seg4_consume<DT, KIND, SYM, true, false>(t, p, s_tbl, lbase, lane_vec, rot, lane, 1, warp, nullptr);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t w0 = (uint32_t)warp * 128u;
+          if (w0 < t.n_vec) {
+            const uint32_t nv = t.n_vec - w0 < 128u ? t.n_vec - w0 : 128u;
+            tma_store_1d(t.dst + (size_t)w0 * 16, data + (size_t)stage * kTileBytes + (size_t)w0 * 16, nv * 16u);
+          }
+          tma_store_commit();
+          tma_store_wait_read<1>();
+          if (pending >= 0) mbar_arrive(&empty[pending]);
+        }
+        pending = stage;
+        aged = false;
+      }
+      if (++stage == n_stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+    if (is_range) {
+      if (acc_job >= 0) flush(acc_job);
+      // arrival of this warp for batch b: a release-ordered fire-and-forget add (the warp does not wait for it);
+      // the batch's publisher CTA watches the counter reach gridDim.x * 8
+      if (lane == 0) red_release_gpu_add(&f.arrive[b], 1u);
+    }
+  }
+  if (lane == 0) tma_store_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------

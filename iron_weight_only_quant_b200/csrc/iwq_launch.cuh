@@ -71,7 +71,28 @@ cudaError_t launch_col(const LaunchParams& p, bool sym, const LaunchTuning& tune
 template <int DT>
 cudaError_t launch_col_double(const LaunchParams& p, cudaStream_t st);
 
+template <int DT, int KIND>
+cudaError_t launch_fused(const LaunchParams& p, const FusedParams& f, bool sym, const LaunchTuning& tune, cudaStream_t st, int* grid_out);
+
 #ifdef IWQ_INSTANTIATE
+
+// the fused per-tensor kernel: the grid size is also the arrival-counter target, so it is returned to the caller
+// (who sized the work list for it); `*grid_out` > 0 on entry means "launch with exactly this grid"
+template <int DT, int KIND, bool SYM>
+static cudaError_t launch_fused_one(LaunchParams p, const FusedParams& f, const LaunchTuning& tune, cudaStream_t st, int* grid_out) {
+  auto k = pertensor_fused_kernel<DT, KIND, SYM>;
+  const size_t smem = kSmemHeader + p.lut_smem_bytes + (size_t)p.n_stages * kTileBytes + (size_t)(kFusedRing + 16) * kFusedMaxBatchJobs * sizeof(float2) + 2 * ((size_t)f.n_batches + 1) * 4;
+  int grid = 0;
+  cudaError_t e = persistent_grid(k, kConsumers + 32, smem, tune.ctas_per_sm, 0xFFFFFFFFu, &grid);
+  if (e != cudaSuccess) return e;
+  *grid_out = grid;
+  k<<<grid, kConsumers + 32, smem, st>>>(p, f);
+  return cudaGetLastError();
+}
+template <int DT, int KIND>
+cudaError_t launch_fused(const LaunchParams& p, const FusedParams& f, bool sym, const LaunchTuning& tune, cudaStream_t st, int* grid_out) {
+  return sym ? launch_fused_one<DT, KIND, true>(p, f, tune, st, grid_out) : launch_fused_one<DT, KIND, false>(p, f, tune, st, grid_out);
+}
 
 template <int DT>
 cudaError_t launch_col_double(const LaunchParams& p, cudaStream_t st) {
@@ -181,7 +202,8 @@ cudaError_t launch_row(const LaunchParams& p, bool sym, int consumers, const Lau
 #define IWQ_INSTANTIATE_KIND(DT, KIND)                                                                                       \
   template cudaError_t launch_seg<DT, KIND>(const LaunchParams&, bool, bool, int, const LaunchTuning&, cudaStream_t);       \
   template cudaError_t launch_row<DT, KIND>(const LaunchParams&, bool, int, const LaunchTuning&, cudaStream_t);   \
-  template cudaError_t launch_col<DT, KIND>(const LaunchParams&, bool, const LaunchTuning&, cudaStream_t);
+  template cudaError_t launch_col<DT, KIND>(const LaunchParams&, bool, const LaunchTuning&, cudaStream_t);            \
+  template cudaError_t launch_fused<DT, KIND>(const LaunchParams&, const FusedParams&, bool, const LaunchTuning&, cudaStream_t, int*);
 
 #endif  // IWQ_INSTANTIATE
 

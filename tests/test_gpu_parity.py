@@ -263,6 +263,32 @@ def test_packed_w4_codes_vs_oracle(dt):
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_per_tensor_fused_single_launch_vs_oracle(dt):
+    """iwq_fake_quant_per_tensor_fused on one GPU (world 1): several matrices of mixed sizes (ragged tiles, more
+    matrices than batches and batches than matrices), asym and sym, bit-exact vs the unfused oracle."""
+    shapes_ = [(64, 1024), (3, 200), (700, 512), (1, 8), (2048, 4096), (129, 264), (4096, 4096), (5, 40)]
+    ws = [seeded(r, c, dt, 300 + i) for i, (r, c) in enumerate(shapes_)]
+    for nb, sym in [(4, False), (8, True), (3, False)]:
+        ds = [w.to(DEV) for w in ws]
+        outs = sharded.pseudo_quantize_tensors_per_tensor_fused(ds, n_bits=nb, zero_point=not sym)
+        assert _lib.read_and_clear_status(torch.device(DEV)) == 0
+        for w, o in zip(ws, outs):
+            ref = O.int_fake_quant(bits(w), dt, nb, not sym, -1)
+            assert_bits(bits(o), ref["out"], dt, f"{dt} fused per-tensor b{nb} sym={sym} {tuple(w.shape)}")
+    # scales / zero points of the module form
+    ds = [w.to(DEV) for w in ws]
+    sc = [torch.zeros(1, dtype=TDT[dt], device=DEV) for _ in ws]
+    zs = [torch.zeros(1, dtype=TDT[dt], device=DEV) for _ in ws]
+    cfg = _lib.make_config(TDT[dt], _lib.SCHEME_INT, -1, bits=4, symmetric=False)
+    mats = [_lib.matrix_desc(d, d, d.shape[0], d.shape[1], s_, z_) for d, s_, z_ in zip(ds, sc, zs)]
+    _lib.per_tensor_fused_(mats, cfg, torch.device(DEV))
+    for w, s_, z_ in zip(ws, sc, zs):
+        ref = O.int_fake_quant(bits(w), dt, 4, True, -1)
+        assert_bits(bits(s_), ref["scales"], dt, "fused scales")
+        assert np.array_equal(O.from_bits(bits(z_), dt), O.from_bits(ref["zeros"], dt)), "fused zeros"
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
 def test_per_channel_row_kernel_vs_oracle(dt):
     """per-channel goes through row_tma_kernel for every row length that is not a power of two <= 1024."""
     # 2048 / 4096-element rows take seg4_tma_kernel with 2 / 4 warps per segment (ragged last tiles included)

@@ -52,7 +52,23 @@ def main():
     r0 = shapes.split_rows(mats[0][0], world, rank)
     ok = bool(np.array_equal(o0.cpu().view(torch.int16).numpy().view(np.uint16), ref[r0.start : r0.stop])) or bool(os.environ.get("IWQ_FAKE_WORLD"))
 
+    fused = bool(os.environ.get("IWQ_C4_FUSED"))
+
     def step(ev=None):
+        if fused:  # one launch: range pass, in-kernel NVLink exchange, apply pass from L2
+            if ev:
+                ev[0].record()
+                ev[1].record()
+            peers = None
+            if world > 1:
+                import ctypes
+
+                st = sharded._peer_buffers(dev, None, len(descs))
+                st["epoch"] += 1
+                peers = _lib.Peers(world=st["world"], rank=st["rank"], slot_ptrs=ctypes.cast(st["slot_ptrs"], ctypes.POINTER(ctypes.c_void_p)),
+                                   flag_ptrs=ctypes.cast(st["flag_ptrs"], ctypes.POINTER(ctypes.c_void_p)), epoch=st["epoch"], spin_limit=0)
+            _lib.per_tensor_fused_(descs, cfg, dev, peers, track_status=False)
+            return
         _lib.minmax_(descs, cfg, dev, rng)
         if ev:
             ev[0].record()
@@ -83,7 +99,7 @@ def main():
     if rank == 0:
         ms = t[3].item()
         n_total = sum(o * k for o, k in mats)
-        print(json.dumps({"config": "opt-6.7b per-tensor w4 asym, every matrix row-split across ranks", "n_gpus": world, "weights": n_total, "ms_total": ms, "ms_range_pass": t[0].item(), "ms_allreduce": t[1].item(), "ms_apply_pass": t[2].item(), "alg_GBps_aggregate": n_total * 4 / ms / 1e6, "traffic_GBps_per_gpu": n_local * 6 / ms / 1e6, "bit_exact_vs_unsharded_oracle": t[4].item() == 0.0}))
+        print(json.dumps({"config": "opt-6.7b per-tensor w4 asym, every matrix row-split across ranks" + (" (FUSED single launch)" if fused else ""), "n_gpus": world, "weights": n_total, "ms_total": ms, "ms_range_pass": t[0].item(), "ms_allreduce": t[1].item(), "ms_apply_pass": t[2].item(), "alg_GBps_aggregate": n_total * 4 / ms / 1e6, "traffic_GBps_per_gpu": n_local * 6 / ms / 1e6, "bit_exact_vs_unsharded_oracle": t[4].item() == 0.0}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -43,6 +43,7 @@ CONFIGS = {
     "fp4e2m1g128_d1_double": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=2, mant_bits=1, symmetric=True, quant_dim=1, approx=2, hi_align_start=0, hi_align_exp_field=2, tail_pad_bits=1),
     "int4pc_sym": dict(scheme=_lib.SCHEME_INT, group=-2, bits=4, symmetric=True),
     "int4pt_sym": dict(scheme=_lib.SCHEME_INT, group=-1, bits=4, symmetric=True),
+    "int4pt_fused": dict(scheme=_lib.SCHEME_INT, group=-1, bits=4, symmetric=False, fused=True),
 }
 
 
@@ -96,7 +97,11 @@ def main():
             z = None if (args.no_emit or c["symmetric"]) else torch.empty(G, dtype=dt, device=dev)
             keep.append((s, z))
             descs.append(_lib.matrix_desc(w, w, o, k, s, z))
-        if c["group"] == -1:
+        if c["group"] == -1 and c.get("fused"):
+
+            def fn():
+                _lib.per_tensor_fused_(descs, cfg, dev, None, track_status=False)
+        elif c["group"] == -1:
             rng = torch.empty(2 * len(descs), dtype=torch.float32, device=dev)
 
             def fn():
