@@ -47,6 +47,7 @@ struct Knobs {
   int col_ctas = env_int("IWQ_COL_CTAS", 0);
   int fused_batch_mb = env_int("IWQ_FUSED_BATCH_MB", 16);  // pertensor_fused_kernel: bytes of weights per batch
   int fused_lookahead = env_int("IWQ_FUSED_LOOKAHEAD", 2); // ... and how many batches the range pass runs ahead
+  int row_tma_out = env_int("IWQ_ROW_TMA_OUT", 1);   // row kernel: bulk stores instead of STG.128 when the ring has >= 3 stages
   int wide_seg4 = env_int("IWQ_WIDE_SEG4", 1);       // 1: segments of 2048/4096/8192 elements go through seg4_tma_kernel
   int col_mode = env_int("IWQ_COL_MODE", 0);         // 0: warp-private cp.async ring (col_async_kernel), 1: register-resident
   int col_stages = env_int("IWQ_COL_STAGES", 0);     // ring depth of col_async_kernel (1..4); 0 = automatic
@@ -274,6 +275,8 @@ static int make_plan(const iwq_config_t* cfg, int64_t cols, uint32_t lut_bytes, 
   if (budget > max_ring) budget = max_ring;
   int st = (int)(budget / stage);
   if (st < 2) st = 2;
+  // three stages let the row kernel send its results through bulk stores (one stage stays parked behind its store)
+  if (st == 2 && knobs().row_tma_out != 0 && stage >= 20 * 1024 && 3ull * stage <= 110 * 1024 && 3ull * stage <= max_ring) st = 3;
   if (st > 4 && knobs().row_smem_kb <= 0) st = 4;
   if (st > kMaxStages) st = kMaxStages;
   pl->stages = st;
@@ -324,6 +327,8 @@ static int fill_params(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, c
   if (st < 2) st = 2;
   if (st > kMaxStages) st = kMaxStages;
   p->n_stages = pl.path == PATH_SEG ? st : pl.stages;
+  // measured (profiles/README.md): bulk stores pay off for long rows (22 KB: +3.4 %, 32 KB: +2 %), not for 10..16 KB ones
+  p->row_tma_out = (pl.path == PATH_ROW && pl.stages >= 3 && knobs().row_tma_out != 0 && (knobs().row_tma_out > 1 || pl.seg_elems * 2ull >= 20 * 1024)) ? 1u : 0u;
   return IWQ_OK;
 }
 
@@ -403,6 +408,7 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
   rc = upload_jobs(jobs, workspace, ws_bytes, &p, st);
   if (rc) return rc;
   p.status = status;
+  if (kind == KIND_FP && knobs().row_tma_out < 2) p.row_tma_out = 0;  // the minifloat rows measured 5 % slower with bulk stores
   const bool sym = p.qc.symmetric != 0;
   const bool per_tensor = cfg->group == IWQ_GROUP_PER_TENSOR;
   LaunchTuning tune;

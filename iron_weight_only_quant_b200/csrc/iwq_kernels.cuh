@@ -65,6 +65,7 @@ struct LaunchParams {
   const FpStep* lut;       // KIND_FP: device step table (qc.lut_n entries), copied into shared memory by every CTA
   uint32_t lut_smem_bytes; // bytes reserved for it in front of the ring (multiple of 1024; 0 for INT kinds)
   uint32_t lut_extra_bytes;// double-approximate decode: value table behind the step table (device: lut + lut_smem_bytes)
+  uint32_t row_tma_out;    // row kernel: results go back into the stage and leave through one bulk store per warp
   uint32_t col_group;      // quant_dim = 1: rows per segment (0: the whole column, i.e. per-channel)
   uint32_t col_tile;       // col_reg_kernel: columns per tile (64 / 128 / 256), 0 = col_kernel
   uint32_t col_rpl;        // col_reg_kernel: vectors (rows) per lane = col_group * (col_tile / 64) / 32
@@ -797,13 +798,14 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
       }
     }
   } else {
-    int stage = 0;
+    int stage = 0, prev_stage = -1;  // prev_stage: stage whose bulk store may still be reading shared memory (TMA-out form)
     uint32_t phase = 0, par = 0;
     const int tid = threadIdx.x;
+    const bool tma_out = p.row_tma_out != 0;
     for (uint32_t row = blockIdx.x; row < p.total_units; row += gridDim.x) {
       mbar_wait(&full[stage], phase);
       const RowCtx t = ctx[stage];
-      const uint8_t* sdata = data + (size_t)stage * p.stage_bytes;
+      uint8_t* sdata = data + (size_t)stage * p.stage_bytes;
       // sweep 1: range of the row
       uint32_t pk = SYM ? 0u : 0xFC00FC00u;  // {0,0} for absmax; {-inf,-inf} otherwise (bf16: see below)
       if (!SYM && DT == IWQ_BF16) pk = 0xFF80FF80u;
@@ -821,7 +823,27 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
       const bool want_codes = t.codes != nullptr;
       Prepared<DT, KIND> prep;
       prep.setup(mx, mn, p.qc, SYM, s_tbl);
-      if (!want_codes && !prep.slow()) {
+      bool stored_by_tma = false;
+      if (tma_out && !want_codes && !prep.slow()) {
+        // hot path, TMA-out form (ring of >= 3 stages): each warp quantises a contiguous slice of the row in place in
+        // the stage and one lane sends it off with a single bulk store -- no per-vector global stores or addresses;
+        // the stage is handed back once the PREVIOUS row's store has finished reading shared memory (as in seg4)
+        const uint32_t slice = (t.n_vec + (uint32_t)n_cwarps * 32u - 1u) / ((uint32_t)n_cwarps * 32u) * 32u;
+        const uint32_t v0 = (uint32_t)warp * slice, v1 = v0 + slice < t.n_vec ? v0 + slice : t.n_vec;
+        for (uint32_t i = v0 + (uint32_t)lane; i < v1; i += 32u) {
+          uint2 codes8;
+          sts128(sdata + (size_t)i * 16, prep.template apply<SYM, 0>(lds128(sdata + (size_t)i * 16), p.qc, s_tbl, false, &codes8));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (v0 < v1) tma_store_1d(t.dst + (size_t)v0 * 16, sdata + (size_t)v0 * 16, (v1 - v0) * 16u);
+          tma_store_commit();
+          tma_store_wait_read<1>();
+          if (prev_stage >= 0) mbar_arrive(&empty[prev_stage]);
+        }
+        stored_by_tma = true;
+      } else if (!want_codes && !prep.slow()) {
         // hot path: the degenerate-scale (IEEE division) variant is selected once per row, not once per pair
         for (uint32_t i = tid; i < t.n_vec; i += n_cons) {
           uint2 codes8;
@@ -841,12 +863,24 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
         if (prep.bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (stored_by_tma) {
+        prev_stage = stage;
+      } else {
+        if (lane == 0) {
+          if (prev_stage >= 0) {  // a rare register-store row after TMA-out rows: settle the parked stage first
+            tma_store_wait_read<0>();
+            mbar_arrive(&empty[prev_stage]);
+          }
+          mbar_arrive(&empty[stage]);
+        }
+        prev_stage = -1;
+      }
       if (++stage == n_stages) {
         stage = 0;
         phase ^= 1u;
       }
     }
+    if (tma_out && lane == 0) tma_store_wait_all();
   }
 }
 
