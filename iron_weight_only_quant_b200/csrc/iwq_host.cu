@@ -710,6 +710,7 @@ int iwq_fake_quant_per_tensor_fused(const iwq_config_t* cfg, const iwq_matrix_t*
   f.rank = rank;
   f.spin_limit = (peers && peers->spin_limit) ? peers->spin_limit : 2000000u;
   f.poll_ns = (uint32_t)env_int("IWQ_FUSED_POLL_NS", 200);
+  f.debug = (uint32_t)env_int("IWQ_FUSED_DEBUG", 0);
   f.lookahead = knobs().fused_lookahead > 0 ? (knobs().fused_lookahead < kFusedRing ? knobs().fused_lookahead : kFusedRing - 1) : 2;
   LaunchTuning tune;
   tune.stages = p.n_stages;

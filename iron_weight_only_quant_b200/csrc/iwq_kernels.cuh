@@ -1685,6 +1685,7 @@ struct FusedParams {
   uint32_t spin_limit;           // bounded wait: afterwards IWQ_STATUS_TIMEOUT is raised instead of hanging
   int32_t lookahead;             // batches the range pass runs ahead of the apply pass (>= 1)
   uint32_t poll_ns;              // sleep of the exchange lanes between polls
+  uint32_t debug;                // diagnostics only (IWQ_FUSED_DEBUG): 2 = no apply tiles, 3 = no range tiles (results are then wrong)
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
@@ -1900,7 +1901,7 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) pertensor_fused_kernel(con
           __threadfence_block();
         }
         const uint32_t j0 = s_bj[b];
-        const uint32_t t1 = s_bt[b + 1];
+        const uint32_t t1 = ((f.debug & 7u) == (is_range ? 3u : 2u)) ? 0u : s_bt[b + 1];
         for (uint32_t tile = fused_first_tile(s_bt[b]); tile < t1; tile += gridDim.x) {
           if (is_range) seek(cr, tile); else seek(ca, tile);
           const int cur = is_range ? cr.cur : ca.cur;
@@ -1917,7 +1918,8 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) pertensor_fused_kernel(con
           const uint32_t bytes = t.n_vec * 16u;
           mbar_arrive_expect_tx(&full[stage], bytes);
           // range tiles come back within a few batches: keep them in L2; apply tiles are never read again
-          tma_load_1d_hint(data + (size_t)stage * kTileBytes, jb.src + (t.vec0 << 4), bytes, &full[stage], is_range ? pol_keep : pol_drop);
+          if (f.debug & 8u) tma_load_1d_hint(data + (size_t)stage * kTileBytes, jb.src + (t.vec0 << 4), bytes, &full[stage], is_range ? pol_keep : pol_drop);
+          else tma_load_1d(data + (size_t)stage * kTileBytes, jb.src + (t.vec0 << 4), bytes, &full[stage]);
           if (++stage == n_stages) {
             stage = 0;
             phase ^= 1u;
@@ -1938,7 +1940,7 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) pertensor_fused_kernel(con
   while (next_a < nb) {
     int b;
     const bool is_range = next_item(&b);
-    const uint32_t t1 = s_bt[b + 1];
+    const uint32_t t1 = ((f.debug & 7u) == (is_range ? 3u : 2u)) ? 0u : s_bt[b + 1];
     uint32_t acc = ident;
     int acc_job = -1;
     auto flush = [&](int job) {
