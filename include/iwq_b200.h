@@ -141,6 +141,7 @@ typedef struct iwq_peers {
   uint32_t spin_limit;    /* 0 = default (about one second) */
 } iwq_peers_t;
 size_t iwq_fused_workspace_bytes(int n);
+long long iwq_debug_fused_trace(int* n_batches); /* diagnostics: see iwq_host.cu */
 int iwq_fake_quant_per_tensor_fused(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, void* workspace, size_t workspace_bytes,
                                     const iwq_peers_t* peers, int32_t* status, void* stream);
 

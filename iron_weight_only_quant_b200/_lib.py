@@ -37,6 +37,7 @@ EXPORTS = (
     "iwq_fake_quant_host",
     "iwq_fake_quant_host_batched",
     "iwq_fused_workspace_bytes",
+    "iwq_debug_fused_trace",
     "iwq_fake_quant_per_tensor_fused",
 )
 

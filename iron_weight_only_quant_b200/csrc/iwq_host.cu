@@ -610,10 +610,19 @@ int iwq_fake_quant_with_range(const iwq_config_t* cfg, const iwq_matrix_t* ms, i
   return run_batched(cfg, ms, n, workspace, workspace_bytes, range, nullptr, status, (cudaStream_t)stream, false);
 }
 
+static long long g_fused_trace_off = -1;
+static int g_fused_trace_nb = 0;
+// diagnostics (IWQ_FUSED_TRACE=1): offset of the [n_batches][4] uint64 globaltimer stamps inside the workspace of the
+// last fused call, or -1; *n_batches receives the batch count
+long long iwq_debug_fused_trace(int* n_batches) {
+  if (n_batches) *n_batches = g_fused_trace_nb;
+  return g_fused_trace_off;
+}
+
 size_t iwq_fused_workspace_bytes(int n) {
   const size_t m = (size_t)(n < 1 ? 1 : n);
   // jobs | batch_tile0 | batch_job0 | arrive | local_range | local slots [2][1][2n] | local flags | 2 x 16 peer pointers
-  return m * sizeof(Job) + 2 * (m + 1) * 4 + m * 4 + 2 * m * 4 + 4 * m * 4 + m * 4 + 2 * 16 * 8 + 256;
+  return m * sizeof(Job) + 2 * (m + 1) * 4 + m * 4 + 2 * m * 4 + 4 * m * 4 + m * 4 + 2 * 16 * 8 + 256 + m * 32;
 }
 
 int iwq_fake_quant_per_tensor_fused(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, void* workspace, size_t workspace_bytes,
@@ -673,6 +682,10 @@ int iwq_fake_quant_per_tensor_fused(const iwq_config_t* cfg, const iwq_matrix_t*
   auto take = [&](size_t bytes, size_t align) { off = (off + align - 1) / align * align; size_t o = off; off += bytes; return o; };
   const size_t o_jobs = take(m * sizeof(Job), 16), o_bt = take((m + 1) * 4, 4), o_bj = take((m + 1) * 4, 4), o_arr = take(m * 4, 4);
   const size_t o_rng = take(2 * m * 4, 4), o_slots = take(4 * m * 4, 16), o_flags = take(m * 4, 4), o_sp = take(16 * 8, 8), o_fp = take(16 * 8, 8);
+  const bool want_trace = env_int("IWQ_FUSED_TRACE", 0) != 0;
+  const size_t o_trace = want_trace ? take((size_t)nb * 4 * 8, 8) : 0;
+  g_fused_trace_off = want_trace ? (long long)o_trace : -1;
+  g_fused_trace_nb = nb;
   if (off > workspace_bytes) return fail(IWQ_ERR_INVALID, "workspace too small (see iwq_fused_workspace_bytes)");
   std::vector<uint8_t> blob(off, 0);
   memcpy(blob.data() + o_jobs, jobs.data(), m * sizeof(Job));
@@ -709,6 +722,7 @@ int iwq_fake_quant_per_tensor_fused(const iwq_config_t* cfg, const iwq_matrix_t*
   f.world = world;
   f.rank = rank;
   f.spin_limit = (peers && peers->spin_limit) ? peers->spin_limit : 2000000u;
+  f.trace = want_trace ? (unsigned long long*)(ws + o_trace) : nullptr;
   f.poll_ns = (uint32_t)env_int("IWQ_FUSED_POLL_NS", 200);
   f.debug = (uint32_t)env_int("IWQ_FUSED_DEBUG", 0);
   f.lookahead = knobs().fused_lookahead > 0 ? (knobs().fused_lookahead < kFusedRing ? knobs().fused_lookahead : kFusedRing - 1) : 2;

@@ -1595,6 +1595,14 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   }
 }
 
+// returning form: the value comes back only after the atomic has been performed at L2, so an instruction that
+// depends on it is ordered after it without a fence
+__device__ __forceinline__ uint32_t atomic_max_float_ret(float* addr, float v) {
+  if (v != v) return (uint32_t)atomicMax(reinterpret_cast<int*>(addr), 0x7FFFFFFF);
+  if (v >= 0.0f) return (uint32_t)atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  return atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
 static __global__ void range_init_kernel(float* ranges, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) ranges[i] = -INFINITY;
@@ -1686,6 +1694,7 @@ struct FusedParams {
   int32_t lookahead;             // batches the range pass runs ahead of the apply pass (>= 1)
   uint32_t poll_ns;              // sleep of the exchange lanes between polls
   uint32_t debug;                // diagnostics only (IWQ_FUSED_DEBUG): 2 = no apply tiles, 3 = no range tiles (results are then wrong)
+  unsigned long long* trace;     // diagnostics only: [n_batches][4] globaltimer stamps written by CTA 0 (nullptr: off)
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
@@ -1700,6 +1709,11 @@ __device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
   float v;
   asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ float max_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
 
@@ -1745,6 +1759,7 @@ template <bool SYM>
 __device__ __forceinline__ void fused_exchange_step(const LaunchParams& p, const FusedParams& f, FusedExchange& x, float2* s_rng, float2* s_tmp,
                                                     const uint32_t* s_bj, int lane) {
   const int nb = f.n_batches, xl = lane - 1;  // xl: 0..30
+  if (f.world == 1) x.pub_b = nb;  // nothing to publish on a single GPU
   if (x.pub_b < nb) {
     uint32_t cnt = 0;
     if (xl == 0) cnt = ld_acquire_gpu_u32(&f.arrive[x.pub_b]);
@@ -1762,6 +1777,20 @@ __device__ __forceinline__ void fused_exchange_step(const LaunchParams& p, const
       if (xl < f.world) st_release_sys_u32(&f.peer_flags[xl][(size_t)f.rank * nb + x.pub_b], f.epoch);
       x.pub_b += (int)gridDim.x;
     }
+  }
+  if (x.gather_b < nb && f.world == 1) {
+    // single GPU: no slots, no flags -- the batch is ready when its arrival counter is complete
+    uint32_t cnt = 0;
+    if (xl == 0) cnt = ld_acquire_gpu_u32(&f.arrive[x.gather_b]);
+    cnt = __shfl_sync(kXchgMask, cnt, 1);
+    if (cnt == gridDim.x * (uint32_t)kConsumerWarps) {
+      const uint32_t j0 = s_bj[x.gather_b], j1 = s_bj[x.gather_b + 1];
+      for (uint32_t j = j0 + (uint32_t)xl; j < j1; j += 31u)
+        s_rng[(x.gather_b % kFusedRing) * kFusedMaxBatchJobs + (j - j0)] = make_float2(__ldcg(&f.local_range[2 * j]), SYM ? 0.f : -__ldcg(&f.local_range[2 * j + 1]));
+      __syncwarp(kXchgMask);
+      ++x.gather_b;
+    }
+    return;
   }
   if (x.gather_b < nb) {
     const uint32_t* my_flags = f.peer_flags[f.rank];
@@ -1858,6 +1887,7 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) pertensor_fused_kernel(con
         if (x.gather_b != before) {
           __threadfence_block();
           if (lane == 1) *s_gathered = (uint32_t)x.gather_b;
+          if (f.trace && blockIdx.x == 0 && lane == 1) f.trace[4 * before + 1] = globaltimer_ns();
         } else {
           __nanosleep(f.poll_ns);
         }
@@ -1899,6 +1929,7 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) pertensor_fused_kernel(con
         if (!is_range) {
           while (*s_gathered <= (uint32_t)b) __nanosleep(64);  // the batch's ranges from every rank (exchange lanes)
           __threadfence_block();
+          if (f.trace && blockIdx.x == 0) f.trace[4 * b + 2] = globaltimer_ns();
         }
         const uint32_t j0 = s_bj[b];
         const uint32_t t1 = ((f.debug & 7u) == (is_range ? 3u : 2u)) ? 0u : s_bt[b + 1];
@@ -1941,7 +1972,7 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) pertensor_fused_kernel(con
     int b;
     const bool is_range = next_item(&b);
     const uint32_t t1 = ((f.debug & 7u) == (is_range ? 3u : 2u)) ? 0u : s_bt[b + 1];
-    uint32_t acc = ident;
+    uint32_t acc = ident, tok = 0;  // tok: depends on every atomic of this item having returned
     int acc_job = -1;
     auto flush = [&](int job) {
 #pragma unroll
@@ -1949,8 +1980,8 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) pertensor_fused_kernel(con
       if (lane == 0) {
         float mx, mn;
         range_unpack<DT>(acc, &mx, &mn);
-        atomic_max_float(&f.local_range[2 * job], mx);
-        if (!SYM) atomic_max_float(&f.local_range[2 * job + 1], -mn);
+        tok ^= atomic_max_float_ret(&f.local_range[2 * job], mx);
+        if (!SYM) tok ^= atomic_max_float_ret(&f.local_range[2 * job + 1], -mn);
       }
       acc = ident;
     };
@@ -2006,11 +2037,20 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) pertensor_fused_kernel(con
         phase ^= 1u;
       }
     }
+    if (!is_range && f.trace && blockIdx.x == 0 && warp == 0 && lane == 0) f.trace[4 * b + 3] = globaltimer_ns();
     if (is_range) {
       if (acc_job >= 0) flush(acc_job);
       // arrival of this warp for batch b: a release-ordered fire-and-forget add (the warp does not wait for it);
       // the batch's publisher CTA watches the counter reach gridDim.x * 8
-      if (lane == 0) red_release_gpu_add(&f.arrive[b], 1u);
+      // (no fence: the increment is computed from the atomics' return values, so it issues only after all of them have
+      //  been performed at L2, the point of coherence the publisher reads from -- a ~1 us round trip instead of the
+      //  ~4 us MEMBAR/ERRBAR a release costs this warp while its bulk stores are in flight)
+      if (lane == 0) {
+        uint32_t one;
+        asm volatile("{ .reg .b32 t; and.b32 t, %1, 0; add.u32 %0, t, 1; }" : "=r"(one) : "r"(tok));
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(&f.arrive[b]), "r"(one) : "memory");
+        if (f.trace && blockIdx.x == 0 && warp == 0) f.trace[4 * b + 0] = globaltimer_ns();
+      }
     }
   }
   if (lane == 0) tma_store_wait_all();
