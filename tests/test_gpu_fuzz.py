@@ -177,3 +177,50 @@ def test_no_out_of_bounds_writes(dt):
         assert _canaries_intact(a_c, n), tag + ": codes canary"
         if not emits_z:
             assert bool((p_z == 0xA5).all().item()), tag + ": zeros written although not requested"
+
+
+ALT_WORKER = r'''
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.environ["IWQ_ROOT"])
+from iron_weight_only_quant_b200 import _lib
+from oracle import fakequant_oracle as O
+DEV = "cuda:0"
+def bits(t): return t.detach().contiguous().cpu().view(torch.int16).numpy().view(np.uint16).copy()
+bad = []
+cases = [  # rows, cols, group, quant_dim, bits, sym
+    (256, 520, 128, 1, 4, False), (512, 264, 64, 1, 4, True), (1024, 136, 256, 1, 3, False), (64, 72, 32, 1, 4, False),
+    (9, 4096, -2, 0, 4, False), (5, 8192, -2, 0, 8, True), (7, 2048, -2, 0, 4, False), (33, 11008, -2, 0, 4, False), (6, 5120, -2, 0, 4, True),
+    (3, 8192, 4096, 0, 4, False), (64, 1024, 128, 0, 4, False),
+]
+for rows, cols, grp, qd, nb, sym in cases:
+    g = torch.Generator().manual_seed(rows * 3 + cols)
+    w = (torch.randn(rows, cols, generator=g) * 0.02).half()
+    ref = O.along_output_dim(O.int_fake_quant, bits(w), "f16", nb, not sym, grp) if qd else O.int_fake_quant(bits(w), "f16", nb, not sym, grp)
+    wd = w.to(DEV)
+    G = _lib.num_segments(rows, cols, grp, qd)
+    sc = torch.zeros(G, dtype=torch.float16, device=DEV)
+    cfg = _lib.make_config(torch.float16, _lib.SCHEME_INT, grp, bits=nb, symmetric=sym, quant_dim=qd)
+    _lib.fake_quant_(wd, wd, cfg, rows, cols, scales=sc, track_status=False)
+    if not (np.array_equal(bits(wd), ref["out"]) and np.array_equal(bits(sc), ref["scales"])):
+        bad.append((rows, cols, grp, qd, nb, sym))
+print("ALT_OK" if not bad else f"ALT_MISMATCH {bad}")
+'''
+
+
+@pytest.mark.parametrize("knobs", ["IWQ_COL_MODE=1", "IWQ_COL_TILE=-1", "IWQ_COL_STAGES=2", "IWQ_WIDE_SEG4=0", "IWQ_WIDE_SEG4=2", "IWQ_ROW_TMA_OUT=0", "IWQ_ROW_TMA_OUT=2", "IWQ_VARIANT=2", "IWQ_SEG_STAGES=4"])
+def test_alternate_kernel_variants_match_oracle(knobs, tmp_path):
+    """The tuning knobs select other kernels / tile shapes (register-resident and two-sweep column kernels, row kernel
+    with and without bulk stores, multi-warp segments on or off ...); they are read once per process, so each setting
+    runs in a subprocess.  Every variant must be bit-exact like the default."""
+    import os
+    import subprocess
+    import sys
+
+    script = tmp_path / "alt_worker.py"
+    script.write_text(ALT_WORKER)
+    env = dict(os.environ, IWQ_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    for kv in knobs.split():
+        k, v = kv.split("=")
+        env[k] = v
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300, env=env)
+    assert "ALT_OK" in out.stdout, knobs + ": " + out.stdout[-1500:] + out.stderr[-1500:]
