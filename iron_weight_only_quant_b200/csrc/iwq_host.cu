@@ -622,7 +622,7 @@ long long iwq_debug_fused_trace(int* n_batches) {
 size_t iwq_fused_workspace_bytes(int n) {
   const size_t m = (size_t)(n < 1 ? 1 : n);
   // jobs | batch_tile0 | batch_job0 | arrive | local_range | local slots [2][1][2n] | local flags | 2 x 16 peer pointers
-  return m * sizeof(Job) + 2 * (m + 1) * 4 + m * 4 + 2 * m * 4 + 4 * m * 4 + m * 4 + 2 * 16 * 8 + 256 + m * 32;
+  return m * sizeof(Job) + 2 * (m + 1) * 4 + m * 4 + 2 * m * 4 + 4 * m * 4 + m * 4 + 2 * 16 * 8 + 256 + m * 32 + 2 * m * 4;
 }
 
 int iwq_fake_quant_per_tensor_fused(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, void* workspace, size_t workspace_bytes,
@@ -682,6 +682,7 @@ int iwq_fake_quant_per_tensor_fused(const iwq_config_t* cfg, const iwq_matrix_t*
   auto take = [&](size_t bytes, size_t align) { off = (off + align - 1) / align * align; size_t o = off; off += bytes; return o; };
   const size_t o_jobs = take(m * sizeof(Job), 16), o_bt = take((m + 1) * 4, 4), o_bj = take((m + 1) * 4, 4), o_arr = take(m * 4, 4);
   const size_t o_rng = take(2 * m * 4, 4), o_slots = take(4 * m * 4, 16), o_flags = take(m * 4, 4), o_sp = take(16 * 8, 8), o_fp = take(16 * 8, 8);
+  const size_t o_ctr = take(2 * m * 4, 4);
   const bool want_trace = env_int("IWQ_FUSED_TRACE", 0) != 0;
   const size_t o_trace = want_trace ? take((size_t)nb * 4 * 8, 8) : 0;
   g_fused_trace_off = want_trace ? (long long)o_trace : -1;
@@ -722,6 +723,7 @@ int iwq_fake_quant_per_tensor_fused(const iwq_config_t* cfg, const iwq_matrix_t*
   f.world = world;
   f.rank = rank;
   f.spin_limit = (peers && peers->spin_limit) ? peers->spin_limit : 2000000u;
+  f.tile_ctr = (uint32_t*)(ws + o_ctr);
   f.trace = want_trace ? (unsigned long long*)(ws + o_trace) : nullptr;
   f.poll_ns = (uint32_t)env_int("IWQ_FUSED_POLL_NS", 200);
   f.debug = (uint32_t)env_int("IWQ_FUSED_DEBUG", 0);

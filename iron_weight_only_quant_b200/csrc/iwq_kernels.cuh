@@ -1695,6 +1695,7 @@ struct FusedParams {
   uint32_t poll_ns;              // sleep of the exchange lanes between polls
   uint32_t debug;                // diagnostics only (IWQ_FUSED_DEBUG): 2 = no apply tiles, 3 = no range tiles (results are then wrong)
   unsigned long long* trace;     // diagnostics only: [n_batches][4] globaltimer stamps written by CTA 0 (nullptr: off)
+  uint32_t* tile_ctr;            // [2][n_batches] work-stealing counters (range items, apply items), zero-initialised
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
@@ -1933,7 +1934,10 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) pertensor_fused_kernel(con
         }
         const uint32_t j0 = s_bj[b];
         const uint32_t t1 = ((f.debug & 7u) == (is_range ? 3u : 2u)) ? 0u : s_bt[b + 1];
-        for (uint32_t tile = fused_first_tile(s_bt[b]); tile < t1; tile += gridDim.x) {
+        // tiles of an item are CLAIMED from a per-batch counter, not assigned statically: with only 2..5 tiles per CTA
+        // and item a static split leaves the slowest CTA a whole tile behind, and every CTA waits for it per batch
+        uint32_t* ctr = &f.tile_ctr[(is_range ? 0 : nb) + b];
+        for (uint32_t tile = s_bt[b] + atomicAdd(ctr, 1u); tile < t1; tile = s_bt[b] + atomicAdd(ctr, 1u)) {
           if (is_range) seek(cr, tile); else seek(ca, tile);
           const int cur = is_range ? cr.cur : ca.cur;
           const Job& jb = is_range ? cr.jb : ca.jb;
@@ -1951,6 +1955,18 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) pertensor_fused_kernel(con
           // range tiles come back within a few batches: keep them in L2; apply tiles are never read again
           if (f.debug & 8u) tma_load_1d_hint(data + (size_t)stage * kTileBytes, jb.src + (t.vec0 << 4), bytes, &full[stage], is_range ? pol_keep : pol_drop);
           else tma_load_1d(data + (size_t)stage * kTileBytes, jb.src + (t.vec0 << 4), bytes, &full[stage]);
+          if (++stage == n_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        {  // end-of-item marker: the consumers cannot know how many tiles this CTA claimed
+          mbar_wait(&empty[stage], phase ^ 1u);
+          TileCtx t;
+          t.dst = nullptr; t.scales = nullptr; t.zeros = nullptr; t.codes = nullptr;
+          t.vec0 = 0; t.n_vec = 0; t.given_mx = 0.f; t.given_mn = 0.f; t.pad = 0xFFFFFFFFu;
+          ctx[stage] = t;
+          mbar_arrive(&full[stage]);
           if (++stage == n_stages) {
             stage = 0;
             phase ^= 1u;
@@ -1985,9 +2001,26 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) pertensor_fused_kernel(con
       }
       acc = ident;
     };
-    for (uint32_t tile = fused_first_tile(s_bt[b]); tile < t1; tile += gridDim.x) {
+    for (;;) {
       mbar_wait(&full[stage], phase);
       const TileCtx t = ctx[stage];
+      if (t.pad == 0xFFFFFFFFu) {  // end of the item: hand the marker's stage back and leave
+        __syncwarp();
+        if (lane == 0) {
+          if (pending >= 0 && aged) {  // (a marker ages the parked stage like a tile does: the ring must keep turning)
+            tma_store_wait_read<0>();
+            mbar_arrive(&empty[pending]);
+          }
+          mbar_arrive(&empty[stage]);
+        }
+        if (pending >= 0 && aged) pending = -1;
+        aged = pending >= 0;
+        if (++stage == n_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        break;
+      }
       uint8_t* lbase = data + (size_t)stage * kTileBytes + (size_t)lane_vec * 16;
       if (is_range) {
         const int job = (int)t.pad - 1;
