@@ -1663,23 +1663,27 @@ __global__ void __launch_bounds__(kConsumers) minmax_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
-// pertensor_fused_kernel: per-tensor granularity in ONE launch, also when every matrix is row-split across the
-// GPUs of a box (BASELINE config 4) -- range pass, range exchange and apply pass fused.
+// pertensor_fused_kernel (EXPERIMENTAL, opt-in: correct, but slower than the three-step path -- DESIGN.md section 4):
+// per-tensor granularity in ONE launch, also when every matrix is row-split across the GPUs of a box (BASELINE
+// config 4) -- range pass, range exchange and apply pass fused.
 //
-//   * the matrices are cut into BATCHES of whole matrices (~24 MB: a few batches fit the 126 MB L2);
-//   * range pass of batch b (the 8 consumer warps of every CTA, 128-bit loads, warp-level reduction, ordered
-//     atomics into this GPU's {max, -min} per matrix); the LAST CTA to finish a batch (arrival counter) publishes
-//     the batch's ranges: it stores them into slot [rank] of EVERY rank's exchange buffer through the peer-mapped
-//     (NVLink / NVSwitch) pointers, fences at system scope and raises flag [rank][b] on every rank -- no NCCL call,
-//     no second launch, a few microseconds per batch, overlapped with the other batches' work;
-//   * the producer lane waits until all ranks' flags for batch b are up (acquire, bounded spin), takes the
-//     maximum over the ranks' slots and streams the batch's tiles through the usual TMA ring; the consumers run
-//     the seg4 element stage with the given range.  The tiles were read by the range pass moments ago, so the
-//     apply pass reads them from L2: HBM sees 2 B/weight of reads + 2 B/weight of writes instead of 4 + 2;
-//   * software pipeline per CTA: range(0), range(1), then for every batch: apply(b), range(b + 2) -- the exchange
-//     latency of a batch hides behind the apply pass of the previous one.
+//   * the matrices are cut into BATCHES of whole matrices (16 MB by default: a few batches fit the 126 MB L2);
+//   * RANGE and APPLY tiles of a batch go through the same TMA ring.  A CTA claims the tiles of an item from a
+//     per-batch counter; an end-of-item marker travels through the ring.  Range tiles are read-only: the consumer
+//     warps reduce them from shared memory, add their partial {max, -min} to this GPU's per-matrix ranges with
+//     returning atomics and then count themselves in on the batch's arrival counter;
+//   * lanes 1..31 of the producer warp run the exchange: the CTA with blockIdx.x == b (mod gridDim.x) publishes batch
+//     b once its counter is complete -- it stores the ranges into slot [rank] of EVERY rank's exchange buffer through
+//     the peer-mapped (NVLink / NVSwitch) pointers, fences at system scope and raises flag [rank][b] on every rank:
+//     no NCCL call, no second launch; every CTA gathers the batches in order (all ranks' flags up -> maximum over
+//     the ranks' slots -> shared-memory ring);
+//   * lane 0 of the producer warp issues the TMA copies; before the apply tiles of batch b it waits for the batch's
+//     gathered ranges and stamps them into the tile contexts; the consumers run the seg4 element stage with the
+//     given range.  The tiles were read by the range item a few batches ago, so the apply item can find them in L2;
+//   * schedule per CTA: R(0) .. R(D-1), A(0), R(D), A(1), ... with look-ahead D, so that a batch's exchange latency
+//     hides behind D - 1 batches of work.
 // All CTAs must be co-resident (persistent grid sized by the occupancy API), as for any arrival-counter scheme.
-// world == 1 runs the same code with the local buffers as the only "peer".
+// world == 1 runs the same code with the local buffers as the only "peer" (and gathers straight from the counter).
 // ------------------------------------------------------------------------------------------------
 struct FusedParams {
   float* local_range;            // [2 * n_jobs] {max, -min}, initialised to -inf by the host
@@ -1725,14 +1729,6 @@ __device__ __forceinline__ float max_nan(float a, float b) { return (a != a) ? a
 constexpr int kFusedMaxBatchJobs = 16;  // matrices per batch (the host closes a batch earlier if need be)
 constexpr int kFusedRing = 8;           // batches whose reduced ranges may be parked in shared memory (lookahead < kFusedRing)
 
-__device__ __forceinline__ uint32_t fused_first_tile(uint32_t t0) {  // first tile >= t0 with tile % gridDim.x == blockIdx.x
-  return t0 + (blockIdx.x + gridDim.x - t0 % gridDim.x) % gridDim.x;
-}
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking
-  uint32_t ok;
-  asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
 __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -1987,7 +1983,6 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) pertensor_fused_kernel(con
   while (next_a < nb) {
     int b;
     const bool is_range = next_item(&b);
-    const uint32_t t1 = ((f.debug & 7u) == (is_range ? 3u : 2u)) ? 0u : s_bt[b + 1];
     uint32_t acc = ident, tok = 0;  // tok: depends on every atomic of this item having returned
     int acc_job = -1;
     auto flush = [&](int job) {
