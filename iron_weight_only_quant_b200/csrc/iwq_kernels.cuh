@@ -1554,15 +1554,7 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
             sg[b] = grid.codec_sign(n);
           }
           // group = the four blocks; low halves and high halves are two independent groups (neighbouring columns)
-          const uint32_t cnt = (info[0] & kDblOutl) + (info[1] & kDblOutl) + (info[2] & kDblOutl) + (info[3] & kDblOutl);  // k * 0x80 per half
-          const uint32_t few = __hle2_mask(from_u32<T2>(cnt), from_u32<T2>(kDblOutl));         // outlier_count <= 1      :338
-          const T2 g01 = __hmax2(from_u32<T2>(info[0] & kDblAe), from_u32<T2>(info[1] & kDblAe));  // positive patterns: float max == integer max
-          const T2 g23 = __hmax2(from_u32<T2>(info[2] & kDblAe), from_u32<T2>(info[3] & kDblAe));
-          const uint32_t gmax = as_u32(__hmax2(g01, g23));
-          uint32_t target = (gmax & ~few) | (hf2 & few);
-          const uint32_t anymax = (info[0] | info[1] | info[2] | info[3]) & kDblMaxOutl;
-          const uint32_t hm = __hne2_mask(from_u32<T2>(anymax), from_u32<T2>(0u));             // has_max_outlier          :342-343
-          target = (target & ~hm) | (maxe2 & hm);
+          const uint32_t target = double_approx_target2<DT>(info, hf2, maxe2);
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             const uint32_t idx = (info[b] & kDblCodeMask) | target | (sg[b] >> 8);             // target << 8 | sign << 7 | code

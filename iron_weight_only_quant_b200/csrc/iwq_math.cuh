@@ -748,6 +748,22 @@ IWQ_HD void double_approx_decode4(const uint32_t (&code)[4], const QuantConsts& 
 constexpr uint32_t kDblCodeMask = 0x007F007Fu, kDblOutl = 0x00800080u, kDblAe = 0x1F001F00u, kDblMaxOutl = 0x20002000u;
 constexpr int kDblValEntries = 32 * 256;
 
+// packed group logic on the INFO words of the four codes of a group -- two groups at once, one per 16-bit half:
+// returns the groups' target exponents in the aligned-exponent position (bits 8..12 of each half)      :334-343
+template <int DT>
+IWQ_HD uint32_t double_approx_target2(const uint32_t (&info)[4], uint32_t hi_field2, uint32_t max_exp2) {
+  using T2 = typename DType<DT>::T2;
+  const uint32_t cnt = (info[0] & kDblOutl) + (info[1] & kDblOutl) + (info[2] & kDblOutl) + (info[3] & kDblOutl);  // k * 0x80 per half
+  const uint32_t few = __hle2_mask(from_u32<T2>(cnt), from_u32<T2>(kDblOutl));             // outlier_count <= 1      :338
+  const T2 g01 = __hmax2(from_u32<T2>(info[0] & kDblAe), from_u32<T2>(info[1] & kDblAe));  // positive patterns: float max == integer max
+  const T2 g23 = __hmax2(from_u32<T2>(info[2] & kDblAe), from_u32<T2>(info[3] & kDblAe));
+  const uint32_t gmax = as_u32(__hmax2(g01, g23));
+  uint32_t target = (gmax & ~few) | (hi_field2 & few);
+  const uint32_t anymax = (info[0] | info[1] | info[2] | info[3]) & kDblMaxOutl;
+  const uint32_t hm = __hne2_mask(from_u32<T2>(anymax), from_u32<T2>(0u));                 // has_max_outlier          :342-343
+  return (target & ~hm) | (max_exp2 & hm);
+}
+
 IWQ_HD uint16_t double_approx_info(uint32_t mag_code, const QuantConsts& c) {
   int ae, mp;
   double_approx_fields(mag_code, c, &ae, &mp);

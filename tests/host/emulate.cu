@@ -245,3 +245,58 @@ extern "C" int emu_fp_roundtrip(int dtype, int flavour, int E, int M, const uint
   if (dtype == IWQ_F16) roundtrip<IWQ_F16>(c, x, y, n); else roundtrip<IWQ_BF16>(c, x, y, n);
   return 0;
 }
+
+
+// Exhaustive check of the table decomposition the device uses for the double-approximate decode (build_double_tables +
+// double_approx_target2) against the direct per-group decode (double_approx_decode4, itself pinned on the reference's
+// golden vectors): every 4-tuple of magnitude codes and signs when that is <= 2^24 tuples, else `samples` random ones.
+// Returns the number of mismatching values (or a negative error code).
+template <int DT>
+static long long double_table_check_t(const QuantConsts& c, long long samples) {
+  const int E = c.exp_bits, M = c.mant_bits, nm = 1 << (E + M), nc = 2 * nm;
+  std::vector<FpStep> steps(c.lut_n);
+  std::vector<uint16_t> val(kDblValEntries);
+  if (!build_double_tables_t<DT>(c, steps.data(), val.data())) return -1;
+  const uint32_t hf2 = ((uint32_t)c.hi_field << 8) * 0x00010001u, maxe2 = ((uint32_t)((1 << E) - 1) << 8) * 0x00010001u;
+  long long bad = 0;
+  const long long total = (long long)nc * nc * nc * nc;
+  const bool exhaustive = total <= (1ll << 24);
+  unsigned long long rs = 88172645463325252ull;
+  const long long n = exhaustive ? total : samples;
+  for (long long it = 0; it < n; ++it) {
+    long long k = it;
+    if (!exhaustive) { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; k = (long long)(rs % (unsigned long long)total); }
+    uint32_t code[4], info[4];
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t cc = (uint32_t)(k % nc);
+      k /= nc;
+      const uint32_t mag = cc % nm, sign = cc / nm;
+      code[i] = mag | (sign << (E + M));
+      const uint32_t inf = double_approx_info(mag, c);
+      info[i] = inf | (inf << 16);  // the same group in both halves
+    }
+    uint16_t want[4];
+    double_approx_decode4<DT>(code, c, want);
+    const uint32_t target = double_approx_target2<DT>(info, hf2, maxe2);
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t sign7 = ((code[i] >> (E + M)) & 1u) << 7;
+      const uint32_t idx = ((info[i] & kDblCodeMask) | target | (sign7 * 0x00010001u)) & 0xFFFFu;
+      const uint32_t idx_hi = ((info[i] & kDblCodeMask) | target | (sign7 * 0x00010001u)) >> 16;
+      if (val[idx] != want[i] || idx_hi != idx) ++bad;
+    }
+  }
+  return bad;
+}
+
+extern "C" long long emu_double_table_check(int dtype, int E, int M, int hi_start, int hi_field, int tail_pad, long long samples) {
+  iwq_config_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.dtype = dtype; cfg.scheme = IWQ_SCHEME_FP_CODEC; cfg.exp_bits = E; cfg.mant_bits = M; cfg.symmetric = 1; cfg.group = 128;
+  cfg.quant_dim = 1; cfg.approx = 2; cfg.hi_align_start = hi_start; cfg.hi_align_exp_field = hi_field; cfg.tail_pad_bits = tail_pad;
+  QuantConsts c;
+  int kind = 0;
+  std::string err;
+  int rc = build_quant_consts(&cfg, &c, &kind, &err);
+  if (rc) return rc;
+  return dtype == IWQ_F16 ? double_table_check_t<IWQ_F16>(c, samples) : double_table_check_t<IWQ_BF16>(c, samples);
+}

@@ -225,3 +225,16 @@ def test_double_approximate_math_matches_reference(emu, golden, dt, case):
     d = F16 if dt == "f16" else BF16
     out, _, _ = run_emu(emu, w, d, SCHEME_FP_CODEC, 128, E=E, M=M, sym=True, approx=2, hs=hs, hf=hf, tp=tp, quant_dim=1)
     assert_bits_equal(out, g[f"{dt}_approx_{name}_g128_d1_out"], dt, name)
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("case", DOUBLE_APPROX, ids=[c[0] for c in DOUBLE_APPROX])
+def test_double_approximate_table_decomposition(emu, dt, case):
+    """The device decodes through tables (INFO-word step table, packed target logic, value table indexed by
+    target | sign | code); on the CPU the same header functions are checked against the direct 4-code decode for
+    EVERY 4-tuple of codes (FP4: 65 536 tuples) or 2 million random ones (FP6 / FP8)."""
+    name, E, M, hs, hf, tp = case
+    emu.emu_double_table_check.restype = ctypes.c_longlong
+    emu.emu_double_table_check.argtypes = [ctypes.c_int] * 6 + [ctypes.c_longlong]
+    bad = emu.emu_double_table_check(0 if dt == "f16" else 1, E, M, hs, hf, tp, 2_000_000)
+    assert bad == 0, f"{name} {dt}: {bad} mismatching values"
