@@ -66,6 +66,16 @@ __global__ void __launch_bounds__(256) probe(uint8_t* w, uint32_t rows, uint32_t
   }
 }
 
+// L2 residency probe: read-only pass over `bytes` (sum kept alive through a never-taken store)
+__global__ void __launch_bounds__(256) read_only(const uint8_t* w, size_t bytes, uint32_t* sink) {
+  uint32_t acc = 0;
+  for (size_t off = ((size_t)blockIdx.x * 256 + threadIdx.x) * 16; off < bytes; off += (size_t)gridDim.x * 256 * 16) {
+    const uint4 v = *reinterpret_cast<const uint4*>(w + off);
+    acc ^= v.x ^ v.y ^ v.z ^ v.w;
+  }
+  if (acc == 0x12345678u) *sink = acc;
+}
+
 template <class F>
 static void run(const char* name, size_t bytes, F launch) {
   cudaEvent_t e0, e1;
@@ -90,6 +100,32 @@ int main(int argc, char** argv) {
   cudaMalloc(&w, bytes * n_mat);
   cudaMemset(w, 0, bytes * n_mat);
   printf("matrix [%u, %u] x %d (%.1f MB each)\n", rows, cols, n_mat, bytes / 1e6);
+  if (argc > 4) {  // tools/membench rows cols n l2: how much of a region just read is still in L2 when it is read again?
+    uint32_t* sink;
+    cudaMalloc(&sink, 4);
+    const size_t total = bytes * n_mat;
+    for (size_t mb : {8, 16, 24, 32, 48, 64, 96, 128, 192}) {
+      const size_t sz = mb << 20;
+      if (sz > total) break;
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      float best = 1e9f;
+      for (int rep = 0; rep < 5; ++rep) {
+        read_only<<<148 * 8, 256>>>(w + total - (256ull << 20), 256ull << 20, sink);  // evict: 256 MB of something else
+        read_only<<<148 * 8, 256>>>(w, sz, sink);                                        // warm
+        cudaEventRecord(e0);
+        read_only<<<148 * 8, 256>>>(w, sz, sink);                                        // re-read (timed)
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+      }
+      printf("re-read of %4zu MB right after reading it: %7.3f ms  %7.0f GB/s\n", mb, best, sz / best / 1e6);
+    }
+    return 0;
+  }
   auto each = [&](auto f) { for (int m = 0; m < n_mat; ++m) f(w + (size_t)m * bytes); };
   const size_t tot = bytes * n_mat;
   for (int ctas : {1, 2, 3, 4}) {
