@@ -199,10 +199,11 @@ struct Plan {
   int stages, consumers;   // row path
 };
 
-static bool seg_shape(uint64_t seg_elems, int* lps, int* vpl, bool seg4_ok) {
-  // seg4 kernel only: segments of 2048 / 4096 elements span 2 / 4 warps of a 16 KB tile (8192 works too, but the
-  // row kernel is faster there: 6073 vs 5924 GB/s on the 70B shapes; IWQ_WIDE_SEG4=2 enables it)
-  if (seg4_ok && (seg_elems == 2048 || seg_elems == 4096 || (seg_elems == 8192 && knobs().wide_seg4 >= 2))) {
+static bool seg_shape(uint64_t seg_elems, int* lps, int* vpl, bool seg4_ok, bool minifloat) {
+  // seg4 kernel only: segments of 2048 / 4096 elements span 2 / 4 warps of a 16 KB tile.  8192 (8 warps) works too: for
+  // INT the row kernel is faster there (6073 vs 5924 GB/s on the 70B shapes; IWQ_WIDE_SEG4=2 forces it), for the
+  // minifloat element stage the row kernel's 2-4 consumer warps are too few and seg4 wins
+  if (seg4_ok && (seg_elems == 2048 || seg_elems == 4096 || (seg_elems == 8192 && (minifloat || knobs().wide_seg4 >= 2)))) {
     *lps = (int)(seg_elems / 32);
     *vpl = 1;
     return true;
@@ -251,7 +252,8 @@ static int make_plan(const iwq_config_t* cfg, int64_t cols, uint32_t lut_bytes, 
     return IWQ_OK;
   }
   const int v = effective_variant(cfg);
-  if (seg_shape(seg, &pl->lps, &pl->vpl, (v < 1 || v > 2) && knobs().wide_seg4 != 0)) {
+  const bool minifloat = cfg->scheme == IWQ_SCHEME_FP_CODEC || cfg->scheme == IWQ_SCHEME_FP_RNE;
+  if (seg_shape(seg, &pl->lps, &pl->vpl, (v < 1 || v > 2) && knobs().wide_seg4 != 0, minifloat)) {
     pl->path = PATH_SEG;
     return IWQ_OK;
   }
@@ -269,6 +271,13 @@ static int make_plan(const iwq_config_t* cfg, int64_t cols, uint32_t lut_bytes, 
   int warps = vecs <= 128 ? 1 : (int)(vecs / 256);
   if (warps < (vecs <= 128 ? 1 : 2)) warps = vecs <= 128 ? 1 : 2;
   if (warps > 4) warps = 4;
+  if (minifloat) {
+    // the table-lookup element stage needs many more warps to hide its shared-memory latency: measured on the 70B
+    // shapes (FP4 per-channel) 3865 GB/s with 4 consumer warps, 4497 with 8, 4757 with 16 -- INT is the other way round
+    warps = (int)(vecs / 128);
+    if (warps < 2) warps = 2;
+    if (warps > 16) warps = 16;
+  }
   if (knobs().row_warps > 0) warps = knobs().row_warps > 16 ? 16 : knobs().row_warps;
   pl->consumers = 32 * warps;
   uint64_t budget = knobs().row_smem_kb > 0 ? (uint64_t)knobs().row_smem_kb * 1024 : 72 * 1024;
