@@ -142,6 +142,8 @@ typedef struct iwq_peers {
 } iwq_peers_t;
 size_t iwq_fused_workspace_bytes(int n);
 long long iwq_debug_fused_trace(int* n_batches); /* diagnostics: see iwq_host.cu */
+/* dispatch decision for a [rows, cols] matrix under `cfg` (kernel, tile shape; no CUDA call): out = int32[8], see iwq_host.cu */
+int iwq_debug_plan(const iwq_config_t* cfg, int64_t rows, int64_t cols, int32_t* out);
 int iwq_fake_quant_per_tensor_fused(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, void* workspace, size_t workspace_bytes,
                                     const iwq_peers_t* peers, int32_t* status, void* stream);
 

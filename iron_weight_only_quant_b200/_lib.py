@@ -38,6 +38,7 @@ EXPORTS = (
     "iwq_fake_quant_host_batched",
     "iwq_fused_workspace_bytes",
     "iwq_debug_fused_trace",
+    "iwq_debug_plan",
     "iwq_fake_quant_per_tensor_fused",
 )
 

@@ -592,6 +592,60 @@ using namespace iwq;
 extern "C" {
 
 int iwq_abi_version(void) { return IWQ_ABI_VERSION; }
+
+// Which kernel and tile shape a [rows, cols] matrix would get under `cfg` (no CUDA call: testable on a GPU-less box).
+// out[0] path: 0 seg4 / seg / direct (see out[1]), 1 row_tma_kernel, 2 col_async_kernel, 3 col_reg_kernel, 4 col_kernel
+//              (two sweeps), 5 col_double_kernel
+// out[1] kernel variant of the segment path (0 seg4_tma, 1 seg_direct, 2 seg_tma), out[2] lanes per segment,
+// out[3] ring stages, out[4] consumer warps (row path), out[5] bytes per stage (row / column paths),
+// out[6] row kernel sends its results through bulk stores, out[7] columns per tile (column paths)
+int iwq_debug_plan(const iwq_config_t* cfg, int64_t rows, int64_t cols, int32_t* out) {
+  if (!cfg || !out) return fail(IWQ_ERR_INVALID, "null argument");
+  memset(out, 0, 8 * sizeof(int32_t));
+  QuantConsts qc;
+  int kind = 0;
+  int rc = build_consts(cfg, &qc, &kind);
+  if (rc) return rc;
+  const uint32_t lut_bytes = kind == KIND_FP ? (uint32_t)(((size_t)qc.lut_n * sizeof(FpStep) + 1023) & ~(size_t)1023) : 0u;
+  if (cfg->quant_dim == 1 && cfg->group != IWQ_GROUP_PER_TENSOR) {
+    if (qc.approx == 2) {
+      out[0] = 5;
+      out[7] = kColTile;
+      return IWQ_OK;
+    }
+    int rpl = 0, stages = 0;
+    const uint32_t ctile = cfg->group > 0 ? col_tile_for(cfg->group, &rpl, &stages) : 0u;
+    out[0] = ctile ? (rpl ? 3 : 2) : 4;
+    out[3] = stages;
+    out[5] = (ctile && !rpl) ? (int32_t)((uint32_t)cfg->group * (ctile / 2)) : 0;
+    out[7] = (int32_t)(ctile ? ctile : (uint32_t)kColTile);
+    return IWQ_OK;
+  }
+  Plan pl;
+  rc = make_plan(cfg, cols, lut_bytes, &pl);
+  if (rc) return rc;
+  const bool per_tensor = cfg->group == IWQ_GROUP_PER_TENSOR;
+  if (pl.path == PATH_SEG) {
+    int variant = effective_variant(cfg);
+    if (variant < 0 || variant > 2) variant = 0;
+    if (variant == 0 && !per_tensor && pl.seg_elems < 32) variant = 2;
+    int st = knobs().seg_stages;
+    if (st < 2) st = 2;
+    if (st > kMaxStages) st = kMaxStages;
+    out[0] = 0;
+    out[1] = variant;
+    out[2] = variant == 0 ? (per_tensor ? 1 : (int32_t)(pl.seg_elems / 32)) : pl.lps;
+    out[3] = st;
+    return IWQ_OK;
+  }
+  out[0] = 1;
+  out[3] = pl.stages;
+  out[4] = pl.consumers / 32;
+  out[5] = (int32_t)pl.stage_bytes;
+  out[6] = (pl.stages >= 3 && knobs().row_tma_out != 0 && kind != KIND_FP && (knobs().row_tma_out > 1 || pl.seg_elems * 2ull >= 20 * 1024)) ? 1 : 0;
+  (void)rows;
+  return IWQ_OK;
+}
 const char* iwq_last_error(void) { return g_err.c_str(); }
 size_t iwq_workspace_bytes(int n) { return (size_t)(n < 1 ? 1 : n) * sizeof(Job); }
 

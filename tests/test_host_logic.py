@@ -180,3 +180,46 @@ def test_range_allreduce_world_size_2_gloo(built, tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_dispatch_plan_for_the_baseline_shapes(built):
+    """Which kernel a shape gets (iwq_debug_plan, no CUDA needed): guards the measured routing decisions."""
+    L = built.lib()
+    L.iwq_debug_plan.restype = ctypes.c_int
+    L.iwq_debug_plan.argtypes = [ctypes.POINTER(built.Config), ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32)]
+
+    def plan(rows, cols, **kw):
+        scheme = kw.pop("scheme", built.SCHEME_INT)
+        group = kw.pop("group")
+        cfg = built.make_config(torch.float16, scheme, group, **kw)
+        out = (ctypes.c_int32 * 8)()
+        built.check(L.iwq_debug_plan(ctypes.byref(cfg), rows, cols, out))
+        return list(out)
+
+    SEG, ROW, COL_ASYNC, COL_REG, COL_2SWEEP, COL_DOUBLE = range(6)
+    # per-group: seg4 (variant 0), lanes per segment = group / 32, 3 stages
+    for g, lps in [(32, 1), (64, 2), (128, 4), (256, 8), (1024, 32)]:
+        p = plan(8192, 8192, group=g, bits=4)
+        assert p[0] == SEG and p[1] == 0 and p[2] == lps and p[3] == 3, (g, p)
+    assert plan(64, 256, group=16, bits=4)[:2] == [SEG, 2]  # groups below 32 elements: one vector per lane-iteration
+    assert plan(4096, 4096, group=-1, bits=4)[:3] == [SEG, 0, 1]  # per-tensor apply pass
+    # per-channel: 2048 / 4096-wide rows through seg4 with 2 / 4 warps per row; others through the row kernel
+    assert plan(11008, 4096, group=-2, bits=4)[:3] == [SEG, 0, 128]
+    assert plan(64, 2048, group=-2, bits=8)[:3] == [SEG, 0, 64]
+    p = plan(4096, 11008, group=-2, bits=4)  # 22 KB rows: 3 stages, bulk stores, 4 consumer warps
+    assert p[0] == ROW and p[3] == 3 and p[4] == 4 and p[6] == 1, p
+    p = plan(8192, 8192, group=-2, bits=4)  # 16 KB rows: row kernel with register stores
+    assert p[0] == ROW and p[6] == 0, p
+    p = plan(8192, 28672, group=-2, bits=4)  # 56 KB rows: 2 stages only
+    assert p[0] == ROW and p[3] == 2 and p[6] == 0, p
+    # minifloat rows: 8192-wide through seg4 (8 warps per row), longer ones with many consumer warps, no bulk stores
+    assert plan(8192, 8192, group=-2, scheme=built.SCHEME_FP_CODEC, exp_bits=2, mant_bits=1, symmetric=True)[:3] == [SEG, 0, 256]
+    p = plan(8192, 28672, group=-2, scheme=built.SCHEME_FP_CODEC, exp_bits=2, mant_bits=1, symmetric=True)
+    assert p[0] == ROW and p[4] == 16 and p[6] == 0, p
+    # quant_dim = 1
+    assert plan(8192, 8192, group=128, bits=4, quant_dim=1)[0] == COL_ASYNC
+    assert plan(8192, 8192, group=-2, bits=4, quant_dim=1)[0] == COL_2SWEEP
+    assert plan(8192, 8192, group=96, bits=4, quant_dim=1)[0] == COL_2SWEEP
+    assert plan(8192, 8192, group=128, scheme=built.SCHEME_FP_CODEC, exp_bits=2, mant_bits=1, symmetric=True, quant_dim=1, approx=2, hi_align_start=0, hi_align_exp_field=2, tail_pad_bits=1)[0] == COL_DOUBLE
+    with pytest.raises(AssertionError):
+        plan(8192, 8200, group=128, bits=4)  # cols % group != 0 -> the reference's assert
