@@ -101,6 +101,20 @@ def workload_shapes(rank: int, world: int):
     return m.matrices(layers)
 
 
+def workload_config(mats_shape) -> dict:
+    """The `config` object of the JSON line: the SAME for this repo's arm and for the reference arm (which times a
+    bounded sample of this workload; the sample is described in its `cpu_baseline.sample`)."""
+    n_weights = sum(o * k for o, k in mats_shape)
+    return {
+        "workload": f"{MODEL}-shaped fp16, {LAYERS_PER_RANK} decoder layers (1/8 of the model: {len(mats_shape)} matrices, {n_weights} weights, {n_weights * 2 / 1e9:.2f} GB) per GPU, INT w{BITS} g{GROUP} asym, in place, scales+zeros emitted; N=8 covers the full 80-layer model",
+        "bits": BITS,
+        "group": GROUP,
+        "symmetric": SYMMETRIC,
+        "l2": "inputs (17.1 GB per GPU) exceed L2 (126 MB); no flush needed",
+        "launches_per_step": 1,
+    }
+
+
 def algorithmic_bytes(mats) -> int:
     n = sum(o * i for o, i in mats)
     return n * 4 + (n // GROUP) * 4  # 16-bit read + 16-bit write per weight; 16-bit scale + zero per group
@@ -162,7 +176,7 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f16",
         "data": "synthetic",
-        "config": {"workload": f"{MODEL} 1/8 shard shapes, INT w{BITS} g{GROUP} asym fp16 (bounded sample: one [8192,8192] matrix per step)", "bits": BITS, "group": GROUP, "symmetric": SYMMETRIC},
+        "config": workload_config(workload_shapes(0, 1)),
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -303,14 +317,7 @@ def run_ours(args):
             "vs_baseline": None,
             "dtype": "f16",
             "data": "synthetic",
-            "config": {
-                "workload": f"{MODEL}-shaped fp16, {LAYERS_PER_RANK} decoder layers (1/8 of the model: {len(mats_shape)} matrices, {n_weights} weights, {n_weights * 2 / 1e9:.2f} GB) per GPU, INT w{BITS} g{GROUP} asym, in place, scales+zeros emitted; N=8 covers the full 80-layer model",
-                "bits": BITS,
-                "group": GROUP,
-                "symmetric": SYMMETRIC,
-                "l2": "inputs (17.1 GB per GPU) exceed L2 (126 MB); no flush needed",
-                "launches_per_step": 1,
-            },
+            "config": workload_config(mats_shape),
             "pct_of_8TBps": 100.0 * value / (8000.0 * world),
             "weights_per_s": n_weights * world / (ms_per_step * 1e-3),
             "llama2_70b_full_model_ms": ms_per_step * (8.0 / world),
