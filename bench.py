@@ -3,26 +3,32 @@
 Llama-2-70B full-model quantise ms).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path (oracle/_ref, else the port)
 
-Workload (per GPU, weak scaling): the Linear weights of a 1/8 shard of a Llama-2-70B-shaped fp16 model
-(10 contiguous decoder layers = 70 matrices = 8.556 G weights = 17.1 GB), random-init on the device,
-fake-quantised IN PLACE at INT w4, group 128, asymmetric, emitting scales and zero points -- exactly what
-`quantize_model` does per device.  At N = 8 the union of the ranks' shards is the full 80-layer model, so
-`ms_per_step` at N = 8 is the "Llama-2-70B full-model quantise ms" of the metric.  One step = one pass over
-the shard = ONE persistent kernel launch (work list of 70 matrices).  Inputs (17.1 GB) exceed L2 (126 MB)
-by two orders of magnitude, so no L2 flush is needed between steps.  Timing is data independent (no
-data-dependent control flow), which is why re-quantising the same buffers every step is legitimate.
+Headline workload (per GPU, weak scaling; BASELINE.json configs[4]): the Linear weights of a 1/8 shard of a
+Llama-2-70B-shaped fp16 model (10 contiguous decoder layers = 70 matrices = 8.556 G weights = 17.1 GB), random-init on
+the device, fake-quantised IN PLACE at INT w4, group 128, asymmetric, emitting scales and zero points -- exactly what
+`quantize_model` does per device.  At N = 8 the union of the ranks' shards is the full 80-layer model, so `ms_per_step`
+at N = 8 is the "Llama-2-70B full-model quantise ms" of the metric.  One step = one pass over the shard = ONE persistent
+kernel launch (work list of 70 matrices).  Inputs (17.1 GB) exceed L2 (126 MB) by two orders of magnitude, so no L2
+flush is needed between steps.  Timing is data independent (no data-dependent control flow), which is why
+re-quantising the same buffers every step is legitimate.
 
-`value`  = algorithmic GB/s summed over ranks (4 B per weight + 4 B per group of emitted scale/zero),
-           inputs resident in HBM, CUDA-event timed, max over ranks.
-`e2e`    = the same metric through the host-buffer C-ABI entry point (`iwq_fake_quant_host_batched`): pinned host
-           weights -> H2D -> kernel -> D2H, every byte of the shard crossing PCIe both ways each step.
+`value`    = algorithmic GB/s summed over ranks (4 B per weight + 4 B per group of emitted scale/zero), inputs resident
+             in HBM, CUDA-event timed, max over ranks.
+`e2e`      = the same metric through the host-buffer C-ABI entry point (`iwq_fake_quant_host_batched`): pinned host
+             weights -> H2D -> kernel -> D2H (weights, scales and zero points), every byte crossing PCIe each step.
+`configs`  = the other BASELINE.json configurations, measured in the same run (kernel GB/s, fraction of the measured HBM
+             peak, and a bit-parity check of sampled rows against the numpy oracle):
+               config2  LLaMA-2-7B shapes, per-channel (group_size = -2) w8 / w4                          (N = 1)
+               config3  LLaMA-2-13B shapes, w4 g32/64/128/256 and FP4 (E2M1, E1M2) / FP6 (E3M2, E2M3) / FP8 (E4M3) g128 (N = 1)
+               config4  OPT-6.7B shapes, per-tensor (-1) w4: whole matrices at N = 1; at N > 1 every matrix row-split
+                        across the ranks, local range pass -> ONE NCCL MAX all-reduce -> local apply pass (per-phase ms)
+             config1 (OPT-125M, every Linear, the reference on CPU) is part of the CPU legs.
 """
 from __future__ import annotations
 
 import argparse
-import ctypes
 import json
 import os
 import statistics
@@ -115,33 +121,69 @@ def workload_config(mats_shape) -> dict:
     }
 
 
-def algorithmic_bytes(mats) -> int:
+def algorithmic_bytes(mats, group=GROUP, meta_per_group=4) -> int:
     n = sum(o * i for o, i in mats)
-    return n * 4 + (n // GROUP) * 4  # 16-bit read + 16-bit write per weight; 16-bit scale + zero per group
+    return n * 4 + (n // group) * meta_per_group  # 16-bit read + 16-bit write per weight; 16-bit scale + zero per group
+
+
+def synth_weight(torch, o, k, seed, device, dtype):
+    """W = (randn(out, in, seed = 1234 + matrix_index) * 0.02).to(dtype); generated in row chunks
+    to bound the fp32 temporaries."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    w = torch.empty(o, k, dtype=dtype, device=device)
+    step_rows = max(1, (64 << 20) // k)
+    for r0 in range(0, o, step_rows):
+        r1 = min(o, r0 + step_rows)
+        w[r0:r1] = (torch.randn(r1 - r0, k, generator=gen, device=device) * 0.02).to(dtype)
+    return w
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU implementation (oracle port) on the host cores
+# CPU legs: the reference's own implementation on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(steps: int, warmup: int, seconds_cap: float = 25.0):
-    """Times oracle/torch_cpu_port.int_fake_quant (the reference's ATen op sequence) on [8192, 8192] fp16
-    matrices (the 70B q_proj/o_proj shape), w4 g128 asym, with every host thread torch will use."""
-    import torch
+def _reference_fn():
+    """(callable(w, n_bits, zero_point, group) -> tensor, kind, description).  oracle/_ref holds the unmodified reference
+    modules (oracle/build_ref.py); without it the eager-torch port of the same ATen op sequence is used."""
+    try:
+        from oracle import build_ref
 
+        if build_ref.available():
+            qf = build_ref.load("quant_funcs")
+            return (lambda w, b, zp, g: qf.pseudo_quantize_tensor(w, n_bits=b, zero_point=zp, q_group_size=g)), "reference", "the reference's unmodified quant_funcs.pseudo_quantize_tensor (oracle/_ref, quant_funcs.py:4-46)"
+    except Exception:
+        pass
     from oracle import torch_cpu_port as P
 
+    return (lambda w, b, zp, g: P.int_fake_quant(w, b, zp, g)), "port", "eager-torch port of the reference's op sequence (oracle/torch_cpu_port.py)"
+
+
+def cpu_sample(steps: int, warmup: int, seconds_cap: float = 25.0):
+    """One step = ONE decoder layer of the headline workload (7 Llama-2-70B-shaped fp16 matrices, 855.6 M weights, 1/10 of
+    a rank's shard), INT w4 g128 asym through the reference's CPU implementation with every host thread torch will use."""
+    import torch
+
+    fn, kind, what = _reference_fn()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    g = torch.Generator().manual_seed(1234)
-    w = (torch.randn(8192, 8192, generator=g) * 0.02).half()
-    nbytes = algorithmic_bytes([(8192, 8192)])
-    for _ in range(max(1, min(warmup, 2))):
-        P.int_fake_quant(w, BITS, not SYMMETRIC, GROUP)
-    times = []
+    layer = workload_shapes(0, 1)[: len(workload_shapes(0, 1)) // LAYERS_PER_RANK]
+    ws = []
+    for i, (o, k) in enumerate(layer):
+        g = torch.Generator().manual_seed(1234 + i)
+        ws.append((torch.randn(o, k, generator=g) * 0.02).half())
+    nbytes = algorithmic_bytes(layer)
+
+    def step():
+        for w in ws:
+            fn(w, BITS, not SYMMETRIC, GROUP)
+
     t_all = time.perf_counter()
+    for _ in range(max(0, min(warmup, 1))):
+        step()
+    times = []
     for _ in range(max(1, steps)):
         t0 = time.perf_counter()
-        P.int_fake_quant(w, BITS, not SYMMETRIC, GROUP)
+        step()
         times.append(time.perf_counter() - t0)
         if time.perf_counter() - t_all > seconds_cap:
             break
@@ -150,18 +192,43 @@ def cpu_sample(steps: int, warmup: int, seconds_cap: float = 25.0):
         "value": nbytes / (ms * 1e-3) / 1e9,
         "unit": UNIT,
         "cores": torch.get_num_threads(),
-        "kind": "port",
-        "sample": f"{len(times)} x one [8192,8192] fp16 matrix (Llama-2-70B q_proj shape, 67.1 M weights), INT w4 g128 asym, torch CPU eager ops in the reference's order (oracle/torch_cpu_port.py)",
+        "kind": kind,
+        "sample": f"{len(times)} x one decoder layer of the headline workload (7 Llama-2-70B-shaped fp16 matrices, {sum(o * k for o, k in layer)} weights = 1/10 of a rank's shard), INT w4 g128 asym, {what}",
         "ms_per_sample": ms,
         "steps_run": len(times),
     }
+
+
+def cpu_config1(repeats: int = 3):
+    """BASELINE.json configs[0]: OPT-125M random-init weights, w4 per-group 128 pseudo_quantize_tensor over all 72 Linear
+    layers on CPU (the reference path), best of `repeats`."""
+    import torch
+
+    from iron_weight_only_quant_b200 import shapes
+
+    fn, kind, _ = _reference_fn()
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = shapes.MODELS["opt-125m"]
+    mats = m.matrices(range(m.n_layers))
+    ws = []
+    for i, (o, k) in enumerate(mats):
+        g = torch.Generator().manual_seed(1234 + i)
+        ws.append((torch.randn(o, k, generator=g) * 0.02).half())
+    best = float("inf")
+    for _ in range(repeats + 1):
+        t0 = time.perf_counter()
+        for w in ws:
+            fn(w, 4, True, 128)
+        best = min(best, time.perf_counter() - t0)
+    n = sum(o * k for o, k in mats)
+    return {"what": "OPT-125M shapes, all 72 Linear weights, INT w4 g128 asym, reference CPU path", "kind": kind, "matrices": len(mats), "weights": n, "ms": best * 1e3, "GBps": algorithmic_bytes(mats) / best / 1e9, "Mweights_per_s": n / best / 1e6, "cores": torch.get_num_threads()}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_sample(args.steps, args.warmup, seconds_cap=120.0)
+    cb = cpu_sample(args.steps, args.warmup, seconds_cap=150.0)
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -169,7 +236,7 @@ def run_reference(args):
         "unit": UNIT,
         "n_gpus": args.gpus,
         "steps": cb["steps_run"],
-        "warmup": args.warmup,
+        "warmup": min(args.warmup, 1),
         "ms_per_step": cb["ms_per_sample"],
         "higher_is_better": True,
         "scaling": "weak",
@@ -180,8 +247,250 @@ def run_reference(args):
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "configs": {"config1": cpu_config1()},
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE configurations (kernel throughput + sampled bit-parity), this repo's arm
+# ------------------------------------------------------------------------------------------------
+def _bits(t):
+    import numpy as np
+    import torch
+
+    return t.detach().contiguous().cpu().view(torch.int16).numpy().view(np.uint16)
+
+
+def _time_cuda(torch, fn, iters, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(iters):
+        fn()
+    ev[1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) / iters
+
+
+def _entry(ms, nbytes, peak, **kw):
+    d = {"ms": ms, "GBps": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak}
+    d.update(kw)
+    return d
+
+
+def run_configs_single_gpu(torch, dev, peak, iters):
+    """configs 2, 3 and (unsharded) 4 on one GPU.  Every entry: ms per pass over the model's weights, algorithmic GB/s
+    (4 B/weight + emitted scales / zero points), fraction of the measured HBM peak, launches per pass, and `parity_ok`:
+    the first pass runs on fresh data and rows 0..7 of matrix 0 are compared bit for bit with the numpy oracle."""
+    import numpy as np
+
+    from iron_weight_only_quant_b200 import _lib, shapes
+    from oracle import fakequant_oracle as O
+
+    out = {}
+    f16 = torch.float16
+
+    def model_weights(name):
+        m = shapes.MODELS[name]
+        mats = m.matrices(range(m.n_layers))
+        return mats, [synth_weight(torch, o, k, 1234 + i, dev, f16) for i, (o, k) in enumerate(mats)]
+
+    def run_case(mats, ws, cfg, group, sym, oracle_fn, emit=True):
+        n = sum(o * k for o, k in mats)
+        descs, keep = [], []
+        n_seg = 0
+        for w in ws:
+            o, k = w.shape
+            G = _lib.num_segments(o, k, group)
+            n_seg += G
+            s = torch.empty(G, dtype=f16, device=dev) if emit else None
+            z = torch.empty(G, dtype=f16, device=dev) if (emit and not sym) else None
+            keep.append((s, z))
+            descs.append(_lib.matrix_desc(w, w, o, k, s, z))
+        by_cols = {}
+        if group == _lib.GROUP_PER_CHANNEL:
+            for d, w in zip(descs, ws):
+                by_cols.setdefault(w.shape[1], []).append(d)  # a batched launch shares the segment shape
+        rng = torch.empty(2 * len(descs), dtype=torch.float32, device=dev)
+
+        def step():
+            if group == _lib.GROUP_PER_TENSOR:
+                _lib.per_tensor_batched_(descs, cfg, dev, rng, track_status=False)
+            elif by_cols:
+                for ds in by_cols.values():
+                    _lib.fake_quant_batched_(ds, cfg, dev, track_status=False)
+            else:
+                _lib.fake_quant_batched_(descs, cfg, dev, track_status=False)
+
+        # parity on fresh data: the whole of matrix 0 for per-tensor (the range is global), its first 8 rows otherwise
+        sample = ws[0] if group == _lib.GROUP_PER_TENSOR else ws[0][:8]
+        before = _bits(sample)
+        step()
+        torch.cuda.synchronize()
+        ref = oracle_fn(before)
+        got = _bits(ws[0] if group == _lib.GROUP_PER_TENSOR else ws[0][:8])
+        ok = bool(np.array_equal(got, ref["out"]))
+        if emit and ok:
+            G8 = ref["scales"].size
+            ok = bool(np.array_equal(_bits(keep[0][0])[:G8], ref["scales"]))
+            if not sym and "zeros" in ref:
+                ok = ok and bool(np.array_equal(_bits(keep[0][1])[:G8], ref["zeros"]))
+        ms = _time_cuda(torch, step, iters, warm=1)
+        launches = 2 * 1 if group == _lib.GROUP_PER_TENSOR else (len(by_cols) if by_cols else 1)
+        nbytes = n * 4 + (n_seg * (2 if sym else 4) if emit else 0)
+        return _entry(ms, nbytes, peak, weights=n, launches_per_pass=launches, parity_ok=ok)
+
+    # ---- config 2: LLaMA-2-7B, per-channel ------------------------------------------------------------
+    mats, ws = model_weights("llama-2-7b")
+    c2 = {"workload": "LLaMA-2-7B-shaped fp16 (224 matrices, 6.48 G weights), per-channel (group_size = -2), asym, scales+zeros emitted"}
+    for bits in (8, 4):
+        cfg = _lib.make_config(f16, _lib.SCHEME_INT, _lib.GROUP_PER_CHANNEL, bits=bits, symmetric=False)
+        c2[f"w{bits}"] = run_case(mats, ws, cfg, _lib.GROUP_PER_CHANNEL, False, lambda b, bits=bits: O.int_fake_quant(b, "f16", bits, True, -2))
+    out["config2"] = c2
+    del ws
+    torch.cuda.empty_cache()
+
+    # ---- config 3: LLaMA-2-13B, group sweep + minifloat formats ----------------------------------------
+    mats, ws = model_weights("llama-2-13b")
+    c3 = {"workload": "LLaMA-2-13B-shaped fp16 (280 matrices, 12.69 G weights); INT w4 asym g32/64/128/256 (scales+zeros emitted); FP4/FP6/FP8 codec formats g128 sym (scales emitted)"}
+    for g in (32, 64, 128, 256):
+        cfg = _lib.make_config(f16, _lib.SCHEME_INT, g, bits=4, symmetric=False)
+        c3[f"w4_g{g}"] = run_case(mats, ws, cfg, g, False, lambda b, g=g: O.int_fake_quant(b, "f16", 4, True, g))
+    for name, (E, M) in (("fp4_e2m1", (2, 1)), ("fp4_e1m2", (1, 2)), ("fp6_e3m2", (3, 2)), ("fp6_e2m3", (2, 3)), ("fp8_e4m3", (4, 3))):
+        cfg = _lib.make_config(f16, _lib.SCHEME_FP_CODEC, 128, exp_bits=E, mant_bits=M, symmetric=True)
+        c3[f"{name}_g128"] = run_case(mats, ws, cfg, 128, True, lambda b, E=E, M=M: O.fp_codec_fake_quant(b, "f16", E, M, True, 128))
+    out["config3"] = c3
+    del ws
+    torch.cuda.empty_cache()
+
+    # ---- config 4 on ONE GPU: whole matrices, per-tensor ----------------------------------------------
+    mats, ws = model_weights("opt-6.7b")
+    cfg = _lib.make_config(f16, _lib.SCHEME_INT, _lib.GROUP_PER_TENSOR, bits=4, symmetric=False)
+    c4 = run_case(mats, ws, cfg, _lib.GROUP_PER_TENSOR, False, lambda b: O.int_fake_quant(b, "f16", 4, True, -1), emit=False)
+    c4["workload"] = "OPT-6.7B-shaped fp16 (192 matrices, 6.44 G weights), per-tensor (-1) w4 asym, whole matrices on one GPU: range pass + apply pass (6 B/weight of HBM traffic for 4 algorithmic)"
+    out["config4"] = c4
+    del ws
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_config4_sharded(torch, dist, dev, rank, world, peak, iters):
+    """BASELINE.json configs[3] at N > 1: OPT-6.7B-shaped fp16 weights, per-tensor (-1) w4 asym, EVERY matrix row-split
+    across the `world` ranks; local range pass -> ONE NCCL MAX all-reduce over {max, -min} of all 192 matrices -> local
+    apply pass (iron_weight_only_quant_b200.sharded).  Per-phase device times are the max over ranks.  `parity_ok`: the
+    global (min, max) of three matrices is recomputed with torch.amin/amax + all_reduce (independent of this library),
+    turned into (scale, zero) by the numpy oracle and applied by the oracle to sampled rows of every rank's shard; the
+    fake-quantised rows must match bit for bit on every rank."""
+    import numpy as np
+
+    from iron_weight_only_quant_b200 import _lib, shapes, sharded
+    from oracle import fakequant_oracle as O
+
+    m = shapes.MODELS["opt-6.7b"]
+    mats = m.matrices(range(m.n_layers))
+    shards = []
+    for i, (o, k) in enumerate(mats):
+        r = shapes.split_rows(o, world, rank)
+        # the same full matrix on every rank would cost 8x the generation time: each rank draws its own row block from a
+        # (matrix, rank)-seeded stream; the union of the blocks is "the matrix"
+        shards.append(synth_weight(torch, r.stop - r.start, k, 1234 + i + 7919 * (rank + 1), dev, torch.float16))
+    n_local = sum(s.numel() for s in shards)
+    n_total = sum(o * k for o, k in mats)
+    cfg = _lib.make_config(torch.float16, _lib.SCHEME_INT, _lib.GROUP_PER_TENSOR, bits=4, symmetric=False)
+    descs = [_lib.matrix_desc(s, s, s.shape[0], s.shape[1]) for s in shards]
+    rng = torch.empty(2 * len(descs), dtype=torch.float32, device=dev)
+
+    # ---- parity on fresh data (first pass) ----
+    probe = [0, 4, 5]  # a [4096,4096], the [16384,4096] and the [4096,16384] matrix of layer 0
+    rows = 4
+    before, ranges = {}, {}
+    for j in probe:
+        before[j] = _bits(shards[j][:rows])
+        mx = shards[j].amax().float().reshape(1)
+        mn = shards[j].amin().float().reshape(1)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        ranges[j] = (float(mx.item()), float(mn.item()))
+    sharded.pseudo_quantize_tensors_per_tensor_sharded(shards, n_bits=4, zero_point=True)
+    torch.cuda.synchronize()
+    ok = True
+    for j in probe:
+        s, z = O.int_ranges_to_qparams(np.float32([ranges[j][0]]), np.float32([ranges[j][1]]), 4, True, "f16")
+        ref, _ = O.int_apply(O.from_bits(before[j], "f16"), s, z, 4, True, "f16")
+        ok = ok and bool(np.array_equal(_bits(shards[j][:rows]), O.to_bits(ref, "f16")))
+    okt = torch.tensor([0 if ok else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(okt, op=dist.ReduceOp.MAX)
+
+    # ---- timing: three phases ----
+    def step(ev=None):
+        _lib.minmax_(descs, cfg, dev, rng)
+        if ev:
+            ev[0].record()
+        sharded.allreduce_ranges(rng)
+        if ev:
+            ev[1].record()
+        _lib.fake_quant_with_range_(descs, cfg, dev, rng, track_status=False)
+
+    for _ in range(2):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    tot = [0.0, 0.0, 0.0, 0.0]
+    for _ in range(iters):
+        dist.barrier()
+        e[0].record()
+        step(ev=e[1:3])
+        e[3].record()
+        torch.cuda.synchronize()
+        tot[0] += e[0].elapsed_time(e[1])
+        tot[1] += e[1].elapsed_time(e[2])
+        tot[2] += e[2].elapsed_time(e[3])
+        tot[3] += e[0].elapsed_time(e[3])
+    t = torch.tensor([x / iters for x in tot], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[3].item())
+    return {
+        "workload": f"OPT-6.7B-shaped fp16 (192 matrices, 6.44 G weights), per-tensor (-1) w4 asym, every matrix row-split across {world} GPUs; range pass -> ONE NCCL MAX all-reduce (192 x 8 B) -> apply pass",
+        "ms": ms,
+        "ms_range_pass": float(t[0].item()),
+        "ms_allreduce": float(t[1].item()),
+        "ms_apply_pass": float(t[2].item()),
+        "GBps": n_total * 4 / ms / 1e6,
+        "GBps_per_gpu": n_local * 4 / ms / 1e6,
+        "frac": n_local * 4 / ms / 1e6 / peak,
+        "traffic_GBps_per_gpu": n_local * 6 / ms / 1e6,
+        "weights": n_total,
+        "launches_per_pass": 3,
+        "collective": "torch.distributed all_reduce(MAX) over NCCL, one call per pass",
+        "parity_ok": bool(okt.item() == 0),
+    }
+
+
+def reference_eager_cuda(torch, dev, iters=5):
+    """SURVEY.md section 8(d) "reference beside it" (2): the reference's own pseudo_quantize_tensor executed as torch-eager
+    ops on cuda:0 (one decoder layer of the headline workload), CUDA-event timed, best of `iters` -- what fusion buys."""
+    fn, kind, what = _reference_fn()
+    layer = workload_shapes(0, 1)[: len(workload_shapes(0, 1)) // LAYERS_PER_RANK]
+    ws = [synth_weight(torch, o, k, 1234 + i, dev, torch.float16) for i, (o, k) in enumerate(layer)]
+    best = float("inf")
+    for it in range(iters + 1):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for w in ws:
+            fn(w, BITS, not SYMMETRIC, GROUP)
+        e1.record()
+        torch.cuda.synchronize()
+        if it:
+            best = min(best, e0.elapsed_time(e1))
+    n = sum(o * k for o, k in layer)
+    del ws
+    torch.cuda.empty_cache()
+    return {"what": f"{what} on cuda:0 (torch eager), one decoder layer of the headline workload ({n} weights), best of {iters}", "kind": kind, "ms": best, "GBps": algorithmic_bytes(layer) / best / 1e6}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -205,16 +514,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     mats_shape = workload_shapes(rank, world)
-    gen = torch.Generator(device=dev)
     weights, scales, zeros, descs = [], [], [], []
     for i, (o, k) in enumerate(mats_shape):
-        gen.manual_seed(1234 + i)
-        w = torch.empty(o, k, dtype=torch.float16, device=dev)
-        # randn * 0.02 generated in chunks to bound fp32 temporaries
-        step_rows = max(1, (64 << 20) // k)
-        for r0 in range(0, o, step_rows):
-            r1 = min(o, r0 + step_rows)
-            w[r0:r1] = (torch.randn(r1 - r0, k, generator=gen, device=dev) * 0.02).half()
+        w = synth_weight(torch, o, k, 1234 + i, dev, torch.float16)
         G = o * k // GROUP
         s = torch.empty(G, dtype=torch.float16, device=dev)
         z = torch.empty(G, dtype=torch.float16, device=dev)
@@ -261,39 +563,62 @@ def run_ours(args):
 
     # ---- end to end: pinned host weights through the host-buffer C-ABI entry point --------------------
     layer_shapes = mats_shape[: len(mats_shape) // LAYERS_PER_RANK]
-    # place this rank's pinned buffers on its GPU's NUMA node (first touch after the affinity change)
-    from iron_weight_only_quant_b200 import hostmem
-
-    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-    phys = int(visible.split(",")[local]) if visible and visible.split(",")[local].strip().isdigit() else local
-    numa_cpus = hostmem.bind_to_gpu_numa(phys)
     host = [torch.empty(o, k, dtype=torch.float16).pin_memory() for o, k in layer_shapes]
+    host_s = [torch.empty(o * k // GROUP, dtype=torch.float16).pin_memory() for o, k in layer_shapes]
+    host_z = [torch.empty(o * k // GROUP, dtype=torch.float16).pin_memory() for o, k in layer_shapes]
     for h, w in zip(host, weights):
         h.copy_(w)  # quantised values: content is irrelevant for timing
-    def e2e_step():
+
+    def e2e_step(copy_only=False):
         # every layer of the shard crosses PCIe both ways: ONE call, one chunk pipeline over all 70 matrices
         # (the 7 pinned buffers of a layer are passed LAYERS_PER_RANK times; 17.1 GB pinned would be wasteful)
-        _lib.fake_quant_host_(host * LAYERS_PER_RANK, cfg, device=local, chunk_bytes=args.e2e_chunk_mb << 20)
+        _lib.fake_quant_host_(host * LAYERS_PER_RANK, cfg, device=local, chunk_bytes=args.e2e_chunk_mb << 20, scales=host_s * LAYERS_PER_RANK, zeros=host_z * LAYERS_PER_RANK, copy_only=copy_only)
 
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    if args.skip_e2e:
-        e2e_steps, e2e_s = 0, float("inf")
-    else:
-        e2e_step()
+    def timed_e2e(steps, copy_only=False):
+        e2e_step(copy_only)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
+        for _ in range(steps):
+            e2e_step(copy_only)
         torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e_value = nbytes * world * e2e_steps / e2e_s / 1e9
+        mine = time.perf_counter() - t0
+        tt = torch.tensor([mine], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(tt) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allt, tt)
+        else:
+            allt = [tt]
+        return [float(x.item()) for x in allt]
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_bytes_in = n_weights * 2
+    e2e_bytes_out = n_weights * 2 + (n_weights // GROUP) * 4  # weights + emitted scales and zero points
+    if args.skip_e2e:
+        e2e_value, e2e_extra = None, {}
+    else:
+        per_rank = timed_e2e(e2e_steps)
+        e2e_s = max(per_rank)
+        e2e_value = nbytes * world * e2e_steps / e2e_s / 1e9
+        ctl = timed_e2e(e2e_steps, copy_only=True)  # the same chunk ring, no kernel: what the copy engines / host give
+        e2e_extra = {
+            "per_rank_h2d_GBps": [e2e_bytes_in * e2e_steps / s / 1e9 for s in per_rank],
+            "per_rank_d2h_GBps": [e2e_bytes_out * e2e_steps / s / 1e9 for s in per_rank],
+            "copy_only_control": {"what": "same pinned buffers, same chunk ring, kernels skipped (iwq host pipeline with copy_only)", "value": nbytes * world * e2e_steps / max(ctl) / 1e9, "per_rank_h2d_GBps": [e2e_bytes_in * e2e_steps / s / 1e9 for s in ctl]},
+            "host": {"cpus": os.cpu_count(), "note": "single-node VM: every GPU reports the same CPU affinity (one NUMA node), so there is no per-GPU NUMA placement to do"},
+        }
+
+    # ---- the other BASELINE configurations -------------------------------------------------------------
+    peak, peak_src = _peaks()
+    configs = {}
+    if not args.skip_configs:
+        del host
+        if world == 1:
+            configs.update(run_configs_single_gpu(torch, dev, peak, args.config_iters))
+            configs["reference_eager_cuda"] = reference_eager_cuda(torch, dev)
+        else:
+            configs["config4"] = run_config4_sharded(torch, dist, dev, rank, world, peak, max(args.config_iters, 10))
 
     if rank == 0:
-        peak, peak_src = _peaks()
         kernel_ms = statistics.mean(per_launch_ms)
         achieved = nbytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
@@ -303,7 +628,7 @@ def run_ours(args):
                 traffic = json.load(open(tp)).get("bench_kernel_dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        cb = cpu_sample(steps=40, warmup=1, seconds_cap=15.0) if (world == 1 and not args.skip_cpu) else None
+        cb = cpu_sample(steps=10, warmup=1, seconds_cap=20.0) if (world == 1 and not args.skip_cpu) else None
         line = {
             "metric": METRIC,
             "value": value,
@@ -321,14 +646,21 @@ def run_ours(args):
             "pct_of_8TBps": 100.0 * value / (8000.0 * world),
             "weights_per_s": n_weights * world / (ms_per_step * 1e-3),
             "llama2_70b_full_model_ms": ms_per_step * (8.0 / world),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel": "seg4_tma_kernel<f16,INT_FAST,asym>", "bytes_per_launch": nbytes, "kernel_ms": kernel_ms},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_weights * 2, "d2h_bytes_per_step": n_weights * 2, "steps": e2e_steps, "api": "iwq_fake_quant_host_batched (pinned host buffers, one 4-deep H2D/kernel/D2H chunk ring over all 70 matrices)", "numa_bound_cpus": len(numa_cpus)},
+            "llama2_70b_full_model_ms_note": "measured at N = 8 (each rank one 1/8 shard); at smaller N it is ms_per_step x 8/N, an extrapolation from the shard actually timed",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload from the committed ncu --set full capture (not re-measured in this run)", "peak_source": peak_src, "kernel": "seg4_tma_kernel<f16,INT_FAST,asym>", "bytes_per_launch": nbytes, "kernel_ms": kernel_ms},
             "gpu_launches": args.steps,
             "clocks": clocks,
             "nan_status": status,
         }
+        if e2e_value is not None:
+            line["e2e"] = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_bytes_in, "d2h_bytes_per_step": e2e_bytes_out, "steps": e2e_steps, "api": "iwq_fake_quant_host_batched (pinned host buffers, one 4-deep H2D/kernel/D2H chunk ring over all 70 matrices; weights, scales and zero points come back)"}
+            line["e2e"].update(e2e_extra)
+        if configs:
+            line["configs"] = configs
         if cb is not None:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            if not args.skip_configs:
+                line.setdefault("configs", {})["config1"] = cpu_config1()
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -343,8 +675,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-chunk-mb", type=int, default=64)
+    ap.add_argument("--config-iters", type=int, default=5, help="timed passes per entry of `configs`")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave out the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: leave out the CPU baseline leg")
+    ap.add_argument("--skip-configs", action="store_true", help="profiling runs only: leave out BASELINE configs 1-4")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define IWQ_ABI_VERSION 3
+#define IWQ_ABI_VERSION 4
 
 /* storage dtype of weights, scales and zeros */
 enum { IWQ_F16 = 0, IWQ_BF16 = 1 };
@@ -116,6 +116,12 @@ int iwq_fake_quant(const iwq_config_t* cfg, const iwq_matrix_t* m, float* range_
 int iwq_fake_quant_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, void* workspace, size_t workspace_bytes,
                            int32_t* status, void* stream);
 
+/* Per-tensor granularity (quant_funcs.py:13-14, quant_linear.py:898-900) for `n` matrices that are WHOLE on this GPU:
+ * the library orders range passes and apply passes itself (per L2-sized slab of matrices, so that the apply pass
+ * reads its slab from L2).  `range`: device float[2*n] scratch, receives {max|absmax, -min} per matrix. */
+int iwq_fake_quant_per_tensor_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, float* range, void* workspace,
+                                      size_t workspace_bytes, int32_t* status, void* stream);
+
 /* ---- per-tensor granularity on a matrix that is sharded across GPUs (no reference counterpart;
  *      SURVEY.md section 8e): range pass, (NCCL MAX all-reduce of `range` by the caller), apply pass.
  * `range`: device float[2*n] laid out {max_or_absmax, -min} per matrix, so one MAX reduction serves both. */
@@ -144,6 +150,8 @@ size_t iwq_fused_workspace_bytes(int n);
 long long iwq_debug_fused_trace(int* n_batches); /* diagnostics: see iwq_host.cu */
 /* dispatch decision for a [rows, cols] matrix under `cfg` (kernel, tile shape; no CUDA call): out = int32[8], see iwq_host.cu */
 int iwq_debug_plan(const iwq_config_t* cfg, int64_t rows, int64_t cols, int32_t* out);
+/* diagnostics: set a tuning knob (the IWQ_* environment variables, name without the prefix in lower case) at run time */
+int iwq_debug_set_knob(const char* name, int value);
 int iwq_fake_quant_per_tensor_fused(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, void* workspace, size_t workspace_bytes,
                                     const iwq_peers_t* peers, int32_t* status, void* stream);
 
@@ -172,6 +180,9 @@ typedef struct iwq_host_matrix {
   void* host_out;     /* may equal host_w                                                    */
   int64_t rows;
   int64_t cols;
+  void* host_scales;  /* optional [G] scales in the weight dtype, HOST memory (G = rows*cols/group | rows): what the module
+                         form stores in `self.scales` (quant_linear.py:924-932, :761-768); NULL = not wanted        */
+  void* host_zeros;   /* optional [G] zero points / mid points, HOST memory; NULL = not wanted                          */
 } iwq_host_matrix_t;
 int iwq_fake_quant_host_batched(const iwq_config_t* cfg, const iwq_host_matrix_t* ms, int n, int device, size_t chunk_bytes,
                                 int32_t* host_status);

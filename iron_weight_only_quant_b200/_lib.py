@@ -30,6 +30,7 @@ EXPORTS = (
     "iwq_workspace_bytes",
     "iwq_fake_quant",
     "iwq_fake_quant_batched",
+    "iwq_fake_quant_per_tensor_batched",
     "iwq_minmax",
     "iwq_fake_quant_with_range",
     "iwq_fp_roundtrip",
@@ -39,6 +40,7 @@ EXPORTS = (
     "iwq_fused_workspace_bytes",
     "iwq_debug_fused_trace",
     "iwq_debug_plan",
+    "iwq_debug_set_knob",
     "iwq_fake_quant_per_tensor_fused",
 )
 
@@ -72,7 +74,7 @@ class Peers(ctypes.Structure):
 class HostMatrix(ctypes.Structure):
     """struct iwq_host_matrix (include/iwq_b200.h)."""
 
-    _fields_ = [("host_w", ctypes.c_void_p), ("host_out", ctypes.c_void_p), ("rows", ctypes.c_int64), ("cols", ctypes.c_int64)]
+    _fields_ = [("host_w", ctypes.c_void_p), ("host_out", ctypes.c_void_p), ("rows", ctypes.c_int64), ("cols", ctypes.c_int64), ("host_scales", ctypes.c_void_p), ("host_zeros", ctypes.c_void_p)]
 
 
 _lib = None
@@ -102,6 +104,8 @@ def lib() -> ctypes.CDLL:
         L.iwq_fake_quant.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(Matrix), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.iwq_fake_quant_batched.restype = ctypes.c_int
         L.iwq_fake_quant_batched.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(Matrix), ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+        L.iwq_fake_quant_per_tensor_batched.restype = ctypes.c_int
+        L.iwq_fake_quant_per_tensor_batched.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(Matrix), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
         L.iwq_minmax.restype = ctypes.c_int
         L.iwq_minmax.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(Matrix), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
         L.iwq_fake_quant_with_range.restype = ctypes.c_int
@@ -114,11 +118,13 @@ def lib() -> ctypes.CDLL:
         L.iwq_fake_quant_host.argtypes = [ctypes.POINTER(Config), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32)]
         L.iwq_fake_quant_host_batched.restype = ctypes.c_int
         L.iwq_fake_quant_host_batched.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(HostMatrix), ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32)]
+        L.iwq_debug_set_knob.restype = ctypes.c_int
+        L.iwq_debug_set_knob.argtypes = [ctypes.c_char_p, ctypes.c_int]
         L.iwq_fused_workspace_bytes.restype = ctypes.c_size_t
         L.iwq_fused_workspace_bytes.argtypes = [ctypes.c_int]
         L.iwq_fake_quant_per_tensor_fused.restype = ctypes.c_int
         L.iwq_fake_quant_per_tensor_fused.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(Matrix), ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(Peers), ctypes.c_void_p, ctypes.c_void_p]
-        if L.iwq_abi_version() != 3:
+        if L.iwq_abi_version() != 4:
             raise RuntimeError("libiwq_b200.so ABI version mismatch")
         _lib = L
     return _lib
@@ -242,6 +248,18 @@ def fake_quant_with_range_(mats: Sequence[Matrix], cfg: Config, device: torch.de
     return status
 
 
+def per_tensor_batched_(mats: Sequence[Matrix], cfg: Config, device: torch.device, rng: torch.Tensor, track_status: bool = True):
+    """Per-tensor granularity for many whole matrices on one GPU: range and apply passes ordered by the library."""
+    n = len(mats)
+    arr = (Matrix * n)(*mats)
+    with torch.cuda.device(device):
+        status, _, ws = scratch(device, n)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        rc = lib().iwq_fake_quant_per_tensor_batched(ctypes.byref(cfg), arr, n, rng.data_ptr(), ws.data_ptr(), ws.numel(), status.data_ptr() if track_status else None, stream)
+    check(rc)
+    return status
+
+
 def read_and_clear_status(device: torch.device) -> int:
     """Synchronising read of the device status word (then reset it)."""
     status, _, _ = scratch(device)
@@ -251,18 +269,34 @@ def read_and_clear_status(device: torch.device) -> int:
     return v
 
 
-def fake_quant_host_(tensors: Sequence[torch.Tensor], cfg: Config, device: int = 0, chunk_bytes: int = 32 << 20) -> int:
+def fake_quant_host_(tensors: Sequence[torch.Tensor], cfg: Config, device: int = 0, chunk_bytes: int = 32 << 20, scales: Optional[Sequence[torch.Tensor]] = None, zeros: Optional[Sequence[torch.Tensor]] = None, copy_only: bool = False) -> int:
     """Fake-quantise 2-D HOST tensors (pinned for full speed) in place through one H2D -> kernel -> D2H chunk
-    pipeline on `device` (iwq_fake_quant_host_batched); synchronises; returns the status word (STATUS_NAN ...)."""
+    pipeline on `device` (iwq_fake_quant_host_batched); synchronises; returns the status word (STATUS_NAN ...).
+    `scales` / `zeros`: optional host tensors (one per matrix, G elements of the weight dtype) that receive the
+    per-segment scales and zero points.  `copy_only` (diagnostics): the same copies without the kernels."""
     ms = []
-    for t in tensors:
+    for i, t in enumerate(tensors):
         if t.is_cuda or t.dim() != 2 or not t.is_contiguous():
             raise ValueError("fake_quant_host_: expected contiguous 2-D host tensors")
         dtype_code(t.dtype)
-        ms.append(HostMatrix(t.data_ptr(), t.data_ptr(), t.shape[0], t.shape[1]))
+        G = num_segments(t.shape[0], t.shape[1], cfg.group)
+        ptrs = []
+        for what, lst in (("scales", scales), ("zeros", zeros)):
+            m = lst[i] if lst is not None else None
+            if m is not None and (m.is_cuda or not m.is_contiguous() or m.dtype != t.dtype or m.numel() < G):
+                raise ValueError(f"fake_quant_host_: {what}[{i}] must be a contiguous host tensor of the weight dtype with >= {G} elements")
+            ptrs.append(None if m is None else m.data_ptr())
+        ms.append(HostMatrix(t.data_ptr(), t.data_ptr(), t.shape[0], t.shape[1], ptrs[0], ptrs[1]))
     arr = (HostMatrix * len(ms))(*ms)
     st = ctypes.c_int32(0)
-    check(lib().iwq_fake_quant_host_batched(ctypes.byref(cfg), arr, len(ms), int(device), int(chunk_bytes), ctypes.byref(st)))
+    if copy_only:
+        check(lib().iwq_debug_set_knob(b"host_copy_only", 1))
+    try:
+        with torch.cuda.device(device):  # the library restores the current device itself; this keeps torch's view in step
+            check(lib().iwq_fake_quant_host_batched(ctypes.byref(cfg), arr, len(ms), int(device), int(chunk_bytes), ctypes.byref(st)))
+    finally:
+        if copy_only:
+            lib().iwq_debug_set_knob(b"host_copy_only", 0)
     return int(st.value)
 
 

@@ -173,6 +173,26 @@ static inline int build_quant_consts(const iwq_config_t* cfg, QuantConsts* c, in
 }
 
 
+// Re-shape the step table of a minifloat launch for `1 << rep_shift` interleaved copies in shared memory (seg4 kernel,
+// FpTable<.., REPL = true>): the table starts at the first pattern that does not quantise to 0 (also for fp16, whose
+// single-copy table starts at pattern 0) and the interval width is capped so that one entry's stride (8 << rep_shift bytes)
+// is a multiple of the interval width in patterns -- the lookup address then is a single multiply-add of the masked
+// pattern.  Narrower intervals still change value at most once each.  rep_shift = 0 restores nothing: call it on fresh consts.
+static inline void set_lut_replication(int dt, QuantConsts* c, int rep_shift) {
+  if (rep_shift <= 0) return;
+  const int MB = dt == IWQ_F16 ? 10 : 7, DB = dt == IWQ_F16 ? 15 : 127;
+  const int E = c->exp_bits, M = c->mant_bits;
+  const int bias = (1 << (E - 1)) - 1, emin = 1 - bias;
+  int llo = emin - M - 1;
+  if (llo + DB < 1) llo = 1 - DB;
+  c->lut_lo_bits = (uint16_t)((llo + DB) << MB);
+  int sh = MB - M - 1;
+  if (sh > 3 + rep_shift) sh = 3 + rep_shift;
+  c->lut_shift = (uint16_t)sh;
+  c->lut_n = (((uint32_t)c->fmax_bits - (uint32_t)c->lut_lo_bits) >> c->lut_shift) + 1u;
+  c->lut_rep_shift = (uint32_t)rep_shift;
+}
+
 // _fp_decode_aligned (quant_linear.py:237-285; align_subnorm_exp_as_one=True, limit_align_exp_to_field=True,
 // decode_dtype = weight dtype, as the driver calls it) for the code of a POSITIVE grid value: the single
 // "approximate" mode only changes which value a code decodes to, so it is folded into the step table.
@@ -201,6 +221,38 @@ static inline uint16_t approx_decode_single(uint16_t vbits, const QuantConsts& c
     v = rD<DT>(a * rD<DT>(ldexpf(1.0f, ef == 0 ? 1 - bias : ef - bias)));
   }
   return DType<DT>::from_f32(v);
+}
+
+// DIRECT table: one value per bit pattern from the first pattern that does not quantise to 0 up to fmax (FpTable<.., LUT_DIRECT>).
+static inline void set_lut_direct(int dt, QuantConsts* c) {
+  const int MB = dt == IWQ_F16 ? 10 : 7, DB = dt == IWQ_F16 ? 15 : 127;
+  const int E = c->exp_bits, M = c->mant_bits;
+  const int bias = (1 << (E - 1)) - 1, emin = 1 - bias;
+  int llo = emin - M - 1;
+  if (llo + DB < 1) llo = 1 - DB;
+  c->lut_lo_bits = (uint16_t)((llo + DB) << MB);
+  c->lut_shift = 0;
+  c->lut_n = (uint32_t)c->fmax_bits - (uint32_t)c->lut_lo_bits + 1u;
+  c->lut_rep_shift = 0;
+  c->lut_direct = 1;
+}
+// values of the direct table: the table-walk quantiser grid() on every pattern (then the single approximate decode, if any)
+template <int DT>
+static inline void build_direct_table_t(const QuantConsts& c, uint16_t* out) {
+  using T2 = typename DType<DT>::T2;
+  FpQ q;
+  q.S = 1.0f; q.r = 1.0f; q.mid = 0.f; q.mid_h = 0.f; q.bad = false; q.slow_div = false;
+  FpTable<DT> f;
+  f.setup(q, c);
+  for (uint32_t i = 0; i < c.lut_n; ++i) {
+    const uint32_t pat = (uint32_t)c.lut_lo_bits + i;
+    uint16_t v = (uint16_t)(as_u32(f.grid(from_u32<T2>(pat | (pat << 16)), 0u, c.tbl)) & 0xFFFFu);
+    if (c.approx == 1) v = approx_decode_single<DT>(v, c);
+    out[i] = v;
+  }
+}
+static inline void build_direct_table(int dtype, const QuantConsts& c, uint16_t* out) {
+  if (dtype == IWQ_F16) build_direct_table_t<IWQ_F16>(c, out); else build_direct_table_t<IWQ_BF16>(c, out);
 }
 
 // Step table (see FpStep): run the table-walk quantiser grid() on every bit pattern of every interval and

@@ -51,11 +51,24 @@ struct Knobs {
   int wide_seg4 = env_int("IWQ_WIDE_SEG4", 1);       // 1: segments of 2048/4096/8192 elements go through seg4_tma_kernel
   int col_mode = env_int("IWQ_COL_MODE", 0);         // 0: warp-private cp.async ring (col_async_kernel), 1: register-resident
   int col_stages = env_int("IWQ_COL_STAGES", 0);     // ring depth of col_async_kernel (1..4); 0 = automatic
+  int pt_slab_mb = env_int("IWQ_PT_SLAB_MB", 0);     // per-tensor: range pass -> apply pass per slab of whole matrices of at most this
+                                                     // many MB (the apply pass then finds the slab in L2); 0 = one range pass over
+                                                     // everything, then one apply pass
+  int pt_reverse = env_int("IWQ_PT_REVERSE", 1);     // per-tensor apply pass walks its tiles from the end (most recently read first)
+  int pt_hint = env_int("IWQ_PT_HINT", 0);           // LaunchParams::l2_hint bits of the per-tensor apply pass
+  int seg_hint = env_int("IWQ_SEG_HINT", 0);         // LaunchParams::l2_hint bits of the one-pass segment kernels
+  int fp_mode = env_int("IWQ_FP_MODE", 2);           // seg4 minifloat kernel: 0 step table, 1 interleaved copies of it, 2 direct table
+  int fp_rep = env_int("IWQ_FP_REP", 4);             // seg4 minifloat kernel: log2 of the interleaved copies of the step table
+                                                     // in shared memory (4 = 16 copies: no bank conflicts); 0 = one copy
+  int fp_rep_kb = env_int("IWQ_FP_REP_KB", 40);      // ... as long as the copies fit this many KB (else fewer copies)
+  int fp_stages = env_int("IWQ_FP_STAGES", 0);       // ring depth of the seg4 minifloat kernel; 0 = IWQ_SEG_STAGES
+  int host_copy_only = env_int("IWQ_HOST_COPY_ONLY", 0);  // diagnostics: the host-buffer pipeline without its kernels (copy ceiling)
 };
-static const Knobs& knobs() {
+static Knobs& knobs_mut() {
   static Knobs k;
   return k;
 }
+static const Knobs& knobs() { return knobs_mut(); }
 
 static int effective_variant(const iwq_config_t* cfg) { return knobs().variant >= 0 ? knobs().variant : cfg->variant; }
 
@@ -70,7 +83,7 @@ static int build_consts(const iwq_config_t* cfg, QuantConsts* c, int* kind) {
 // minifloat LUT cache: one small device buffer per (device, dtype, E, M, flavour), built on first use
 // ------------------------------------------------------------------------------------------------
 static std::mutex g_lut_mu;
-static std::map<std::tuple<int, int, int, int, int, int, int, int, int>, FpStep*> g_luts;
+static std::map<std::tuple<int, int, int, int, int, int, int, int, int, int, int, int>, FpStep*> g_luts;
 
 static int get_fp_lut(const iwq_config_t* cfg, const QuantConsts& qc, cudaStream_t st, const FpStep** out) {
   int dev = 0;
@@ -78,21 +91,24 @@ static int get_fp_lut(const iwq_config_t* cfg, const QuantConsts& qc, cudaStream
   if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
   const bool ap = qc.approx != 0;
   auto key = std::make_tuple(dev, cfg->dtype, cfg->exp_bits, cfg->mant_bits, qc.flavour_rne, qc.approx, ap ? qc.hi_start : 0,
-                             ap ? qc.hi_field : 0, ap ? qc.tail_pad : 0);
+                             ap ? qc.hi_field : 0, ap ? qc.tail_pad : 0, (int)qc.lut_shift, (int)qc.lut_lo_bits, (int)qc.lut_direct);
   std::lock_guard<std::mutex> lk(g_lut_mu);
   auto it = g_luts.find(key);
   if (it != g_luts.end()) {
     *out = it->second;
     return IWQ_OK;
   }
-  if (qc.lut_n > 4096) return fail(IWQ_ERR_UNSUPPORTED, "minifloat step table too large");
+  if (!qc.lut_direct && qc.lut_n > 4096) return fail(IWQ_ERR_UNSUPPORTED, "minifloat step table too large");
   // approx == 2: [step table in info form, padded to 1 KB][value table, 16 KB] (build_double_tables)
   const size_t step_bytes = ((size_t)qc.lut_n * sizeof(FpStep) + 1023) & ~(size_t)1023;
-  const size_t total = qc.approx == 2 ? step_bytes + kDblValEntries * sizeof(uint16_t) : (size_t)qc.lut_n * sizeof(FpStep);
+  const size_t total = qc.lut_direct ? (((size_t)qc.lut_n * 2 + 7) & ~(size_t)7)
+                     : qc.approx == 2 ? step_bytes + kDblValEntries * sizeof(uint16_t) : (size_t)qc.lut_n * sizeof(FpStep);
   std::vector<uint8_t> host(total, 0);
   FpStep* hsteps = reinterpret_cast<FpStep*>(host.data());
-  const bool ok = qc.approx == 2 ? build_double_tables(cfg->dtype, qc, hsteps, reinterpret_cast<uint16_t*>(host.data() + step_bytes))
-                                 : build_step_table(cfg->dtype, qc, hsteps);
+  bool ok = true;
+  if (qc.lut_direct) build_direct_table(cfg->dtype, qc, reinterpret_cast<uint16_t*>(host.data()));
+  else ok = qc.approx == 2 ? build_double_tables(cfg->dtype, qc, hsteps, reinterpret_cast<uint16_t*>(host.data() + step_bytes))
+                           : build_step_table(cfg->dtype, qc, hsteps);
   if (!ok) return fail(IWQ_ERR_UNSUPPORTED, "minifloat format changes value more than once inside a half-step interval");
   FpStep* buf = nullptr;
   e = cudaMalloc((void**)&buf, total);
@@ -352,18 +368,21 @@ static int upload_jobs(const std::vector<Job>& jobs, void* workspace, size_t ws_
   return IWQ_OK;
 }
 
-static int run_minmax(const iwq_config_t* cfg, const LaunchParams& base, float* range, cudaStream_t st) {
+static int run_minmax(const iwq_config_t* cfg, const LaunchParams& base, float* range, cudaStream_t st, bool init = true, bool strided = false) {
   LaunchParams p = base;
   p.ranges_out = range;
-  const int n2 = 2 * p.n_jobs;
-  range_init_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(range, n2);
+  p.l2_hint = strided ? 8u : 0u;
+  if (init) {
+    const int n2 = 2 * p.n_jobs;
+    range_init_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(range, n2);
+  }
   int grid = 0;
   cudaError_t e;
   const bool sym = p.qc.symmetric != 0;
 #define IWQ_MM(DT, SYM)                                                                \
   do {                                                                                 \
     auto k = minmax_kernel<DT, SYM>;                                                   \
-    e = persistent_grid(k, kConsumers, 0, 0, p.total_units, &grid);                    \
+    e = persistent_grid(k, kConsumers, 0, 0, p.total_units - p.unit_begin, &grid);     \
     if (e == cudaSuccess) {                                                            \
       k<<<grid, kConsumers, 0, st>>>(p);                                               \
       e = cudaGetLastError();                                                          \
@@ -387,11 +406,17 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
   int kind = 0;
   int rc = build_consts(cfg, &p.qc, &kind);
   if (rc) return rc;
-  if (kind == KIND_FP) {
-    rc = get_fp_lut(cfg, p.qc, st, &p.lut);
-    if (rc) return rc;
-    p.lut_smem_bytes = (uint32_t)(((size_t)p.qc.lut_n * sizeof(FpStep) + 1023) & ~(size_t)1023);
+  auto bind_lut = [&]() -> int {  // (re)build / fetch the device step table for the current p.qc
+    int r = get_fp_lut(cfg, p.qc, st, &p.lut);
+    if (r) return r;
+    p.lut_smem_bytes = p.qc.lut_direct ? (uint32_t)(((size_t)p.qc.lut_n * 2 + 1023) & ~(size_t)1023)
+                                       : (uint32_t)((((size_t)p.qc.lut_n * sizeof(FpStep)) << p.qc.lut_rep_shift) + 1023) & ~(uint32_t)1023;
     p.lut_extra_bytes = p.qc.approx == 2 ? (uint32_t)(kDblValEntries * sizeof(uint16_t)) : 0u;
+    return IWQ_OK;
+  };
+  if (kind == KIND_FP) {
+    rc = bind_lut();
+    if (rc) return rc;
   }
   if (p.qc.approx == 2 && cfg->quant_dim != 1)
     return fail(IWQ_ERR_UNSUPPORTED, "double-approximate decode is implemented for quant_dim = 1 only (what the reference's scripts use)");
@@ -431,21 +456,79 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
   if (variant == 0 && pl.path == PATH_SEG) {
     p.lps = per_tensor ? 1 : (int)(pl.seg_elems / 32);
     p.vpl = 1;
+    if (kind == KIND_FP && knobs().fp_mode == 2 && p.qc.approx != 2) {
+      // seg4 minifloat kernel, DIRECT table: one 16-bit value per bit pattern (2 loads + 1 pack per pair instead of
+      // 2 loads + 3 packs + compare + select), as long as it fits the shared-memory budget
+      QuantConsts q = p.qc;
+      set_lut_direct(cfg->dtype, &q);
+      if ((size_t)q.lut_n * 2 <= (size_t)knobs().fp_rep_kb * 1024) {
+        p.qc = q;
+        rc = bind_lut();
+        if (rc) return rc;
+      }
+      if (knobs().fp_stages >= 2) tune.stages = p.n_stages = knobs().fp_stages > kMaxStages ? kMaxStages : knobs().fp_stages;
+    } else if (kind == KIND_FP && knobs().fp_mode == 1 && knobs().fp_rep > 0) {
+      // seg4 minifloat kernel: interleaved copies of the step table (no shared-memory bank conflicts in the lookups)
+      const QuantConsts base = p.qc;
+      for (int rs = knobs().fp_rep > 4 ? 4 : knobs().fp_rep; rs > 0; --rs) {
+        QuantConsts q = base;
+        set_lut_replication(cfg->dtype, &q, rs);
+        if ((((size_t)q.lut_n * sizeof(FpStep)) << rs) <= (size_t)knobs().fp_rep_kb * 1024) {
+          p.qc = q;
+          break;
+        }
+      }
+      if (p.qc.lut_rep_shift > 0) {
+        rc = bind_lut();
+        if (rc) return rc;
+      }
+      if (knobs().fp_stages >= 2) tune.stages = p.n_stages = knobs().fp_stages > kMaxStages ? kMaxStages : knobs().fp_stages;
+    }
   }
   if (per_tensor) {
     const float* rng = given_range;
-    if (!rng) {
-      if (!range_ws) return fail(IWQ_ERR_INVALID, "per-tensor granularity needs a device range buffer of 2 floats per matrix");
-      rc = run_minmax(cfg, p, range_ws, st);
-      if (rc) return rc;
-      rng = range_ws;
-    }
-    if (minmax_only) return IWQ_OK;
-    p.ranges = rng;
+    if (!rng && !range_ws) return fail(IWQ_ERR_INVALID, "per-tensor granularity needs a device range buffer of 2 floats per matrix");
     tune.ctas_per_sm = knobs().seg_ctas;
-    e = dispatch_seg(cfg->dtype, kind, p, sym, true, variant, tune, st);
+    const bool seg4 = variant == 0;
+    if (!rng && !minmax_only && seg4 && knobs().pt_slab_mb > 0) {
+      // SLAB ORDER: range pass and apply pass alternate over slabs of whole matrices that fit L2, so that the apply pass
+      // finds its slab in L2 (4 B/weight of HBM traffic instead of 6); a matrix larger than the slab is a slab of its own
+      // (its apply pass still starts with the tiles the range pass read last).  quant_linear.py:898-900
+      const uint64_t slab_bytes = (uint64_t)knobs().pt_slab_mb << 20;
+      const uint32_t end_units = p.total_units;
+      const int n2 = 2 * n;
+      range_init_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(range_ws, n2);
+      p.ranges = range_ws;
+      e = cudaSuccess;
+      for (int j0 = 0; j0 < n && e == cudaSuccess;) {
+        int j1 = j0 + 1;
+        uint64_t acc = jobs[j0].bytes;
+        while (j1 < n && acc + jobs[j1].bytes <= slab_bytes) acc += jobs[j1++].bytes;
+        p.unit_begin = jobs[j0].first_unit;
+        p.total_units = j1 < n ? jobs[j1].first_unit : end_units;
+        p.reverse = 0;
+        rc = run_minmax(cfg, p, range_ws, st, false, true);
+        if (rc) return rc;
+        p.reverse = 1;
+        p.l2_hint = (uint32_t)knobs().pt_hint & 7u;
+        e = dispatch_seg(cfg->dtype, kind, p, sym, true, variant, tune, st);
+        j0 = j1;
+      }
+    } else {
+      if (!rng) {
+        rc = run_minmax(cfg, p, range_ws, st);
+        if (rc) return rc;
+        rng = range_ws;
+      }
+      if (minmax_only) return IWQ_OK;
+      p.ranges = rng;
+      p.reverse = (seg4 && knobs().pt_reverse != 0) ? 1u : 0u;
+      p.l2_hint = (uint32_t)knobs().pt_hint & 7u;
+      e = dispatch_seg(cfg->dtype, kind, p, sym, true, variant, tune, st);
+    }
   } else if (pl.path == PATH_SEG) {
     tune.ctas_per_sm = knobs().seg_ctas;
+    p.l2_hint = (uint32_t)knobs().seg_hint & 7u;
     e = dispatch_seg(cfg->dtype, kind, p, sym, false, variant, tune, st);
   } else {
     tune.ctas_per_sm = knobs().row_ctas;
@@ -647,6 +730,25 @@ int iwq_debug_plan(const iwq_config_t* cfg, int64_t rows, int64_t cols, int32_t*
   return IWQ_OK;
 }
 const char* iwq_last_error(void) { return g_err.c_str(); }
+
+// Tuning knobs are read from the environment once (IWQ_*); this sets one at run time so that a sweep can run inside one
+// process (tools/sweep_r2.py).  `name` is the environment variable's name without the IWQ_ prefix, lower case.
+int iwq_debug_set_knob(const char* name, int value) {
+  if (!name) return fail(IWQ_ERR_INVALID, "null knob name");
+  Knobs& k = knobs_mut();
+  const std::string n(name);
+#define IWQ_KNOB(field)   \
+  if (n == #field) {      \
+    k.field = value;      \
+    return IWQ_OK;        \
+  }
+  IWQ_KNOB(seg_stages) IWQ_KNOB(seg_ctas) IWQ_KNOB(row_ctas) IWQ_KNOB(row_smem_kb) IWQ_KNOB(variant) IWQ_KNOB(row_warps) IWQ_KNOB(col_tile)
+  IWQ_KNOB(col_ctas) IWQ_KNOB(fused_batch_mb) IWQ_KNOB(fused_lookahead) IWQ_KNOB(row_tma_out) IWQ_KNOB(wide_seg4) IWQ_KNOB(col_mode)
+  IWQ_KNOB(col_stages) IWQ_KNOB(pt_slab_mb) IWQ_KNOB(pt_reverse) IWQ_KNOB(pt_hint) IWQ_KNOB(seg_hint) IWQ_KNOB(fp_mode) IWQ_KNOB(fp_rep) IWQ_KNOB(fp_rep_kb)
+  IWQ_KNOB(fp_stages) IWQ_KNOB(host_copy_only)
+#undef IWQ_KNOB
+  return fail(IWQ_ERR_INVALID, "unknown knob: " + n);
+}
 size_t iwq_workspace_bytes(int n) { return (size_t)(n < 1 ? 1 : n) * sizeof(Job); }
 
 int iwq_fake_quant(const iwq_config_t* cfg, const iwq_matrix_t* m, float* range_ws, int32_t* status, void* stream) {
@@ -658,6 +760,13 @@ int iwq_fake_quant_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int 
   if (cfg && cfg->group == IWQ_GROUP_PER_TENSOR)
     return fail(IWQ_ERR_INVALID, "per-tensor granularity: use iwq_minmax + iwq_fake_quant_with_range (or iwq_fake_quant per matrix)");
   return run_batched(cfg, ms, n, workspace, workspace_bytes, nullptr, nullptr, status, (cudaStream_t)stream, false);
+}
+
+int iwq_fake_quant_per_tensor_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, float* range, void* workspace, size_t workspace_bytes,
+                                      int32_t* status, void* stream) {
+  if (!cfg || cfg->group != IWQ_GROUP_PER_TENSOR) return fail(IWQ_ERR_INVALID, "iwq_fake_quant_per_tensor_batched is for per-tensor granularity");
+  if (!range) return fail(IWQ_ERR_INVALID, "null range buffer");
+  return run_batched(cfg, ms, n, workspace, workspace_bytes, nullptr, range, status, (cudaStream_t)stream, false);
 }
 
 int iwq_minmax(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, float* range, void* workspace, size_t workspace_bytes, void* stream) {
@@ -846,64 +955,108 @@ int iwq_selftest_division(int dtype, unsigned long long* mismatches, void* strea
 // One chunk pipeline over ALL matrices of the call: chunk i goes through staging buffer / stream i % kBuf
 // (H2D -> kernel -> D2H in stream order), so the H2D of later chunks overlaps the D2H of earlier ones on the two
 // copy engines and the ring is drained only once, at the end of the call -- not once per matrix.
+namespace {
+struct DeviceGuard {  // restores the caller's current device on every exit path
+  int prev = -1;
+  bool armed = false;
+  cudaError_t enter(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return e;
+    armed = true;
+    return prev == device ? cudaSuccess : cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    if (armed) cudaSetDevice(prev);
+  }
+};
+}  // namespace
+
 static int host_pipeline(const iwq_config_t* cfg, const iwq_host_matrix_t* ms, int n, int device, size_t chunk_bytes, int32_t* host_status) {
   if (!cfg || !ms || n < 1) return fail(IWQ_ERR_INVALID, "null argument");
   if (cfg->group == IWQ_GROUP_PER_TENSOR) return fail(IWQ_ERR_UNSUPPORTED, "host pipeline: per-tensor granularity needs the whole matrix on the device");
   if (cfg->quant_dim != 0) return fail(IWQ_ERR_UNSUPPORTED, "host pipeline: quant_dim = 1 needs whole columns on the device");
   if (device < 0 || device >= 16) return fail(IWQ_ERR_INVALID, "device ordinal out of range");
   if (chunk_bytes == 0) chunk_bytes = 32ull << 20;
-  size_t max_chunk = 0;
+  auto rows_per_chunk = [&](const iwq_host_matrix_t& m) {
+    const size_t row_bytes = (size_t)m.cols * 2;
+    int64_t r = (int64_t)(chunk_bytes / row_bytes);
+    if (r < 1) r = 1;
+    if (row_bytes % 16 != 0) r = (r + 7) / 8 * 8;  // keep chunk starts 16-byte aligned
+    return r > m.rows ? m.rows : r;
+  };
+  auto segs_per_row = [&](const iwq_host_matrix_t& m) -> int64_t { return cfg->group > 0 ? m.cols / cfg->group : 1; };
+  size_t max_chunk = 0, max_meta = 0;
+  bool want_meta = false;
   for (int i = 0; i < n; ++i) {
     if (!ms[i].host_w || !ms[i].host_out) return fail(IWQ_ERR_INVALID, "null host pointer");
     if (ms[i].rows <= 0 || ms[i].cols <= 0) return fail(IWQ_ERR_INVALID, "rows and cols must be positive");
     if (cfg->group > 0 && ms[i].cols % cfg->group != 0) return fail(IWQ_ERR_INDIVISIBLE, "cols is not divisible by the group size");
-    const size_t row_bytes = (size_t)ms[i].cols * 2;
-    int64_t chunk_rows = (int64_t)(chunk_bytes / row_bytes);
-    if (chunk_rows < 1) chunk_rows = 1;
-    if (row_bytes % 16 != 0) chunk_rows = (chunk_rows + 7) / 8 * 8;  // keep chunk starts 16-byte aligned
-    if (chunk_rows > ms[i].rows) chunk_rows = ms[i].rows;
-    if ((size_t)chunk_rows * row_bytes > max_chunk) max_chunk = (size_t)chunk_rows * row_bytes;
+    const int64_t cr = rows_per_chunk(ms[i]);
+    const size_t bytes = (size_t)cr * (size_t)ms[i].cols * 2;
+    if (bytes > max_chunk) max_chunk = bytes;
+    if (ms[i].host_scales || ms[i].host_zeros) {
+      want_meta = true;
+      const size_t mb = ((size_t)(cr * segs_per_row(ms[i])) * 2 + 255) & ~(size_t)255;
+      if (mb > max_meta) max_meta = mb;
+    }
   }
-  cudaError_t e = cudaSetDevice(device);
+  DeviceGuard guard;
+  cudaError_t e = guard.enter(device);
   if (e != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
   std::lock_guard<std::mutex> lk(g_pipe_mu);
   HostPipe* hp = &g_pipes[device];
-  int rc = pipe_prepare(hp, device, max_chunk);
+  // staging: [weights chunk | scales of the chunk | zero points of the chunk] per ring slot
+  const size_t slot_bytes = ((max_chunk + 255) & ~(size_t)255) + (want_meta ? 2 * max_meta : 0);
+  int rc = pipe_prepare(hp, device, slot_bytes);
   if (rc) return rc;
+  const size_t meta_off = (max_chunk + 255) & ~(size_t)255;
   e = cudaMemsetAsync(hp->status, 0, sizeof(int32_t), hp->stream[0]);
   if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
   e = cudaStreamSynchronize(hp->stream[0]);
   if (e != cudaSuccess) return fail_cuda(e, "cudaStreamSynchronize");
+  // on any error below: let the queued copies / kernels finish before returning -- D2H copies still in flight would
+  // otherwise keep writing into the caller's buffers after the error return
+  auto drain = [&]() {
+    for (int b = 0; b < HostPipe::kBuf; ++b) cudaStreamSynchronize(hp->stream[b]);
+  };
+  const bool copy_only = knobs().host_copy_only != 0;  // diagnostics: the same copies without the kernels
   int ci = 0;
   for (int i = 0; i < n; ++i) {
     const int64_t rows = ms[i].rows, cols = ms[i].cols;
     const size_t row_bytes = (size_t)cols * 2;
-    int64_t chunk_rows = (int64_t)(chunk_bytes / row_bytes);
-    if (chunk_rows < 1) chunk_rows = 1;
-    if (row_bytes % 16 != 0) chunk_rows = (chunk_rows + 7) / 8 * 8;
-    if (chunk_rows > rows) chunk_rows = rows;
+    const int64_t chunk_rows = rows_per_chunk(ms[i]), spr = segs_per_row(ms[i]);
     for (int64_t r0 = 0; r0 < rows; r0 += chunk_rows, ++ci) {
       const int64_t nr = rows - r0 < chunk_rows ? rows - r0 : chunk_rows;
       const size_t bytes = (size_t)nr * row_bytes;
       const int b = ci % HostPipe::kBuf;
       cudaStream_t st = hp->stream[b];
-      e = cudaMemcpyAsync(hp->buf[b], (const uint8_t*)ms[i].host_w + (size_t)r0 * row_bytes, bytes, cudaMemcpyHostToDevice, st);
-      if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(H2D)");
+      uint8_t* dbuf = (uint8_t*)hp->buf[b];
+      e = cudaMemcpyAsync(dbuf, (const uint8_t*)ms[i].host_w + (size_t)r0 * row_bytes, bytes, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) { drain(); return fail_cuda(e, "cudaMemcpyAsync(H2D)"); }
       iwq_matrix_t m;
       memset(&m, 0, sizeof(m));
-      m.w = hp->buf[b];
-      m.out = hp->buf[b];
+      m.w = dbuf;
+      m.out = dbuf;
       m.rows = nr;
       m.cols = cols;
-      rc = run_batched(cfg, &m, 1, nullptr, 0, nullptr, nullptr, hp->status, st, false);
-      if (rc) return rc;
-      e = cudaMemcpyAsync((uint8_t*)ms[i].host_out + (size_t)r0 * row_bytes, hp->buf[b], bytes, cudaMemcpyDeviceToHost, st);
-      if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(D2H)");
+      if (ms[i].host_scales) m.scales = dbuf + meta_off;
+      if (ms[i].host_zeros) m.zeros = dbuf + meta_off + max_meta;
+      if (!copy_only) {
+        rc = run_batched(cfg, &m, 1, nullptr, 0, nullptr, nullptr, hp->status, st, false);
+        if (rc) { drain(); return rc; }
+      }
+      e = cudaMemcpyAsync((uint8_t*)ms[i].host_out + (size_t)r0 * row_bytes, dbuf, bytes, cudaMemcpyDeviceToHost, st);
+      const size_t meta_bytes = (size_t)(nr * spr) * 2, meta_at = (size_t)(r0 * spr) * 2;
+      if (e == cudaSuccess && ms[i].host_scales)
+        e = cudaMemcpyAsync((uint8_t*)ms[i].host_scales + meta_at, dbuf + meta_off, meta_bytes, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess && ms[i].host_zeros)
+        e = cudaMemcpyAsync((uint8_t*)ms[i].host_zeros + meta_at, dbuf + meta_off + max_meta, meta_bytes, cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) { drain(); return fail_cuda(e, "cudaMemcpyAsync(D2H)"); }
     }
   }
   for (int b = 0; b < HostPipe::kBuf; ++b) {
     e = cudaStreamSynchronize(hp->stream[b]);
-    if (e != cudaSuccess) return fail_cuda(e, "cudaStreamSynchronize");
+    if (e != cudaSuccess) { drain(); return fail_cuda(e, "cudaStreamSynchronize"); }
   }
   e = cudaMemcpy(hp->status_host, hp->status, sizeof(int32_t), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpy(status)");
@@ -914,6 +1067,7 @@ static int host_pipeline(const iwq_config_t* cfg, const iwq_host_matrix_t* ms, i
 int iwq_fake_quant_host(const iwq_config_t* cfg, const void* host_w, void* host_out, int64_t rows, int64_t cols, int device,
                         size_t chunk_bytes, int32_t* host_status) {
   iwq_host_matrix_t m;
+  memset(&m, 0, sizeof(m));
   m.host_w = host_w;
   m.host_out = host_out;
   m.rows = rows;

@@ -69,6 +69,11 @@ struct LaunchParams {
   uint32_t col_group;      // quant_dim = 1: rows per segment (0: the whole column, i.e. per-channel)
   uint32_t col_tile;       // col_reg_kernel: columns per tile (64 / 128 / 256), 0 = col_kernel
   uint32_t col_rpl;        // col_reg_kernel: vectors (rows) per lane = col_group * (col_tile / 64) / 32
+  uint32_t unit_begin;     // first unit of this launch (a launch may cover a SLAB [unit_begin, total_units) of the work list)
+  uint32_t reverse;        // seg4 / GIVEN: walk the slab's tiles from its end (per-tensor apply pass: the tiles the range pass
+                           // read last are still in L2)
+  uint32_t l2_hint;        // bit 0: bulk loads evict_first, bit 1: bulk loads evict_last, bit 2: bulk stores evict_first,
+                           // bit 3: minmax kernel walks tiles strided (blockIdx.x + k * gridDim.x) instead of in contiguous runs
   QuantConsts qc;
 };
 
@@ -131,6 +136,10 @@ __device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gme
 // shared::cta -> global bulk store (SASS: UBLKCP), tracked by the thread's bulk async-group
 __device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d_hint(void* gmem_dst, const void* smem_src, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy)
+               : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -290,10 +299,10 @@ struct Prepared<DT, KIND_INT_GENERIC> {
   }
 };
 
-template <int DT>
-struct Prepared<DT, KIND_FP> {
+template <int DT, int LUT>
+struct PreparedFp {
   using T2 = typename DType<DT>::T2;
-  FpTable<DT> f;
+  FpTable<DT, false, LUT> f;
   float scale, zero;
   bool bad;
   __device__ __forceinline__ void setup(float mx, float mn, const QuantConsts& c, bool /*sym*/, const FpStep* steps) {
@@ -331,6 +340,9 @@ struct Prepared<DT, KIND_FP> {
     return o;
   }
 };
+
+template <int DT>
+struct Prepared<DT, KIND_FP> : PreparedFp<DT, LUT_STEP> {};
 
 template <int DT>
 struct Prepared<DT, KIND_BFP> {
@@ -382,6 +394,7 @@ __device__ __forceinline__ void advance_job(const LaunchParams& p, uint32_t unit
     j = lo;
   }
   while (j + 1 < p.n_jobs && unit >= jobs[j + 1].first_unit) ++j;
+  while (j > 0 && unit < jobs[j].first_unit) --j;  // reverse walks (per-tensor apply pass) step backwards
   if (j != *cur) {
     *cur = j;
     *jb = jobs[j];
@@ -465,7 +478,12 @@ __device__ __forceinline__ void consume_tile(uint4 (&v)[kVPT], const TileCtx& t,
 __device__ __forceinline__ const FpStep* load_fp_lut(const LaunchParams& p, uint8_t* s_lut) {
   const uint2* g = reinterpret_cast<const uint2*>(p.lut);
   uint2* s = reinterpret_cast<uint2*>(s_lut);
-  for (uint32_t i = threadIdx.x; i < p.qc.lut_n; i += blockDim.x) s[i] = g[i];
+  const uint32_t rs = p.qc.lut_rep_shift;  // interleaved copies: entry i of copy r at [i][r]
+  if (p.qc.lut_direct) {                   // direct table: lut_n 16-bit values (device buffer padded to 8 bytes)
+    for (uint32_t i = threadIdx.x; i < (p.qc.lut_n * 2u + 7u) / 8u; i += blockDim.x) s[i] = g[i];
+    return reinterpret_cast<const FpStep*>(s_lut);
+  }
+  for (uint32_t i = threadIdx.x; i < (p.qc.lut_n << rs); i += blockDim.x) s[i] = g[i >> rs];
   if (p.lut_extra_bytes) {
     const uint32_t o = p.lut_smem_bytes / 8u, n = p.lut_extra_bytes / 8u;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s[o + i] = g[o + i];
@@ -504,7 +522,7 @@ __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_c
       int stage = 0, cur = -1;
       uint32_t phase = 0;
       Job jb;
-      for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+      for (uint32_t tile = p.unit_begin + blockIdx.x; tile < p.total_units; tile += gridDim.x) {
         mbar_wait(&empty[stage], phase ^ 1u);
         advance_job(p, tile, &cur, &jb);
         const TileCtx t = make_tile_ctx(p, jb, cur, tile, GIVEN);
@@ -522,7 +540,7 @@ __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_c
     // ---------------- consumers ----------------
     int stage = 0;
     uint32_t phase = 0;
-    for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+    for (uint32_t tile = p.unit_begin + blockIdx.x; tile < p.total_units; tile += gridDim.x) {
       mbar_wait(&full[stage], phase);
       const TileCtx t = ctx[stage];
       const uint8_t* sbase = data + (size_t)stage * kTileBytes + (size_t)warp * (32 * kVPT * 16) + lane * 16;
@@ -560,7 +578,7 @@ __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_c
 // ------------------------------------------------------------------------------------------------
 // One lane's share of a tile in seg4_tma_kernel: four vectors through registers, results back to the stage.
 // FAST = full 16 KB tile and no code emission: no per-vector predicates at all.
-template <int DT, int KIND, bool SYM, bool GIVEN, bool FAST>
+template <int DT, int KIND, bool SYM, bool GIVEN, bool FAST, int LUT = LUT_STEP>
 __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParams& p, const FpStep* s_tbl, uint8_t* lbase, uint32_t lane_vec,
                                              uint32_t rot, int lane, int lps, int warp, uint32_t* xchg) {
   uint4 v[4];
@@ -569,7 +587,7 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
     const uint32_t j = (k + rot) & 3u;
     v[k] = (FAST || lane_vec + j < t.n_vec) ? lds128(lbase + j * 16) : make_uint4(0u, 0u, 0u, 0u);
   }
-  Prepared<DT, KIND> prep;
+  typename std::conditional<LUT != LUT_STEP && KIND == KIND_FP, PreparedFp<DT, LUT>, Prepared<DT, KIND>>::type prep;
   if (GIVEN) {
     prep.setup(t.given_mx, t.given_mn, p.qc, SYM, s_tbl);
   } else {
@@ -628,7 +646,7 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
   }
 }
 
-template <int DT, int KIND, bool SYM, bool GIVEN>
+template <int DT, int KIND, bool SYM, bool GIVEN, int LUT = LUT_STEP>
 __global__ void __launch_bounds__(kConsumers + 32, 3) seg4_tma_kernel(const __grid_constant__ LaunchParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -654,14 +672,18 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) seg4_tma_kernel(const __gr
       int stage = 0, cur = -1;
       uint32_t phase = 0;
       Job jb;
-      for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+      const uint32_t hint = p.l2_hint & 3u;
+      const uint64_t pol = hint == 1u ? l2_policy_evict_first() : (hint == 2u ? l2_policy_evict_last() : 0ull);
+      for (uint32_t seq = p.unit_begin + blockIdx.x; seq < p.total_units; seq += gridDim.x) {
+        const uint32_t tile = p.reverse ? p.total_units - 1u - (seq - p.unit_begin) : seq;
         mbar_wait(&empty[stage], phase ^ 1u);
         advance_job(p, tile, &cur, &jb);
         const TileCtx t = make_tile_ctx(p, jb, cur, tile, GIVEN);
         ctx[stage] = t;
         const uint32_t bytes = t.n_vec * 16u;
         mbar_arrive_expect_tx(&full[stage], bytes);
-        tma_load_1d(data + (size_t)stage * kTileBytes, jb.src + (t.vec0 << 4), bytes, &full[stage]);
+        if (hint) tma_load_1d_hint(data + (size_t)stage * kTileBytes, jb.src + (t.vec0 << 4), bytes, &full[stage], pol);
+        else tma_load_1d(data + (size_t)stage * kTileBytes, jb.src + (t.vec0 << 4), bytes, &full[stage]);
         if (++stage == n_stages) {
           stage = 0;
           phase ^= 1u;
@@ -675,24 +697,27 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) seg4_tma_kernel(const __gr
   const int lps = p.lps;                      // lanes per segment = group / 32 (1..32); unused when GIVEN
   const uint32_t lane_vec = (uint32_t)warp * 128u + (uint32_t)lane * 4u;  // first vector of this lane in the tile
   const uint32_t rot = (uint32_t)lane >> 1;
+  const bool store_hint = (p.l2_hint & 4u) != 0;
+  const uint64_t store_pol = l2_policy_evict_first();
   int stage = 0, prev_stage = -1;
   uint32_t phase = 0;
-  for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+  for (uint32_t tile = p.unit_begin + blockIdx.x; tile < p.total_units; tile += gridDim.x) {
     mbar_wait(&full[stage], phase);
     const TileCtx t = ctx[stage];
     uint8_t* lbase = data + (size_t)stage * kTileBytes + (size_t)lane_vec * 16;
     uint32_t* xchg = reinterpret_cast<uint32_t*>(smem + 640) + stage * kConsumerWarps;  // [stage][warp] range slots
     if (t.n_vec == (uint32_t)(kTileBytes / 16) && t.codes == nullptr)
-      seg4_consume<DT, KIND, SYM, GIVEN, true>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps, warp, xchg);
+      seg4_consume<DT, KIND, SYM, GIVEN, true, LUT>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps, warp, xchg);
     else
-      seg4_consume<DT, KIND, SYM, GIVEN, false>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps, warp, xchg);
+      seg4_consume<DT, KIND, SYM, GIVEN, false, LUT>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps, warp, xchg);
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
       const uint32_t w0 = (uint32_t)warp * 128u;
       if (w0 < t.n_vec) {
         const uint32_t nv = t.n_vec - w0 < 128u ? t.n_vec - w0 : 128u;
-        tma_store_1d(t.dst + (size_t)w0 * 16, data + (size_t)stage * kTileBytes + (size_t)w0 * 16, nv * 16u);
+        if (store_hint) tma_store_1d_hint(t.dst + (size_t)w0 * 16, data + (size_t)stage * kTileBytes + (size_t)w0 * 16, nv * 16u, store_pol);
+        else tma_store_1d(t.dst + (size_t)w0 * 16, data + (size_t)stage * kTileBytes + (size_t)w0 * 16, nv * 16u);
       }
       tma_store_commit();
       tma_store_wait_read<1>();                       // the previous tile's store no longer reads its stage
@@ -721,7 +746,7 @@ __global__ void __launch_bounds__(kConsumers) seg_direct_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int cur = -1;
   Job jb;
-  for (uint32_t tile = blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+  for (uint32_t tile = p.unit_begin + blockIdx.x; tile < p.total_units; tile += gridDim.x) {
     advance_job(p, tile, &cur, &jb);
     const TileCtx t = make_tile_ctx(p, jb, cur, tile, GIVEN);
     const uint8_t* gbase = jb.src + (t.vec0 << 4);
@@ -1632,10 +1657,14 @@ __global__ void __launch_bounds__(kConsumers) minmax_kernel(const __grid_constan
   // few matrix boundaries inside it, so the block reduction + atomics (flush) run once per (CTA, matrix) instead
   // of once per tile -- with the small shards of the 8-GPU per-tensor configuration (4..16 MB per matrix) a
   // strided assignment flushed on nearly every tile
-  const uint32_t per = (p.total_units + gridDim.x - 1) / gridDim.x;
-  const uint32_t t_begin = blockIdx.x * per;
-  const uint32_t t_end = t_begin + per < p.total_units ? t_begin + per : p.total_units;
-  for (uint32_t tile = t_begin; tile < t_end; ++tile) {
+  const bool strided = (p.l2_hint & 8u) != 0;  // slab mode: one matrix per launch, walk it like the apply pass does
+  const uint32_t n_units = p.total_units - p.unit_begin;
+  const uint32_t per = (n_units + gridDim.x - 1) / gridDim.x;
+  const uint32_t t_begin = p.unit_begin + (strided ? blockIdx.x : blockIdx.x * per);
+  const uint32_t t_stop = p.unit_begin + blockIdx.x * per + per;
+  const uint32_t t_end = strided ? p.total_units : (t_stop < p.total_units ? t_stop : p.total_units);
+  const uint32_t t_step = strided ? gridDim.x : 1u;
+  for (uint32_t tile = t_begin; tile < t_end; tile += t_step) {
     advance_job(p, tile, &cur, &jb);
     if (cur != acc_job) {
       if (acc_job >= 0) flush(acc_job);  // block-uniform: every thread sees the same tile sequence

@@ -156,19 +156,31 @@ static cudaError_t launch_seg_one(LaunchParams p, int variant, const LaunchTunin
   if (variant == 1) {
     auto k = seg_direct_kernel<DT, KIND, SYM, GIVEN>;
     const size_t smem = p.lut_smem_bytes;
-    cudaError_t e = persistent_grid(k, kConsumers, smem, tune.ctas_per_sm, p.total_units, &grid);
+    cudaError_t e = persistent_grid(k, kConsumers, smem, tune.ctas_per_sm, p.total_units - p.unit_begin, &grid);
     if (e != cudaSuccess) return e;
     k<<<grid, kConsumers, smem, st>>>(p);
+  } else if (variant == 0 && KIND == KIND_FP && p.qc.lut_direct) {
+    auto k = seg4_tma_kernel<DT, KIND, SYM, GIVEN, KIND == KIND_FP ? LUT_DIRECT : LUT_STEP>;  // one value per bit pattern
+    const size_t smem = kSmemHeader + p.lut_smem_bytes + (size_t)p.n_stages * kTileBytes;
+    cudaError_t e = persistent_grid(k, kConsumers + 32, smem, tune.ctas_per_sm, p.total_units - p.unit_begin, &grid);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kConsumers + 32, smem, st>>>(p);
+  } else if (variant == 0 && KIND == KIND_FP && p.qc.lut_rep_shift > 0) {
+    auto k = seg4_tma_kernel<DT, KIND, SYM, GIVEN, KIND == KIND_FP ? LUT_REPL : LUT_STEP>;  // interleaved copies of the step table
+    const size_t smem = kSmemHeader + p.lut_smem_bytes + (size_t)p.n_stages * kTileBytes;
+    cudaError_t e = persistent_grid(k, kConsumers + 32, smem, tune.ctas_per_sm, p.total_units - p.unit_begin, &grid);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kConsumers + 32, smem, st>>>(p);
   } else if (variant == 0) {
     auto k = seg4_tma_kernel<DT, KIND, SYM, GIVEN>;
     const size_t smem = kSmemHeader + p.lut_smem_bytes + (size_t)p.n_stages * kTileBytes;
-    cudaError_t e = persistent_grid(k, kConsumers + 32, smem, tune.ctas_per_sm, p.total_units, &grid);
+    cudaError_t e = persistent_grid(k, kConsumers + 32, smem, tune.ctas_per_sm, p.total_units - p.unit_begin, &grid);
     if (e != cudaSuccess) return e;
     k<<<grid, kConsumers + 32, smem, st>>>(p);
   } else {
     auto k = seg_tma_kernel<DT, KIND, SYM, GIVEN>;
     const size_t smem = kSmemHeader + p.lut_smem_bytes + (size_t)p.n_stages * kTileBytes;
-    cudaError_t e = persistent_grid(k, kConsumers + 32, smem, tune.ctas_per_sm, p.total_units, &grid);
+    cudaError_t e = persistent_grid(k, kConsumers + 32, smem, tune.ctas_per_sm, p.total_units - p.unit_begin, &grid);
     if (e != cudaSuccess) return e;
     k<<<grid, kConsumers + 32, smem, st>>>(p);
   }

@@ -249,6 +249,11 @@ struct QuantConsts {
   uint16_t lut_lo_bits;    // D bits of 2^(emin-M-1): everything at or below it quantises to 0 (exact tie -> even)
   uint16_t lut_shift;      // log2 of the interval width W = 2^(mantissa_bits(D) - M - 1) bit patterns (half a grid step)
   uint32_t lut_n;          // number of FpStep intervals covering bit patterns lut_lo_bits .. fmax_bits
+  uint32_t lut_rep_shift;  // log2 of the number of interleaved copies of the step table in shared memory (seg4 kernel: 16
+                           // copies, entry i of copy r at [i][r], so that the lanes of a half-warp hit 16 distinct bank pairs
+                           // whatever their indices -- no bank conflicts); 0: a single copy
+  uint32_t lut_direct;     // 1: the table is DIRECT -- one 16-bit value per bit pattern lut_lo_bits .. fmax_bits (lut_n entries):
+                           // one 2-byte load per element, no threshold compare / select (FpTable<.., LUT_DIRECT>)
   FpEntry tbl[40];
 };
 
@@ -295,7 +300,10 @@ IWQ_HD IntQ int_segment_params(float mx, float mn, const QuantConsts& c, bool sy
     q.z = 0.0f;                                           // zeros = 0                          :29
   } else {
     float zq = rD<DT>((q.slow_div || c.inv_div == 0.0f) ? ieee_div(mn, q.s) : fast_quot(mn, q.s, q.r));  // min_val / scales  :22
-    q.z = clamp_nan(-rintf(zq), c.min_int, c.max_int);    // (-round(.)).clamp_(min_int,max_int):22
+    // (-round(.)).clamp_(min_int,max_int) :22.  A zero keeps its sign through torch.clamp (min/s in [0, 0.5] gives -0.0,
+    // the reference stores that bit pattern), a negative value comes back as the bound +0.0
+    const float rz = -rintf(zq);
+    q.z = (rz == 0.0f) ? rz : clamp_nan(rz, c.min_int, c.max_int);
   }
   q.lo = c.min_int - q.z;
   q.hi = c.max_int - q.z;
@@ -425,8 +433,11 @@ IWQ_HD FpQ fp_segment_params(float mx, float mn, const QuantConsts& c) {
 //   sign: codec -> (n < 0), so a negative input that flushes to zero gives -0.0 (quirk Q4, :130,:234)
 //         RNE   -> sign bit of n (rint(-0.0/sc)*sc = -0.0, fp4_quantize_cpu.py:42-43)
 //   out = rD(v * S) [+ mid_h]                                                      :774-777
-template <int DT, bool PAIR = false>
+enum { LUT_STEP = 0, LUT_REPL = 1, LUT_DIRECT = 2 };
+
+template <int DT, bool PAIR = false, int LUT = LUT_STEP>
 struct FpTable {
+  static constexpr bool REPL = LUT == LUT_REPL;
   using D = DType<DT>;
   using T2 = typename D::T2;
   using F = typename PerHalf<PAIR>::F;
@@ -437,6 +448,9 @@ struct FpTable {
   uint32_t lo2, sh;          // step table: packed low pattern, log2 interval width
   const FpStep* steps;       // host: pointer; device: also as a 32-bit shared-memory address
   uint32_t steps_saddr;
+  // REPL (replicated table): byte address of entry i for this lane = rep_base + i * (8 << rep_shift); the interval index is
+  // never materialised -- the masked pattern is scaled straight into the address by one multiply-add per half
+  uint32_t rep_base, rep_mask_hi, rep_mul_lo, rep_mul_hi;
 
   IWQ_HD void setup(const FpQ& q, const QuantConsts& c, const FpStep* step_tbl = nullptr) { setup2(q, q, c, step_tbl); }
   IWQ_HD void setup2(const FpQ& q, const FpQ& qb, const QuantConsts& c, const FpStep* step_tbl = nullptr) {
@@ -459,6 +473,18 @@ struct FpTable {
     rne = c.flavour_rne != 0;
     slow_div = q.slow_div || qb.slow_div;
     tbl_off = c.tbl_base;
+    rep_base = rep_mask_hi = rep_mul_lo = rep_mul_hi = 0;
+#ifdef __CUDA_ARCH__
+    if (LUT == LUT_DIRECT) rep_base = steps_saddr - 2u * (uint32_t)c.lut_lo_bits;  // byte address of pattern p: rep_base + 2 p
+    if (REPL) {
+      // stride = 8 << rep_shift bytes per entry, k = log2(stride) - sh >= 0 (the host caps the interval width accordingly)
+      const uint32_t k = 3u + c.lut_rep_shift - c.lut_shift;
+      rep_mask_hi = (0xFFFFu & ~((1u << c.lut_shift) - 1u)) << 16;
+      rep_mul_lo = 1u << k;           // (pattern_lo & mask) * 2^k          = index * stride
+      rep_mul_hi = 16u - k;           // ((pattern_hi & mask) << 16) >> (16 - k) = index * stride
+      rep_base = steps_saddr + (threadIdx.x & ((1u << c.lut_rep_shift) - 1u)) * 8u - (((uint32_t)c.lut_lo_bits >> c.lut_shift) << (3u + c.lut_rep_shift));
+    }
+#endif
   }
 
   // quantise an already-normalised pair n2 (D values) onto the minifloat grid; sign handled here.
@@ -498,6 +524,34 @@ struct FpTable {
   // magnitude part: the selected `below` / `above` entries of both halves, packed
   IWQ_HD uint32_t steps_select(T2 n2) const {
     T2 a = __hmin2(__habs2(n2), fmax2);
+#ifdef __CUDA_ARCH__
+    if (LUT == LUT_DIRECT) {
+      a = __hmax2(a, lutlo2);
+      const uint32_t d = as_u32(a);
+      uint16_t v0, v1;
+      // low half: pattern * 2; high half: (d >> 16) * 2 == d >> 15 because bit 15 (the low half's sign) is clear
+      uint32_t a0;
+      asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(a0) : "r"(d & 0xFFFFu), "r"(rep_base));
+      asm("ld.shared.u16 %0, [%1];" : "=h"(v0) : "r"(a0));
+      asm("ld.shared.u16 %0, [%1];" : "=h"(v1) : "r"(rep_base + (d >> 15)));
+      return (uint32_t)v0 | ((uint32_t)v1 << 16);
+    }
+    if (REPL) {
+      a = __hmax2(a, lutlo2);
+      const uint32_t d = as_u32(a);
+      uint32_t a0, a1;
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a0) : "r"(d & (rep_mask_hi >> 16)), "r"(rep_mul_lo), "r"(rep_base));
+      a1 = rep_base + ((d & rep_mask_hi) >> rep_mul_hi);  // (a mad.hi.u32 drags a 64-bit addend along: two extra moves)
+      uint2 e0, e1;
+      asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(e0.x), "=r"(e0.y) : "r"(a0));
+      asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(e1.x), "=r"(e1.y) : "r"(a1));
+      const uint32_t thr = __byte_perm(e0.x, e1.x, 0x5410);
+      const uint32_t below = __byte_perm(e0.x, e1.x, 0x7632);
+      const uint32_t above = __byte_perm(e0.y, e1.y, 0x5410);
+      const uint32_t m = __hge2_mask(a, from_u32<T2>(thr));
+      return (below & ~m) | (above & m);
+    }
+#endif
     uint32_t d = as_u32(a);
     if (!kFromZero) {
       a = __hmax2(a, lutlo2);

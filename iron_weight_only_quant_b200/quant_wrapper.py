@@ -89,8 +89,7 @@ class _Batcher:
             outs.append((ql, scales, zeros))
         if cfg.group == _lib.GROUP_PER_TENSOR:
             rng = torch.empty(2 * len(mats), dtype=torch.float32, device=device)
-            _lib.minmax_(mats, cfg, device, rng)
-            _lib.fake_quant_with_range_(mats, cfg, device, rng, track_status=False)
+            _lib.per_tensor_batched_(mats, cfg, device, rng, track_status=False)
         else:
             _lib.fake_quant_batched_(mats, cfg, device, track_status=False)
         for ql, scales, zeros in outs:

@@ -130,7 +130,9 @@ def int_ranges_to_qparams(mx, mn, n_bits: int, zero_point: bool, dtype: str):
         s = rD(_div(d, np.float32(max_int)), dtype)
         z = rD(_div(mn, s), dtype)
         z = -np.rint(z)
-        z = _clamp(z, min_int, max_int)
+        # torch.clamp keeps the sign of a zero (ATen CPU: min(max(x, lo), hi) returns x when x == lo): min/s in [0, 0.5]
+        # -> round = +0 -> negated -0.0 -> stays -0.0; a negative value comes back as the bound +0.0
+        z = np.where(z == 0, z, _clamp(z, min_int, max_int))
     else:
         d = rD(_clamp(mx, lo=1e-5), dtype)
         s = rD(_div(d, np.float32(max_int)), dtype)

@@ -119,8 +119,7 @@ def test_random_configurations_match_oracle(seed):
         if scheme != "bfp":
             same(bits(scales), ref["scales"], dt, tag + " scales")
         if emit_z and "zeros" in ref:
-            # the sign of a zero zero-point is a documented divergence: compare values
-            assert np.array_equal(O.from_bits(bits(zeros), dt), O.from_bits(ref["zeros"], dt), equal_nan=True), tag + " zeros"
+            same(bits(zeros), ref["zeros"], dt, tag + " zeros")  # bit-exact, the sign of a zero zero-point included
 
 
 def _guarded(nbytes: int, guard: int = 4096):

@@ -73,8 +73,7 @@ def test_int_matches_reference_golden(golden, dt, sym, nb):
         if sym:
             assert ql.zeros is None
         else:
-            zr = O.from_bits(g[f"ql_{key}_zeros"], dt)
-            assert np.array_equal(O.from_bits(bits(ql.zeros.reshape(-1)), dt), zr), key + " zeros"
+            assert_bits(bits(ql.zeros.reshape(-1)), g[f"ql_{key}_zeros"], dt, key + " zeros")  # sign of a zero zero-point included
         # function form (quant_funcs.py:4-46)
         if f"fn_{key}_assert" in g.files:
             with pytest.raises(AssertionError):
@@ -216,7 +215,7 @@ def test_int_vs_oracle_all_outputs(dt, variant):
         tag = f"{dt} b{nb} sym={sym} g{grp} v{variant}"
         assert_bits(bits(out), ref["out"], dt, tag)
         assert_bits(bits(scales), ref["scales"], dt, tag + " scales")
-        assert np.array_equal(O.from_bits(bits(zeros), dt), O.from_bits(ref["zeros"], dt)), tag + " zeros"
+        assert_bits(bits(zeros), ref["zeros"], dt, tag + " zeros")
         c = codes.cpu().numpy().astype(np.int32)
         if sym:
             c = np.where(c >= 128, c - 256, c)  # two's complement int8
@@ -285,7 +284,7 @@ def test_per_tensor_fused_single_launch_vs_oracle(dt):
     for w, s_, z_ in zip(ws, sc, zs):
         ref = O.int_fake_quant(bits(w), dt, 4, True, -1)
         assert_bits(bits(s_), ref["scales"], dt, "fused scales")
-        assert np.array_equal(O.from_bits(bits(z_), dt), O.from_bits(ref["zeros"], dt)), "fused zeros"
+        assert_bits(bits(z_), ref["zeros"], dt, "fused zeros")
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
@@ -498,6 +497,22 @@ def test_host_buffer_pipeline():
     nan = hs[2].clone().pin_memory()
     nan[5, 7] = float("nan")
     assert _lib.fake_quant_host_([hs[0], nan], cfg) & _lib.STATUS_NAN
+    # scales and zero points come back through the same pipeline (what the module form stores: quant_linear.py:924-932),
+    # bit-exact against the oracle, across ragged chunk boundaries; per-group and per-channel
+    for grp, sym, nb in [(128, False, 4), (-2, False, 8), (64, True, 4)]:
+        cfg = _lib.make_config(torch.float16, _lib.SCHEME_INT, grp, bits=nb, symmetric=sym)
+        hs = [x.clone().pin_memory() for x in ws]
+        sc = [torch.empty(_lib.num_segments(r, c, grp), dtype=torch.float16).pin_memory() for r, c in shapes_]
+        zs = None if sym else [torch.empty(_lib.num_segments(r, c, grp), dtype=torch.float16).pin_memory() for r, c in shapes_]
+        assert _lib.fake_quant_host_(hs, cfg, device=0, chunk_bytes=192 * 1024, scales=sc, zeros=zs) == 0
+        for i, (x, h) in enumerate(zip(ws, hs)):
+            ref = O.int_fake_quant(bits(x), "f16", nb, not sym, grp)
+            assert np.array_equal(bits(h), ref["out"])
+            assert_bits(bits(sc[i]), ref["scales"], "f16", f"host scales g{grp}")
+            if not sym:
+                assert_bits(bits(zs[i]), ref["zeros"], "f16", f"host zeros g{grp}")
+    # the call leaves the caller's current device alone
+    assert torch.cuda.current_device() == 0
 
 
 # ------------------------------------------------------------------------------------------------
@@ -693,7 +708,7 @@ def test_quant_dim1_vs_oracle_larger(dt):
         tag = f"{dt} [{rows},{cols}] g{grp} b{nb} sym={sym}"
         assert_bits(bits(wd), ref["out"], dt, tag)
         assert_bits(bits(scales), ref["scales"], dt, tag + " scales")
-        assert np.array_equal(O.from_bits(bits(zeros), dt), O.from_bits(ref["zeros"], dt)), tag + " zeros"
+        assert_bits(bits(zeros), ref["zeros"], dt, tag + " zeros")
     w = seeded(512, 768, dt, 77)
     ref = O.along_output_dim(O.fp_approx_fake_quant, bits(w), dt, 4, 3, 128, 12, 15, 1, False)
     wd = w.to(DEV)

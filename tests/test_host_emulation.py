@@ -79,6 +79,8 @@ def test_int_fast_math_matches_reference(emu, golden, dt, sym, bits):
         out, scales, zeros = run_emu(emu, w, F16 if dt == "f16" else BF16, SCHEME_INT, grp, bits=bits, sym=sym)
         assert_bits_equal(out, g[f"ql_{key}_out"], dt, key)
         assert_bits_equal(scales, g[f"ql_{key}_scales"], dt, key)
+        if not sym:
+            assert_bits_equal(zeros, g[f"ql_{key}_zeros"], dt, key + " zeros")  # the sign of a zero zero-point included
 
 
 @pytest.mark.parametrize("dt", ["f16", "bf16"])

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in sorted(declared):
         assert hasattr(L, name), name
     assert set(built.EXPORTS) == declared
-    assert L.iwq_abi_version() == 3
+    assert L.iwq_abi_version() == 4
     L.iwq_workspace_bytes.restype = ctypes.c_size_t
     assert L.iwq_workspace_bytes(10) == 640
 

@@ -33,8 +33,8 @@ def test_int_matches_reference(golden, dtype, sym, bits):
         assert _nan_equal_bits(r["out"], g[f"ql_{key}_out"], dtype), key
         assert _nan_equal_bits(r["scales"], g[f"ql_{key}_scales"], dtype), key
         if not sym:
-            # sign of a zero zero-point is not observable in the output; compare values
-            assert np.array_equal(O.from_bits(r["zeros"], dtype), O.from_bits(g[f"ql_{key}_zeros"], dtype)), key
+            # bit-exact, the sign of a zero zero-point included (quant_funcs.py:22)
+            assert _nan_equal_bits(r["zeros"], g[f"ql_{key}_zeros"], dtype), key
         # function form (quant_funcs.py:4-46) either asserts on NaN or returns the same bits
         if f"fn_{key}_assert" in g.files:
             assert r["has_nan"], key

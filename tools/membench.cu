@@ -124,6 +124,21 @@ int main(int argc, char** argv) {
       }
       printf("re-read of %4zu MB right after reading it: %7.3f ms  %7.0f GB/s\n", mb, best, sz / best / 1e6);
     }
+    {  // read-only streaming ceiling over the whole buffer (the per-tensor range pass is such a stream)
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      for (int ctas : {2, 4, 8}) {
+        read_only<<<148 * ctas, 256>>>(w, total, sink);
+        cudaEventRecord(e0);
+        for (int i = 0; i < 5; ++i) read_only<<<148 * ctas, 256>>>(w, total, sink);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf("read-only stream of %zu MB, %d CTAs/SM: %7.0f GB/s\n", total >> 20, ctas, total * 5 / ms / 1e6);
+      }
+    }
     return 0;
   }
   auto each = [&](auto f) { for (int m = 0; m < n_mat; ++m) f(w + (size_t)m * bytes); };
