@@ -159,6 +159,9 @@ int iwq_fake_quant_per_tensor_fused(const iwq_config_t* cfg, const iwq_matrix_t*
 /* decode(encode(x)) of the quant_linear minifloat codec on `n` 16-bit values (quant_linear.py:126-163,
  * :213-235); `codes` optional. flavour = IWQ_SCHEME_FP_CODEC or IWQ_SCHEME_FP_RNE (then: _fp_scale with S=1). */
 int iwq_fp_roundtrip(int dtype, int flavour, int exp_bits, int mant_bits, const void* x, void* y, void* codes, int64_t n, void* stream);
+/* _fp_scale (fp4_quantize_cpu.py:37-44) on `n` fp16 values with an ELEMENT-WISE fp16 scale array (the caller broadcasts
+ * the reference's S): y = RNE-onto-the-(E, M)-grid(clamp(x / S, +-max_float)), not multiplied back by S. */
+int iwq_fp_scale(int exp_bits, int mant_bits, const void* x, const void* scale, void* y, int64_t n, void* stream);
 /* exhaustive device check of the reciprocal+FMA quotient against IEEE division for every (w, s) pair of
  * the dtype; writes the number of mismatching pairs to *mismatches (device int64*, caller zeroes it). */
 int iwq_selftest_division(int dtype, unsigned long long* mismatches, void* stream);

@@ -34,6 +34,7 @@ EXPORTS = (
     "iwq_minmax",
     "iwq_fake_quant_with_range",
     "iwq_fp_roundtrip",
+    "iwq_fp_scale",
     "iwq_selftest_division",
     "iwq_fake_quant_host",
     "iwq_fake_quant_host_batched",
@@ -112,6 +113,8 @@ def lib() -> ctypes.CDLL:
         L.iwq_fake_quant_with_range.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(Matrix), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
         L.iwq_fp_roundtrip.restype = ctypes.c_int
         L.iwq_fp_roundtrip.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        L.iwq_fp_scale.restype = ctypes.c_int
+        L.iwq_fp_scale.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
         L.iwq_selftest_division.restype = ctypes.c_int
         L.iwq_selftest_division.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.iwq_fake_quant_host.restype = ctypes.c_int

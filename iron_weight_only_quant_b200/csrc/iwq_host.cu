@@ -1,6 +1,7 @@
 // iwq_host.cu -- C ABI of libiwq_b200.so (declared in include/iwq_b200.h): argument validation,
 // launch-constant construction (including the per-binade minifloat table), work-list building and
 // kernel dispatch.  No torch types; plain pointers, sizes and a cudaStream_t.
+#include <cuda.h>  // CUtensorMap + enums only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint (no libcuda link)
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -49,7 +50,8 @@ struct Knobs {
   int fused_lookahead = env_int("IWQ_FUSED_LOOKAHEAD", 2); // ... and how many batches the range pass runs ahead
   int row_tma_out = env_int("IWQ_ROW_TMA_OUT", 1);   // row kernel: bulk stores instead of STG.128 when the ring has >= 3 stages
   int wide_seg4 = env_int("IWQ_WIDE_SEG4", 1);       // 1: segments of 2048/4096/8192 elements go through seg4_tma_kernel
-  int col_mode = env_int("IWQ_COL_MODE", 0);         // 0: warp-private cp.async ring (col_async_kernel), 1: register-resident
+  int col_mode = env_int("IWQ_COL_MODE", 2);         // 2: 2-D tensor-map boxes (col_tma_kernel), 0: warp-private cp.async ring
+                                                     // (col_async_kernel), 1: register-resident (col_reg_kernel)
   int col_stages = env_int("IWQ_COL_STAGES", 0);     // ring depth of col_async_kernel (1..4); 0 = automatic
   int pt_slab_mb = env_int("IWQ_PT_SLAB_MB", 0);     // per-tensor: range pass -> apply pass per slab of whole matrices of at most this
                                                      // many MB (the apply pass then finds the slab in L2); 0 = one range pass over
@@ -332,6 +334,8 @@ static int fill_params(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, c
     if (rc) return rc;
     if (units >= 0xFFFFFFFFull) return fail(IWQ_ERR_INVALID, "too much work for one launch");
     Job j = make_job(&ms[i], (uint32_t)units);
+    if (cfg->group == IWQ_GROUP_PER_TENSOR && (j.bytes & 15))
+      return fail(IWQ_ERR_UNSUPPORTED, "per-tensor granularity needs rows * cols to be a multiple of 8 (16-byte vectors); pad the tensor with one of its own values");
     if (pl.path == PATH_SEG) {
       units += (j.bytes + kTileBytes - 1) / kTileBytes;
     } else {
@@ -418,8 +422,40 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
     rc = bind_lut();
     if (rc) return rc;
   }
-  if (p.qc.approx == 2 && cfg->quant_dim != 1)
-    return fail(IWQ_ERR_UNSUPPORTED, "double-approximate decode is implemented for quant_dim = 1 only (what the reference's scripts use)");
+  if (p.qc.approx == 2 && cfg->quant_dim == 0) {
+    // double-approximate decode along the rows (quant_linear.py:484-488): groups of four = the same offset of four
+    // consecutive segments (of a row, or of neighbouring rows when a row holds fewer than four)
+    if (given_range || minmax_only) return fail(IWQ_ERR_INVALID, "range entry points are for per-tensor granularity");
+    const int g = cfg->group;
+    if (g != 32 && g != 64 && g != 128 && g != 256) return fail(IWQ_ERR_UNSUPPORTED, "double-approximate decode with quant_dim = 0 is implemented for group 32 / 64 / 128 / 256");
+    std::vector<Job> jobs;
+    uint64_t units = 0;
+    const uint64_t quads_per_unit = 8ull * (256 / g);
+    for (int i = 0; i < n; ++i) {
+      rc = check_matrix(&ms[i]);
+      if (rc) return rc;
+      if (ms[i].codes) return fail(IWQ_ERR_UNSUPPORTED, "the double-approximate decode does not emit codes");
+      if (ms[i].cols % g != 0) return fail(IWQ_ERR_INDIVISIBLE, "cols is not divisible by the group size");
+      // four consecutive segments (row-major segment order) are 4 * group contiguous elements whatever the row length
+      if (((uint64_t)ms[i].rows * (uint64_t)(ms[i].cols / g)) % 4 != 0)
+        return fail(IWQ_ERR_UNSUPPORTED, "double-approximate decode needs the number of segments to be a multiple of 4");
+      Job j = make_job(&ms[i], (uint32_t)units);
+      units += (j.bytes / (8ull * g) + quads_per_unit - 1) / quads_per_unit;
+      if (units >= 0xFFFFFFFFull) return fail(IWQ_ERR_INVALID, "too much work for one launch");
+      jobs.push_back(j);
+    }
+    p.n_jobs = n;
+    p.total_units = (uint32_t)units;
+    p.single = jobs[0];
+    p.jobs = nullptr;
+    p.col_group = (uint32_t)g;
+    p.status = status;
+    rc = upload_jobs(jobs, workspace, ws_bytes, &p, st);
+    if (rc) return rc;
+    cudaError_t e2 = cfg->dtype == IWQ_F16 ? launch_seg_double<IWQ_F16>(p, st) : launch_seg_double<IWQ_BF16>(p, st);
+    if (e2 != cudaSuccess) return fail_cuda(e2, "double-approximate (quant_dim 0) kernel launch");
+    return IWQ_OK;
+  }
   if (cfg->quant_dim == 1 && cfg->group != IWQ_GROUP_PER_TENSOR) {
     if (given_range || minmax_only) return fail(IWQ_ERR_INVALID, "range entry points are for per-tensor granularity");
     p.status = status;
@@ -563,11 +599,67 @@ static uint32_t col_tile_for(int64_t g, int* rpl, int* stages) {
   return 32u * lpr;
 }
 
+// 2-D tensor map of a row-major [rows, cols] 16-bit matrix with a box of [box_rows x box_cols] elements (col_tma_kernel)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int encode_map(TensorMap2D* out, const void* base, int64_t rows, int64_t cols, uint32_t box_rows, uint32_t box_cols) {
+  static EncodeTiledFn fn = nullptr;
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!fn) {
+      void* f = nullptr;
+      cudaDriverEntryPointQueryResult qr;
+      cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr);
+      if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !f) return fail(IWQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+      fn = (EncodeTiledFn)f;
+    }
+  }
+  static_assert(sizeof(TensorMap2D) == sizeof(CUtensorMap), "tensor map size");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  alignas(64) CUtensorMap m;
+  const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(IWQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+  memcpy(out, &m, sizeof(m));
+  return IWQ_OK;
+}
+
+static cudaError_t dispatch_col_tma(int dt, int kind, const LaunchParams& p, const TensorMapPair& single, const TensorMapPair* maps, bool sym, const LaunchTuning& t,
+                                    cudaStream_t st) {
+  if (dt == IWQ_F16) {
+    switch (kind) {
+      case KIND_INT_FAST: return launch_col_tma<IWQ_F16, KIND_INT_FAST>(p, single, maps, sym, t, st);
+      case KIND_FP: return launch_col_tma<IWQ_F16, KIND_FP>(p, single, maps, sym, t, st);
+      case KIND_BFP: return launch_col_tma<IWQ_F16, KIND_BFP>(p, single, maps, sym, t, st);
+      default: return launch_col_tma<IWQ_F16, KIND_INT_GENERIC>(p, single, maps, sym, t, st);
+    }
+  }
+  switch (kind) {
+    case KIND_INT_FAST: return launch_col_tma<IWQ_BF16, KIND_INT_FAST>(p, single, maps, sym, t, st);
+    case KIND_INT_WIDE: return launch_col_tma<IWQ_BF16, KIND_INT_WIDE>(p, single, maps, sym, t, st);
+    case KIND_FP: return launch_col_tma<IWQ_BF16, KIND_FP>(p, single, maps, sym, t, st);
+    case KIND_BFP: return launch_col_tma<IWQ_BF16, KIND_BFP>(p, single, maps, sym, t, st);
+    default: return launch_col_tma<IWQ_BF16, KIND_INT_GENERIC>(p, single, maps, sym, t, st);
+  }
+}
+
+// tile shape of col_tma_kernel: 8 KB boxes (g rows x 4096 / g columns; 64-byte rows at least) -> columns per tile, 0 = not applicable
+static uint32_t col_tma_tile(int64_t g) {
+  if (knobs().col_mode != 2) return 0;
+  if (g != 32 && g != 64 && g != 128 && g != 256) return 0;
+  return g == 32 ? 128u : g == 64 ? 64u : 32u;
+}
+
 static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, LaunchParams& p, int kind, void* workspace, size_t ws_bytes, cudaStream_t st) {
   std::vector<Job> jobs;
   uint64_t units = 0;
   int rpl = 0, stages = 0;
-  const uint32_t ctile = (cfg->group > 0 && p.qc.approx != 2) ? col_tile_for(cfg->group, &rpl, &stages) : 0u;
+  const uint32_t tma_tile = (cfg->group > 0 && p.qc.approx != 2) ? col_tma_tile(cfg->group) : 0u;
+  const uint32_t ctile = tma_tile ? tma_tile : ((cfg->group > 0 && p.qc.approx != 2) ? col_tile_for(cfg->group, &rpl, &stages) : 0u);
   const uint32_t unit_cols = ctile ? ctile : (uint32_t)kColTile;
   for (int i = 0; i < n; ++i) {
     int rc = check_matrix(&ms[i]);
@@ -613,6 +705,35 @@ static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, Launc
   LaunchTuning tune;
   tune.stages = 0;
   tune.ctas_per_sm = knobs().col_ctas;
+  if (tma_tile) {
+    // ---- col_tma_kernel: tensor maps (input / output) per matrix; behind the job table in the workspace, or in the kernel
+    //      parameters for a single matrix ----
+    p.stage_bytes = (uint32_t)cfg->group * tma_tile * 2u;
+    p.n_stages = knobs().col_stages == 1 ? 1 : 2;
+    if (cfg->group == 256 && knobs().col_stages == 0) p.n_stages = 1;  // 16 KB boxes: one stage, more resident warps
+    std::vector<TensorMapPair> maps((size_t)n);
+    for (int i = 0; i < n; ++i) {
+      rc = encode_map(&maps[i].in, ms[i].w, ms[i].rows, ms[i].cols, (uint32_t)cfg->group, tma_tile);
+      if (rc) return rc;
+      if (ms[i].out == ms[i].w) maps[i].out = maps[i].in;
+      else {
+        rc = encode_map(&maps[i].out, ms[i].out, ms[i].rows, ms[i].cols, (uint32_t)cfg->group, tma_tile);
+        if (rc) return rc;
+      }
+    }
+    const TensorMapPair* dmaps = nullptr;
+    if (n > 1) {
+      const size_t off = ((size_t)n * sizeof(Job) + 127) & ~(size_t)127;
+      if (!workspace || ws_bytes < off + (size_t)n * sizeof(TensorMapPair)) return fail(IWQ_ERR_INVALID, "workspace too small (see iwq_workspace_bytes)");
+      if ((uintptr_t)workspace & 127) return fail(IWQ_ERR_ALIGN, "workspace must be 128-byte aligned for quant_dim = 1");
+      cudaError_t e2 = cudaMemcpyAsync((uint8_t*)workspace + off, maps.data(), (size_t)n * sizeof(TensorMapPair), cudaMemcpyHostToDevice, st);
+      if (e2 != cudaSuccess) return fail_cuda(e2, "cudaMemcpyAsync(tensor maps)");
+      dmaps = (const TensorMapPair*)((uint8_t*)workspace + off);
+    }
+    cudaError_t e2 = dispatch_col_tma(cfg->dtype, kind, p, maps[0], dmaps, p.qc.symmetric != 0, tune, st);
+    if (e2 != cudaSuccess) return fail_cuda(e2, "column-group (tensor map) kernel launch");
+    return IWQ_OK;
+  }
   // the light INT / BFP element stages run best with 4 CTAs (16 warps) per SM at group >= 128; the minifloat
   // stage (two table lookups per pair) wants every warp it can get
   if (tune.ctas_per_sm == 0 && ctile && rpl == 0 && kind != KIND_FP && cfg->group >= 128) tune.ctas_per_sm = 4;
@@ -678,7 +799,7 @@ int iwq_abi_version(void) { return IWQ_ABI_VERSION; }
 
 // Which kernel and tile shape a [rows, cols] matrix would get under `cfg` (no CUDA call: testable on a GPU-less box).
 // out[0] path: 0 seg4 / seg / direct (see out[1]), 1 row_tma_kernel, 2 col_async_kernel, 3 col_reg_kernel, 4 col_kernel
-//              (two sweeps), 5 col_double_kernel
+//              (two sweeps), 5 col_double_kernel, 6 col_tma_kernel (2-D tensor-map boxes)
 // out[1] kernel variant of the segment path (0 seg4_tma, 1 seg_direct, 2 seg_tma), out[2] lanes per segment,
 // out[3] ring stages, out[4] consumer warps (row path), out[5] bytes per stage (row / column paths),
 // out[6] row kernel sends its results through bulk stores, out[7] columns per tile (column paths)
@@ -697,6 +818,13 @@ int iwq_debug_plan(const iwq_config_t* cfg, int64_t rows, int64_t cols, int32_t*
       return IWQ_OK;
     }
     int rpl = 0, stages = 0;
+    if (cfg->group > 0 && col_tma_tile(cfg->group)) {
+      out[0] = 6;  // col_tma_kernel
+      out[3] = (knobs().col_stages == 1 || (cfg->group == 256 && knobs().col_stages == 0)) ? 1 : 2;
+      out[5] = (int32_t)((uint32_t)cfg->group * col_tma_tile(cfg->group) * 2u);
+      out[7] = (int32_t)col_tma_tile(cfg->group);
+      return IWQ_OK;
+    }
     const uint32_t ctile = cfg->group > 0 ? col_tile_for(cfg->group, &rpl, &stages) : 0u;
     out[0] = ctile ? (rpl ? 3 : 2) : 4;
     out[3] = stages;
@@ -749,7 +877,11 @@ int iwq_debug_set_knob(const char* name, int value) {
 #undef IWQ_KNOB
   return fail(IWQ_ERR_INVALID, "unknown knob: " + n);
 }
-size_t iwq_workspace_bytes(int n) { return (size_t)(n < 1 ? 1 : n) * sizeof(Job); }
+// job table, then (128-byte aligned) one pair of tensor maps per matrix for the quant_dim = 1 kernels
+size_t iwq_workspace_bytes(int n) {
+  const size_t m = (size_t)(n < 1 ? 1 : n);
+  return ((m * sizeof(Job) + 127) & ~(size_t)127) + m * sizeof(TensorMapPair);
+}
 
 int iwq_fake_quant(const iwq_config_t* cfg, const iwq_matrix_t* m, float* range_ws, int32_t* status, void* stream) {
   return run_batched(cfg, m, 1, nullptr, 0, nullptr, range_ws, status, (cudaStream_t)stream, false);
@@ -935,6 +1067,31 @@ int iwq_fp_roundtrip(int dtype, int flavour, int exp_bits, int mant_bits, const 
     fp_roundtrip_kernel<IWQ_BF16><<<grid, 256, 0, st>>>((const uint32_t*)x, (uint32_t*)y, (uint16_t*)codes, pairs, qc);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "fp_roundtrip kernel launch");
+  return IWQ_OK;
+}
+
+int iwq_fp_scale(int exp_bits, int mant_bits, const void* x, const void* scale, void* y, int64_t n, void* stream) {
+  iwq_config_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.dtype = IWQ_F16;
+  cfg.scheme = IWQ_SCHEME_FP_RNE;
+  cfg.exp_bits = exp_bits;
+  cfg.mant_bits = mant_bits;
+  cfg.symmetric = 1;
+  cfg.group = 128;
+  QuantConsts qc;
+  int kind = 0;
+  int rc = build_consts(&cfg, &qc, &kind);
+  if (rc) return rc;
+  if (!x || !scale || !y) return fail(IWQ_ERR_INVALID, "null pointer");
+  if (n <= 0 || (n & 1)) return fail(IWQ_ERR_INVALID, "n must be positive and even");
+  if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)scale) & 3) return fail(IWQ_ERR_ALIGN, "x, scale and y must be 4-byte aligned");
+  const int64_t pairs = n / 2;
+  int grid = (int)((pairs + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  fp_scale_kernel<IWQ_F16><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)x, (const uint32_t*)scale, (uint32_t*)y, pairs, qc);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, "fp_scale kernel launch");
   return IWQ_OK;
 }
 

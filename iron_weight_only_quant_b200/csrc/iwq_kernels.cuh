@@ -225,6 +225,14 @@ __device__ __forceinline__ void store_codes(uint8_t* codes, uint64_t vec, const 
   }
 }
 
+// any NaN among the 8 values of a vector (suspect segments only: see IntQ::bad)
+template <int DT>
+__device__ __forceinline__ bool vec_has_nan(const uint4& v) {
+  using T2 = typename DType<DT>::T2;
+  const T2 a = from_u32<T2>(v.x), b = from_u32<T2>(v.y), c = from_u32<T2>(v.z), d = from_u32<T2>(v.w);
+  return (__hneu2_mask(a, a) | __hneu2_mask(b, b) | __hneu2_mask(c, c) | __hneu2_mask(d, d)) != 0u;
+}
+
 template <int DT, int KIND>
 struct Prepared;
 
@@ -460,7 +468,7 @@ __device__ __forceinline__ void consume_tile(uint4 (&v)[kVPT], const TileCtx& t,
     if (idx < t.n_vec) {
       stg128(t.dst + (size_t)idx * 16, o);
       if (want_codes) store_codes(t.codes, t.vec0 + idx, codes8, p.qc.code_nibbles != 0);
-      any_bad |= prep.bad;
+      if (prep.bad) any_bad |= vec_has_nan<DT>(o);
       // segment parameters: one lane per segment; per-tensor (GIVEN) has a single segment per matrix
       const bool owner = GIVEN ? (t.vec0 + idx == 0) : ((lane & (lps - 1)) == 0 && (it & (vpl - 1)) == 0);
       if (owner) {
@@ -611,6 +619,7 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
     prep.setup(mx, mn, p.qc, SYM, s_tbl);
   }
   const bool want_codes = !FAST && t.codes != nullptr;
+  bool nan_seen = false;
   if (FAST && !prep.slow()) {
     // the hot path: no code emission, reciprocal+FMA quotient; one segment-uniform branch per lane-tile keeps the
     // IEEE-division variant (degenerate scales only) out of the instruction stream
@@ -631,6 +640,7 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
       const uint4 o = prep.template apply<SYM>(vv, p.qc, s_tbl, want_codes, &codes8);
       sts128(lbase + j * 16, o);
       if (want_codes && lane_vec + j < t.n_vec) store_codes(t.codes, t.vec0 + lane_vec + j, codes8, p.qc.code_nibbles != 0);
+      if (prep.bad && (FAST || lane_vec + j < t.n_vec)) nan_seen |= vec_has_nan<DT>(o);
     }
   }
   if (FAST || lane_vec < t.n_vec) {
@@ -642,7 +652,7 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
       if (t.scales) reinterpret_cast<uint16_t*>(t.scales)[g] = DType<DT>::from_f32(prep.scale);
       if (t.zeros) reinterpret_cast<uint16_t*>(t.zeros)[g] = DType<DT>::from_f32(prep.zero);
     }
-    if (prep.bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
+    if (nan_seen && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
   }
 }
 
@@ -882,12 +892,12 @@ __global__ void __launch_bounds__(512 + 32) row_tma_kernel(const __grid_constant
           const uint4 o = prep.template apply<SYM>(lds128(sdata + (size_t)i * 16), p.qc, s_tbl, want_codes, &codes8);
           stg128(t.dst + (size_t)i * 16, o);
           if (want_codes) store_codes(t.codes, i, codes8, p.qc.code_nibbles != 0);
+          if (prep.bad && vec_has_nan<DT>(o) && p.status) atomicOr(p.status, IWQ_STATUS_NAN);  // suspect rows only
         }
       }
       if (tid == 0) {
         if (t.scales) reinterpret_cast<uint16_t*>(t.scales)[t.row] = DType<DT>::from_f32(prep.scale);
         if (t.zeros) reinterpret_cast<uint16_t*>(t.zeros)[t.row] = DType<DT>::from_f32(prep.zero);
-        if (prep.bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
       }
       __syncwarp();
       if (stored_by_tma) {
@@ -938,6 +948,18 @@ struct PreparedPairInt {
     *bad = qa.bad || qb.bad;
   }
   __device__ __forceinline__ bool slow() const { return f.slow_div; }
+  // take the per-segment constants from lane `src` (which ran setup2 for this column pair)
+  __device__ __forceinline__ void shfl_from(const PreparedPairInt& o, int src) {
+    using T2 = typename DType<DT>::T2;
+    f.lo2 = from_u32<T2>(__shfl_sync(0xFFFFFFFFu, as_u32(o.f.lo2), src));
+    f.hi2 = from_u32<T2>(__shfl_sync(0xFFFFFFFFu, as_u32(o.f.hi2), src));
+    f.s2 = from_u32<T2>(__shfl_sync(0xFFFFFFFFu, as_u32(o.f.s2), src));
+    f.s.x = __shfl_sync(0xFFFFFFFFu, o.f.s.x, src);
+    f.s.y = __shfl_sync(0xFFFFFFFFu, o.f.s.y, src);
+    f.r.x = __shfl_sync(0xFFFFFFFFu, o.f.r.x, src);
+    f.r.y = __shfl_sync(0xFFFFFFFFu, o.f.r.y, src);
+    f.slow_div = __shfl_sync(0xFFFFFFFFu, (int)o.f.slow_div, src) != 0;
+  }
   template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const {
     typename DType<DT>::T2 d;
@@ -960,6 +982,19 @@ struct PreparedPair<DT, KIND_INT_GENERIC> {
     *bad = qa.bad || qb.bad;
   }
   __device__ __forceinline__ bool slow() const { return false; }
+  __device__ __forceinline__ void shfl_from(const PreparedPair& o, int src) {
+    auto one = [&](IntQ& d, const IntQ& q) {
+      d.s = __shfl_sync(0xFFFFFFFFu, q.s, src);
+      d.r = __shfl_sync(0xFFFFFFFFu, q.r, src);
+      d.z = __shfl_sync(0xFFFFFFFFu, q.z, src);
+      d.lo = __shfl_sync(0xFFFFFFFFu, q.lo, src);
+      d.hi = __shfl_sync(0xFFFFFFFFu, q.hi, src);
+      d.bad = __shfl_sync(0xFFFFFFFFu, (int)q.bad, src) != 0;
+      d.slow_div = __shfl_sync(0xFFFFFFFFu, (int)q.slow_div, src) != 0;
+    };
+    one(qa, o.qa);
+    one(qb, o.qb);
+  }
   template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts& c) const {
     float k;
@@ -980,6 +1015,18 @@ struct PreparedPair<DT, KIND_FP> {
     *bad = qa.bad || qb.bad;
   }
   __device__ __forceinline__ bool slow() const { return f.slow_div; }
+  __device__ __forceinline__ void shfl_from(const PreparedPair& o, int src) {
+    using T2 = typename DType<DT>::T2;
+    f = o.f;  // launch-uniform members (clamp bounds, table address, flags)
+    f.S2 = from_u32<T2>(__shfl_sync(0xFFFFFFFFu, as_u32(o.f.S2), src));
+    f.mid2 = from_u32<T2>(__shfl_sync(0xFFFFFFFFu, as_u32(o.f.mid2), src));
+    f.midh2 = from_u32<T2>(__shfl_sync(0xFFFFFFFFu, as_u32(o.f.midh2), src));
+    f.S.x = __shfl_sync(0xFFFFFFFFu, o.f.S.x, src);
+    f.S.y = __shfl_sync(0xFFFFFFFFu, o.f.S.y, src);
+    f.r.x = __shfl_sync(0xFFFFFFFFu, o.f.r.x, src);
+    f.r.y = __shfl_sync(0xFFFFFFFFu, o.f.r.y, src);
+    f.slow_div = __shfl_sync(0xFFFFFFFFu, (int)o.f.slow_div, src) != 0;
+  }
   template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const {
     typename DType<DT>::T2 v;
@@ -998,6 +1045,13 @@ struct PreparedPair<DT, KIND_BFP> {
     *bad = false;
   }
   __device__ __forceinline__ bool slow() const { return false; }
+  __device__ __forceinline__ void shfl_from(const PreparedPair& o, int src) {
+    f = o.f;
+    f.step.x = __shfl_sync(0xFFFFFFFFu, o.f.step.x, src);
+    f.step.y = __shfl_sync(0xFFFFFFFFu, o.f.step.y, src);
+    f.inv_step.x = __shfl_sync(0xFFFFFFFFu, o.f.inv_step.x, src);
+    f.inv_step.y = __shfl_sync(0xFFFFFFFFu, o.f.inv_step.y, src);
+  }
   template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const { return f.apply(w2); }
 };
@@ -1118,12 +1172,12 @@ __global__ void __launch_bounds__(256) col_kernel(const __grid_constant__ Launch
         }
       }
     }
-    if (live && any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
+    bool nan_seen = false;
 
     // ---- sweep 2: quantise (tile re-read from L2), store in place ----
     if (live) {
       uint32_t k = (uint32_t)warp;
-      for (; k + 8 < g; k += 16) {  // 2 rows in flight
+      for (; k + 8 < g && !any_bad; k += 16) {  // 2 rows in flight (suspect tiles take the one-row loop, which inspects its outputs)
         const uint4 v0 = ldg128(src + (size_t)k * jb.row_bytes);
         const uint4 v1 = ldg128(src + (size_t)(k + 8) * jb.row_bytes);
         uint4 o0, o1;
@@ -1137,8 +1191,10 @@ __global__ void __launch_bounds__(256) col_kernel(const __grid_constant__ Launch
         uint4 o0;
         o0.x = prep[0].template apply<SYM>(v0.x, p.qc); o0.y = prep[1].template apply<SYM>(v0.y, p.qc); o0.z = prep[2].template apply<SYM>(v0.z, p.qc); o0.w = prep[3].template apply<SYM>(v0.w, p.qc);
         stg128(dst + (size_t)k * jb.row_bytes, o0);
+        if (any_bad) nan_seen |= vec_has_nan<DT>(o0);
       }
     }
+    if (nan_seen && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
   }
 }
 
@@ -1245,9 +1301,8 @@ __global__ void __launch_bounds__(256, 2) col_reg_kernel(const __grid_constant__
         }
       }
     }
-    if (live && any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
-
     // ---- element stage on the registers, store in place ----
+    bool nan_seen = false;
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
       uint4 o;
@@ -1256,7 +1311,9 @@ __global__ void __launch_bounds__(256, 2) col_reg_kernel(const __grid_constant__
       o.z = prep[2].template apply<SYM>(v[i].z, p.qc);
       o.w = prep[3].template apply<SYM>(v[i].w, p.qc);
       if (live) stg128(dst + (size_t)i * step, o);
+      if (live && any_bad) nan_seen |= vec_has_nan<DT>(o);
     }
+    if (nan_seen && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
   }
 }
 
@@ -1412,10 +1469,8 @@ __global__ void __launch_bounds__(kColAsyncWarps * 32) col_async_kernel(const __
         }
       }
     }
-    if (t.live && any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
-
     // ---- sweep 2: quantise from shared memory, store from registers ----
-    const bool any_slow = prep[0].slow() || prep[1].slow() || prep[2].slow() || prep[3].slow();
+    const bool any_slow = prep[0].slow() || prep[1].slow() || prep[2].slow() || prep[3].slow();  // includes every suspect segment
     if (t.live && !any_slow) {
       // hot path: reciprocal+FMA quotient fixed at compile time (the IEEE-division variant is for degenerate scales)
       uint32_t i = 0;
@@ -1445,12 +1500,236 @@ __global__ void __launch_bounds__(kColAsyncWarps * 32) col_async_kernel(const __
         o0.x = prep[0].template apply<SYM>(v0.x, p.qc); o0.y = prep[1].template apply<SYM>(v0.y, p.qc);
         o0.z = prep[2].template apply<SYM>(v0.z, p.qc); o0.w = prep[3].template apply<SYM>(v0.w, p.qc);
         stg128(t.dst + (size_t)i * t.step, o0);
+        if (any_bad && vec_has_nan<DT>(o0) && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
       }
     }
     __syncwarp();  // the stage may be refilled by the next iteration's copies
     if (++st == n_stages) st = 0;
   }
   cp_async_wait_dyn(0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// col_tma_kernel (default for quant_dim = 1 with group 32 .. 256): the [g rows x C columns] tile of a warp moves through a
+// 2-D TENSOR MAP -- one cp.async.bulk.tensor.2d instruction (SASS: UTMALDG) brings the whole box into the warp's
+// shared-memory stage (dense row-major [g][2C bytes]), one UTMASTG sends the quantised box back; no per-vector copy or
+// store instructions and no 64-bit address arithmetic in the lanes at all.  Like col_async_kernel the pipeline is
+// WARP-PRIVATE (an mbarrier per warp and stage, nothing but __syncwarp() couples the lanes): with two stages the load of
+// the warp's next tile is issued right after the range sweep of the current one -- by then the store of the previous tile
+// has long finished reading that stage -- and runs under the parameter + apply phases.  The tile is 8 KB for every group
+// size (C = 4096 / g columns; 16 KB at g = 256), so a lane always holds 16 vectors of its 8 columns.
+// The per-column parameters are computed ONCE per column pair: the 32 / lpr lanes that hold the same 8 columns (one per
+// row phase) split the 4 pairs between them -- one setup2 per lane instead of four -- and hand the constants round with
+// shuffles.  Tensor maps: one per matrix for the input and one for the output, built on the host
+// (cuTensorMapEncodeTiled), in the launch's workspace behind the job table (or in the kernel parameters for a single
+// matrix).  Ragged last column tiles: the hardware zero-fills the load and clips the store.
+// ------------------------------------------------------------------------------------------------
+struct alignas(64) TensorMap2D {
+  uint64_t opaque[16];  // CUtensorMap (128 bytes)
+};
+struct TensorMapPair {
+  TensorMap2D in, out;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const TensorMap2D* map, uint32_t c0, uint32_t c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const TensorMap2D* map, uint32_t c0, uint32_t c1, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(smem_src)) : "memory");
+}
+// a tensor map that was written to global memory by a copy (generic proxy) must be acquired by the tensormap proxy
+__device__ __forceinline__ void tensormap_acquire(const TensorMap2D* map) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(map) : "memory");
+}
+
+constexpr int kColTmaWarps = 4;
+
+template <int DT, int KIND, bool SYM>
+__global__ void __launch_bounds__(kColTmaWarps * 32) col_tma_kernel(const __grid_constant__ LaunchParams p, const __grid_constant__ TensorMapPair single_maps,
+                                                                     const TensorMapPair* __restrict__ maps) {
+  using T2 = typename DType<DT>::T2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const FpStep* s_tbl = nullptr;
+  if (KIND == KIND_FP) s_tbl = load_fp_lut(p, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_stages = p.n_stages;  // 1 or 2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.lut_smem_bytes) + warp * 2;
+  if (lane == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const uint32_t C = p.col_tile, g = p.col_group;
+  const uint32_t lpr = C >> 3;                 // lanes per tile row: 4 / 8 / 16
+  const uint32_t rps = 32u / lpr;              // rows per warp-wide access = row phases: 8 / 4 / 2
+  const uint32_t sub = (uint32_t)lane & (lpr - 1u), rph = (uint32_t)lane / lpr;
+  const uint32_t n_it = g / rps;               // vectors per lane per tile (16; 32 at g = 256)
+  const uint32_t stage_bytes = p.stage_bytes;  // g * C * 2
+  uint8_t* ring = smem + p.lut_smem_bytes + 128u + (size_t)warp * n_stages * stage_bytes;
+  const uint8_t* lane_off = ring + (size_t)lane * 16u;  // + it * 512: dense rows, a warp-wide LDS.128 reads 512 contiguous bytes
+  const uint32_t m_share = rps < 4u ? rps : 4u;         // lanes that split the 4 column pairs of an 8-column group
+  const uint32_t my_slot = rph & (m_share - 1u);
+  const uint32_t ident_max = SYM ? 0u : (DT == IWQ_F16 ? 0xFC00FC00u : 0xFF80FF80u);  // {0,0} | {-inf,-inf}
+  const uint32_t ident_min = DT == IWQ_F16 ? 0x7C007C00u : 0x7F807F80u;                // {+inf,+inf}
+
+  struct Tile {
+    const TensorMapPair* map;
+    uint8_t* scales;
+    uint8_t* zeros;
+    size_t seg0;      // segment index of this lane's first column: col * n_rb + rb
+    uint32_t n_rb, c0, c1;
+    bool live;        // this lane's 8 columns exist
+  };
+  int cur_l = -1, cur_c = -1, fenced = -1;  // job cursors of the load-issue path and of the arithmetic path
+  Job jb_l, jb_c;
+  auto describe = [&](uint32_t unit, int* cur, Job* jb) -> Tile {
+    Tile t;
+    advance_job(p, unit, cur, jb);
+    const uint32_t cols = jb->row_bytes >> 1;
+    const uint32_t rows = (uint32_t)(jb->bytes / jb->row_bytes);
+    const uint32_t n_ct = (cols + C - 1) / C;
+    const uint32_t local = unit - jb->first_unit;
+    const uint32_t rb = local / n_ct, ct = local - rb * n_ct;
+    t.c0 = ct * C;
+    t.c1 = rb * g;
+    const uint32_t col = t.c0 + sub * 8u;
+    t.live = col < cols;
+    t.scales = jb->scales;
+    t.zeros = jb->zeros;
+    t.n_rb = rows / g;
+    t.seg0 = (size_t)col * t.n_rb + rb;
+    t.map = maps ? &maps[*cur] : &single_maps;
+    return t;
+  };
+  const uint32_t stride_units = gridDim.x * (uint32_t)kColTmaWarps;
+  auto issue = [&](uint32_t unit, int st) {  // lane 0 only
+    if (unit >= p.total_units) return;
+    const Tile t = describe(unit, &cur_l, &jb_l);
+    if (maps && fenced != cur_l) {
+      tensormap_acquire(&t.map->in);
+      tensormap_acquire(&t.map->out);
+      fenced = cur_l;
+    }
+    mbar_arrive_expect_tx(&bars[st], stage_bytes);
+    tma_load_2d(ring + (size_t)st * stage_bytes, &t.map->in, t.c0, t.c1, &bars[st]);
+  };
+
+  const uint32_t first = blockIdx.x * (uint32_t)kColTmaWarps + (uint32_t)warp;
+  if (n_stages == 2 && lane == 0) issue(first, 0);
+  uint32_t phase0 = 0, phase1 = 0;
+  int st = 0;
+  for (uint32_t unit = first; unit < p.total_units; unit += stride_units) {
+    if (n_stages == 1 && lane == 0) {
+      tma_store_wait_read<0>();  // the previous tile's store has finished reading the stage
+      issue(unit, 0);
+    }
+    mbar_wait(&bars[st], st ? phase1 : phase0);
+    if (st) phase1 ^= 1u; else phase0 ^= 1u;
+    const Tile t = describe(unit, &cur_c, &jb_c);
+    uint8_t* sd = const_cast<uint8_t*>(lane_off) + (size_t)st * stage_bytes;
+
+    // ---- sweep 1: per-column range over this lane's rows, then across the row phases ----
+    uint32_t mx[4] = {ident_max, ident_max, ident_max, ident_max};
+    uint32_t mn[4] = {ident_min, ident_min, ident_min, ident_min};
+    for (uint32_t i = 0; i < n_it; i += 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = lds128(sd + (size_t)(i + u) * 512u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) col_range_update<DT, SYM>(mx, mn, v[u]);
+    }
+    if (n_stages == 2 && lane == 0) {
+      // the other stage held the previous tile: its store was committed a whole range sweep ago
+      tma_store_wait_read<0>();
+      issue(unit + stride_units, st ^ 1);
+    }
+#pragma unroll 1
+    for (uint32_t o = lpr; o < 32u; o <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mx[j] = as_u32(__hmax2_nan(from_u32<T2>(mx[j]), from_u32<T2>(__shfl_xor_sync(0xFFFFFFFFu, mx[j], o))));
+        if (!SYM) mn[j] = as_u32(__hmin2_nan(from_u32<T2>(mn[j]), from_u32<T2>(__shfl_xor_sync(0xFFFFFFFFu, mn[j], o))));
+      }
+    }
+
+    // ---- per-column parameters: each row-phase lane takes 4 / m_share of the 4 pairs, shuffles distribute them ----
+    PreparedPair<DT, KIND> prep[4];
+    bool any_bad = false;
+#pragma unroll 1
+    for (uint32_t pass = 0; pass < 4u; pass += m_share) {
+      const uint32_t jm = pass + my_slot;  // the pair this lane computes in this pass
+      const uint32_t mxs = jm == 0 ? mx[0] : jm == 1 ? mx[1] : jm == 2 ? mx[2] : mx[3];
+      const uint32_t mns = jm == 0 ? mn[0] : jm == 1 ? mn[1] : jm == 2 ? mn[2] : mn[3];
+      const float mxa = DType<DT>::to_f32((uint16_t)(mxs & 0xFFFFu)), mxb = DType<DT>::to_f32((uint16_t)(mxs >> 16));
+      const float mna = DType<DT>::to_f32((uint16_t)(mns & 0xFFFFu)), mnb = DType<DT>::to_f32((uint16_t)(mns >> 16));
+      PreparedPair<DT, KIND> mine;
+      float sa, za, sb, zb;
+      bool bad;
+      mine.setup2(mxa, SYM ? -mxa : mna, mxb, SYM ? -mxb : mnb, p.qc, SYM, s_tbl, &sa, &za, &sb, &zb, &bad);
+      if (t.live && rph < m_share) {
+        // segment order of the reference for quant_dim = 1: column-major over (column, row block)
+        const size_t ga = t.seg0 + (size_t)(2u * jm) * t.n_rb, gb = ga + t.n_rb;
+        if (t.scales) {
+          reinterpret_cast<uint16_t*>(t.scales)[ga] = DType<DT>::from_f32(sa);
+          reinterpret_cast<uint16_t*>(t.scales)[gb] = DType<DT>::from_f32(sb);
+        }
+        if (t.zeros) {
+          reinterpret_cast<uint16_t*>(t.zeros)[ga] = DType<DT>::from_f32(za);
+          reinterpret_cast<uint16_t*>(t.zeros)[gb] = DType<DT>::from_f32(zb);
+        }
+      }
+      // pair (pass + s) was computed by the lanes of row phase s: fetch it from lane s * lpr + sub
+#pragma unroll
+      for (uint32_t sl = 0; sl < 4u; ++sl) {
+        if (sl < m_share) {
+          const int src = (int)(sl * lpr + sub);
+          const uint32_t j = pass + sl;
+          const bool b = __shfl_sync(0xFFFFFFFFu, (int)bad, src) != 0;
+          any_bad |= b;
+          if (j == 0) prep[0].shfl_from(mine, src);
+          else if (j == 1) prep[1].shfl_from(mine, src);
+          else if (j == 2) prep[2].shfl_from(mine, src);
+          else prep[3].shfl_from(mine, src);
+        }
+      }
+    }
+
+    // ---- sweep 2: quantise in place in the stage ----
+    const bool any_slow = prep[0].slow() || prep[1].slow() || prep[2].slow() || prep[3].slow();  // includes every suspect segment
+    if (!any_slow) {
+      for (uint32_t i = 0; i < n_it; i += 2) {
+        const uint4 v0 = lds128(sd + (size_t)i * 512u);
+        const uint4 v1 = lds128(sd + (size_t)(i + 1) * 512u);
+        uint4 o0, o1;
+        o0.x = prep[0].template apply<SYM, 0>(v0.x, p.qc); o0.y = prep[1].template apply<SYM, 0>(v0.y, p.qc);
+        o0.z = prep[2].template apply<SYM, 0>(v0.z, p.qc); o0.w = prep[3].template apply<SYM, 0>(v0.w, p.qc);
+        o1.x = prep[0].template apply<SYM, 0>(v1.x, p.qc); o1.y = prep[1].template apply<SYM, 0>(v1.y, p.qc);
+        o1.z = prep[2].template apply<SYM, 0>(v1.z, p.qc); o1.w = prep[3].template apply<SYM, 0>(v1.w, p.qc);
+        sts128(sd + (size_t)i * 512u, o0);
+        sts128(sd + (size_t)(i + 1) * 512u, o1);
+      }
+    } else {
+      for (uint32_t i = 0; i < n_it; ++i) {
+        const uint4 v0 = lds128(sd + (size_t)i * 512u);
+        uint4 o0;
+        o0.x = prep[0].template apply<SYM>(v0.x, p.qc); o0.y = prep[1].template apply<SYM>(v0.y, p.qc);
+        o0.z = prep[2].template apply<SYM>(v0.z, p.qc); o0.w = prep[3].template apply<SYM>(v0.w, p.qc);
+        sts128(sd + (size_t)i * 512u, o0);
+        if (t.live && any_bad && vec_has_nan<DT>(o0) && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&t.map->out, t.c0, t.c1, ring + (size_t)st * stage_bytes);
+      tma_store_commit();
+    }
+    if (n_stages == 2) st ^= 1;
+  }
+  if (lane == 0) tma_store_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1597,6 +1876,108 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
       }
       };
       if (slow) sweep2(std::true_type{}); else sweep2(std::false_type{});
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// seg_double_kernel: the double-approximate decode with quant_dim = 0 (quant_linear.py:484-488 -> :288-363).
+// The reference's groups of four run along the flattened transpose of the [segments, group] code matrix: with the number
+// of segments a multiple of 4 they are the codes at the same offset k of FOUR consecutive segments.  A "quad" is those
+// 4 segments = 4 * group contiguous elements of the row-major matrix (possibly spanning rows); group / 8 lanes share a quad and every lane holds the four vectors at
+// its offset (one per segment), so the neighbourhood never leaves the thread -- the same element logic as
+// col_double_kernel, where the two halves of a packed register are two independent groups (here: offsets k and k + 1).
+// Plain 128-bit global loads / stores: every byte crosses HBM once each way; the element stage (~100 scalar-ish ops per
+// 4 elements) bounds this research path, not the memory system.  blockDim.x = 256; unit = 8 warps x (256 / group) quads.
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(256, 2) seg_double_kernel(const __grid_constant__ LaunchParams p) {
+  using D = DType<DT>;
+  using T2 = typename D::T2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const FpStep* s_tbl = load_fp_lut(p, smem);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t g = p.col_group, vps = g >> 3;            // vectors (= lanes) per segment: 4, 8, 16 or 32
+  const uint32_t qpw = 32u / vps;                            // quads per warp
+  const uint32_t qslot = (uint32_t)lane / vps, v = (uint32_t)lane & (vps - 1u);
+  const uint32_t quads_per_unit = 8u * qpw;
+  int cur = -1;
+  Job jb;
+  FpQ q1;
+  q1.S = 1.f; q1.r = 1.f; q1.mid = 0.f; q1.mid_h = 0.f; q1.bad = false; q1.slow_div = false;
+  FpTable<DT, true> grid;  // only its scale-independent members are used (clamp bounds, step table)
+  grid.setup2(q1, q1, p.qc, s_tbl);
+  const uint32_t hf2 = ((uint32_t)p.qc.hi_field << 8) * 0x00010001u;
+  const uint32_t maxe2 = ((uint32_t)((1 << p.qc.exp_bits) - 1) << 8) * 0x00010001u;
+  const uint32_t val_saddr = smem_u32(smem + p.lut_smem_bytes);
+  for (uint32_t unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+    advance_job(p, unit, &cur, &jb);
+    const uint64_t n_quads = jb.bytes / (8ull * g);        // 4 * g elements of 2 bytes
+    const uint64_t quad = (uint64_t)(unit - jb.first_unit) * quads_per_unit + (uint32_t)warp * qpw + qslot;
+    const bool live = quad < n_quads;
+    const size_t off = (size_t)quad * 8u * g + (size_t)v * 16u;
+    const uint8_t* src = jb.src + off;
+    uint8_t* dst = jb.dst + off;
+    const size_t seg_bytes = (size_t)g * 2u;
+    uint4 vec[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) vec[b] = live ? ldg128(src + b * seg_bytes) : make_uint4(0u, 0u, 0u, 0u);
+    // ---- absmax per segment: this lane's vector, then across the vps lanes of the quad ----
+    uint32_t mx[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) mx[b] = vec_range<DT, true>(vec[b]);
+#pragma unroll 1
+    for (uint32_t o = vps >> 1; o > 0; o >>= 1) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) mx[b] = range_max<DT>(mx[b], __shfl_xor_sync(0xFFFFFFFFu, mx[b], o));
+    }
+    float2 S[4], R[4];
+    uint32_t S2[4];
+    bool any_bad = false, slow = false;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      float m, unused;
+      range_unpack<DT>(mx[b], &m, &unused);
+      const FpQ qa = fp_segment_params<DT>(m, -m, p.qc);
+      S[b] = make_float2(qa.S, qa.S);
+      R[b] = make_float2(qa.r, qa.r);
+      S2[b] = as_u32(D::from_f32x2(qa.S, qa.S));
+      any_bad |= qa.bad;
+      slow |= qa.slow_div;
+      if (live && v == 0 && jb.scales) reinterpret_cast<uint16_t*>(jb.scales)[quad * 4u + b] = D::from_f32(qa.S);
+    }
+    if (live && any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
+    // ---- element stage: packed quantiser -> info words -> packed group logic -> value table ----
+    uint32_t o[4][4];
+    auto stage = [&](auto slow_c) {
+      constexpr bool kSlow = decltype(slow_c)::value;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t info[4], sg[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t w2 = j == 0 ? vec[b].x : j == 1 ? vec[b].y : j == 2 ? vec[b].z : vec[b].w;
+          const T2 n = kSlow ? ieee_quot2<DT>(from_u32<T2>(w2), S[b]) : fast_quot2<DT>(from_u32<T2>(w2), S[b], R[b]);
+          info[b] = grid.steps_select(n);
+          sg[b] = grid.codec_sign(n);
+        }
+        const uint32_t target = double_approx_target2<DT>(info, hf2, maxe2);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t idx = (info[b] & kDblCodeMask) | target | (sg[b] >> 8);
+          uint16_t lo, hi;
+          asm("ld.shared.u16 %0, [%1];" : "=h"(lo) : "r"(val_saddr + (idx & 0xFFFFu) * 2u));
+          asm("ld.shared.u16 %0, [%1];" : "=h"(hi) : "r"(val_saddr + (idx >> 16) * 2u));
+          const T2 dec = from_u32<T2>((uint32_t)lo | ((uint32_t)hi << 16));
+          o[b][j] = as_u32(__hmul2(dec, from_u32<T2>(S2[b])));  // decoded * scales   quant_linear.py:606
+        }
+      }
+    };
+    if (slow) stage(std::true_type{}); else stage(std::false_type{});
+    if (live) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) stg128(dst + b * seg_bytes, make_uint4(o[b][0], o[b][1], o[b][2], o[b][3]));
     }
   }
 }
@@ -2110,6 +2491,29 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) pertensor_fused_kernel(con
 // ------------------------------------------------------------------------------------------------
 // element-wise test kernels (exhaustive parity checks)
 // ------------------------------------------------------------------------------------------------
+// _fp_scale (fp4_quantize_cpu.py:37-44) with an element-wise scale array: y = grid(clamp(rD(x / S), +-max_float)); the
+// result is NOT multiplied back by S (the caller does that, :72).  IEEE division: S is arbitrary here.
+template <int DT>
+__global__ void fp_scale_kernel(const uint32_t* __restrict__ x, const uint32_t* __restrict__ scale, uint32_t* __restrict__ y, int64_t n_pairs,
+                                const __grid_constant__ QuantConsts qc) {
+  __shared__ FpEntry s_tbl[40];
+  if (threadIdx.x < 40) s_tbl[threadIdx.x] = qc.tbl[threadIdx.x];
+  __syncthreads();
+  using T2 = typename DType<DT>::T2;
+  FpQ q;
+  q.S = 1.0f; q.r = 1.0f; q.mid = 0.f; q.mid_h = 0.f; q.bad = false; q.slow_div = false;
+  FpTable<DT> f;
+  f.setup(q, qc);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_pairs; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 w = DType<DT>::to_f32x2(from_u32<T2>(x[i])), sc = DType<DT>::to_f32x2(from_u32<T2>(scale[i]));
+    const T2 n = DType<DT>::from_f32x2(ieee_div(w.x, sc.x), ieee_div(w.y, sc.y));       // tensor / S                   :38
+    const uint32_t nb = as_u32(n);
+    uint32_t vb = as_u32(f.grid(n, nb, s_tbl));                                          // clamp, log2 scale, round     :39-43
+    vb |= __hneu2_mask(n, n);                                                            // 0 / 0 stays NaN through the clamp
+    y[i] = vb;
+  }
+}
+
 template <int DT>
 __global__ void fp_roundtrip_kernel(const uint32_t* __restrict__ x, uint32_t* __restrict__ y, uint16_t* __restrict__ codes, int64_t n_pairs,
                                     const __grid_constant__ QuantConsts qc) {

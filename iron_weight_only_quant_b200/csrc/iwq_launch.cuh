@@ -74,7 +74,41 @@ cudaError_t launch_col_double(const LaunchParams& p, cudaStream_t st);
 template <int DT, int KIND>
 cudaError_t launch_fused(const LaunchParams& p, const FusedParams& f, bool sym, const LaunchTuning& tune, cudaStream_t st, int* grid_out);
 
+template <int DT>
+cudaError_t launch_seg_double(const LaunchParams& p, cudaStream_t st);
+
+template <int DT, int KIND>
+cudaError_t launch_col_tma(const LaunchParams& p, const TensorMapPair& single, const TensorMapPair* maps, bool sym, const LaunchTuning& tune, cudaStream_t st);
+
 #ifdef IWQ_INSTANTIATE
+
+template <int DT, int KIND, bool SYM>
+static cudaError_t launch_col_tma_one(const LaunchParams& p, const TensorMapPair& single, const TensorMapPair* maps, const LaunchTuning& tune, cudaStream_t st) {
+  auto k = col_tma_kernel<DT, KIND, SYM>;
+  // [step table][mbarriers, 128 B][ring: warps x stages x stage]
+  const size_t smem = p.lut_smem_bytes + 128 + (size_t)kColTmaWarps * p.n_stages * p.stage_bytes;
+  int grid = 0;
+  const uint32_t cta_units = (p.total_units + kColTmaWarps - 1) / kColTmaWarps;
+  cudaError_t e = persistent_grid(k, kColTmaWarps * 32, smem, tune.ctas_per_sm, cta_units, &grid);
+  if (e != cudaSuccess) return e;
+  k<<<grid, kColTmaWarps * 32, smem, st>>>(p, single, maps);
+  return cudaGetLastError();
+}
+template <int DT, int KIND>
+cudaError_t launch_col_tma(const LaunchParams& p, const TensorMapPair& single, const TensorMapPair* maps, bool sym, const LaunchTuning& tune, cudaStream_t st) {
+  return sym ? launch_col_tma_one<DT, KIND, true>(p, single, maps, tune, st) : launch_col_tma_one<DT, KIND, false>(p, single, maps, tune, st);
+}
+
+template <int DT>
+cudaError_t launch_seg_double(const LaunchParams& p, cudaStream_t st) {
+  auto k = seg_double_kernel<DT>;
+  const size_t smem = p.lut_smem_bytes + p.lut_extra_bytes;
+  int grid = 0;
+  cudaError_t e = persistent_grid(k, 256, smem, 0, p.total_units, &grid);
+  if (e != cudaSuccess) return e;
+  k<<<grid, 256, smem, st>>>(p);
+  return cudaGetLastError();
+}
 
 // the fused per-tensor kernel: the grid size is also the arrival-counter target, so it is returned to the caller
 // (who sized the work list for it); `*grid_out` > 0 on entry means "launch with exactly this grid"
@@ -215,6 +249,7 @@ cudaError_t launch_row(const LaunchParams& p, bool sym, int consumers, const Lau
   template cudaError_t launch_seg<DT, KIND>(const LaunchParams&, bool, bool, int, const LaunchTuning&, cudaStream_t);       \
   template cudaError_t launch_row<DT, KIND>(const LaunchParams&, bool, int, const LaunchTuning&, cudaStream_t);   \
   template cudaError_t launch_col<DT, KIND>(const LaunchParams&, bool, const LaunchTuning&, cudaStream_t);            \
+  template cudaError_t launch_col_tma<DT, KIND>(const LaunchParams&, const TensorMapPair&, const TensorMapPair*, bool, const LaunchTuning&, cudaStream_t); \
   template cudaError_t launch_fused<DT, KIND>(const LaunchParams&, const FusedParams&, bool, const LaunchTuning&, cudaStream_t, int*);
 
 #endif  // IWQ_INSTANTIATE

@@ -290,11 +290,14 @@ IWQ_HD IntQ int_segment_params(float mx, float mn, const QuantConsts& c, bool sy
   }
   q.s = rD<DT>(div_const(d, c.max_int, c.inv_div));       // / max_int                          :21 / :28
   q.r = ieee_rcp(q.s);
+  // "suspect": the segment MAY yield NaN (quant_funcs.py:40 asserts on NaN in the result).  s NaN / inf always does;
+  // s == 0 (a range below ~max_int * 2^-25 at >= 9 bits in fp16) does only where an element is 0 (0 / 0) -- a suspect
+  // segment takes the IEEE-division form (w / 0 = inf -> clamps like the reference's) and its outputs are inspected
   q.bad = !(q.s > 0.0f && q.s < INFINITY);
-  q.slow_div = false;
+  q.slow_div = q.bad;
   if (DT == IWQ_BF16) {
     float big = fmaxf(fabsf(mx), sym ? 0.0f : fabsf(mn));
-    q.slow_div = !(big * q.r < 1e37f);
+    q.slow_div = q.bad || !(big * q.r < 1e37f);
   }
   if (sym) {
     q.z = 0.0f;                                           // zeros = 0                          :29

@@ -47,28 +47,33 @@ def quantize_fp16_to_fp4_e1m2(tensor, group_size=128, per_tensor=False, return_s
 
 
 def _fp_scale(tensor, S, M, bias, max_float, min_float):
-    """reference fp4_quantize_cpu.py:37-44 for the case the reference itself uses it in: `tensor` is a 2-D
-    fp16 tensor whose rows are the groups, `S` is the per-row absmax scale `absmax / max_float`, the
-    format is (E, M) with bias = 2^(E-1)-1 and min_float = -max_float.  Returns `tensor_q` (not multiplied
-    back by S).  Other argument combinations are not implemented and raise."""
+    """reference fp4_quantize_cpu.py:37-44: `tensor / S` clamped to +-max_float and rounded (RNE, per-binade scale with the
+    biased exponent clamped to >= 1) onto the (E, M) minifloat grid whose (M, bias, max_float) these are; returns
+    `tensor_q`, NOT multiplied back by S.  `S` is anything that broadcasts against `tensor` (the reference passes the
+    per-row `absmax / max_float`, shape [rows, 1]); fp16 CUDA tensors.  min_float must be -max_float (as in every call of
+    the reference) and the triple must belong to a minifloat format with bias = 2^(E-1)-1."""
     E = None
     for e in range(1, 6):
         if 2 ** (e - 1) - 1 == bias and abs((2 - 2 ** (-M)) * 2 ** (2 ** e - 1 - bias) - max_float) < 1e-6:
             E = e
     if E is None or min_float != -max_float:
         raise NotImplementedError("_fp_scale: only (M, bias, max_float) triples of an (E, M) minifloat with min_float = -max_float")
-    if not (torch.is_tensor(S) and S.numel() == 1 and float(S) == 1.0):
-        raise NotImplementedError("_fp_scale: call quantize_fp16_to_minifloat for scaled groups; only S == 1 is exposed here")
     if tensor.dtype != torch.float16 or not tensor.is_cuda:
         raise RuntimeError("_fp_scale: fp16 CUDA tensor expected")
-    x = tensor.contiguous().reshape(-1)
+    if not torch.is_tensor(S):
+        S = torch.tensor(float(S), dtype=torch.float16, device=tensor.device)
+    S = S.to(device=tensor.device, dtype=torch.float16)
+    shape = torch.broadcast_shapes(tensor.shape, S.shape)
+    x = tensor.expand(shape).contiguous().reshape(-1)
+    s = S.expand(shape).contiguous().reshape(-1)
     pad = x.numel() % 2
     if pad:
         x = torch.cat([x, x.new_zeros(1)])
+        s = torch.cat([s, s.new_ones(1)])
     y = torch.empty_like(x)
     with torch.cuda.device(x.device):
-        rc = _lib.lib().iwq_fp_roundtrip(_lib.IWQ_F16, _lib.SCHEME_FP_RNE, E, int(M), x.data_ptr(), y.data_ptr(), None, x.numel(), torch.cuda.current_stream(x.device).cuda_stream)
+        rc = _lib.lib().iwq_fp_scale(E, int(M), x.data_ptr(), s.data_ptr(), y.data_ptr(), x.numel(), torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(rc)
     if pad:
         y = y[:-1]
-    return y.reshape(tensor.shape)
+    return y.reshape(shape)

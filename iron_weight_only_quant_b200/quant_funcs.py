@@ -37,18 +37,64 @@ def pseudo_quantize_tensor(tensor, n_bits=8, zero_point=True, q_group_size=-1, p
         group = _lib.GROUP_PER_CHANNEL
     if not tensor.is_cuda:
         raise RuntimeError("pseudo_quantize_tensor: tensor must be on a CUDA device (no CPU fallback in iron_weight_only_quant_b200)")
+    if tensor.numel() == 0:
+        return tensor if inplace else tensor.clone()
     src = tensor if tensor.is_contiguous() else tensor.contiguous()
+    if src.data_ptr() % 16 != 0:
+        src = src.clone()  # a view at an odd storage offset: the kernels move 16-byte vectors
     cols = int(org_tensor_shape[-1]) if tensor.dim() > 0 else 1
     rows = src.numel() // max(cols, 1)
-    if src.numel() == 0:
-        return tensor if inplace else tensor.clone()
     out = src if inplace else torch.empty_like(src)
-    cfg = _lib.make_config(src.dtype, _lib.SCHEME_INT, group, bits=n_bits, symmetric=not zero_point)
     check = NAN_CHECK == "sync"
-    _lib.fake_quant_(src, out, cfg, rows, cols, track_status=check)
+    if _kernel_shape_ok(rows, cols, group):
+        cfg = _lib.make_config(src.dtype, _lib.SCHEME_INT, group, bits=n_bits, symmetric=not zero_point)
+        _lib.fake_quant_(src, out, cfg, rows, cols, track_status=check)
+    else:
+        _run_odd_shape(src, out, rows, cols, group, n_bits, zero_point, check)
     if check:
         assert _lib.read_and_clear_status(src.device) & _lib.STATUS_NAN == 0  # quant_funcs.py:40
+    if inplace and out is not tensor:
+        tensor.copy_(out.reshape(org_tensor_shape))  # non-contiguous input: the reference mutates the caller's storage
+        return tensor
     return out.reshape(org_tensor_shape)
+
+
+_MAX_ROW = 51200  # longest segment the one-pass row kernel stages in shared memory
+
+
+def _kernel_shape_ok(rows: int, cols: int, group: int) -> bool:
+    """Shapes the vectorised kernels take directly: every segment a whole number of 16-byte vectors."""
+    if group == _lib.GROUP_PER_TENSOR:
+        return (rows * cols) % 8 == 0
+    seg = cols if group == _lib.GROUP_PER_CHANNEL else group
+    return seg % 8 == 0 and (group > 0 or seg <= _MAX_ROW)
+
+
+def _run_odd_shape(src, out, rows, cols, group, n_bits, zero_point, check):
+    """The reference takes ANY shape (quant_funcs.py:10-15).  Segments that are not a whole number of 16-byte vectors
+    are copied into a padded [segments, seg_pad] buffer whose pad columns repeat each segment's first element (which
+    changes neither its min nor its max), quantised there by the same kernels and copied back; per-channel rows too long
+    for the one-pass row kernel go through the two-pass per-tensor kernels, one job per row."""
+    dev, dt = src.device, src.dtype
+    if group == _lib.GROUP_PER_TENSOR:
+        segs = src.reshape(1, -1)
+    elif group == _lib.GROUP_PER_CHANNEL:
+        segs = src.reshape(rows, cols)
+    else:
+        segs = src.reshape(-1, group)
+    n_seg, seg = segs.shape
+    pad = (-seg) % 8
+    work = torch.cat([segs, segs[:, :1].expand(n_seg, pad)], dim=1).contiguous() if pad else segs.clone()
+    seg_pad = seg + pad
+    if group == _lib.GROUP_PER_TENSOR or seg_pad > _MAX_ROW:
+        cfg = _lib.make_config(dt, _lib.SCHEME_INT, _lib.GROUP_PER_TENSOR, bits=n_bits, symmetric=not zero_point)
+        mats = [_lib.matrix_desc(work[i], work[i], 1, seg_pad) for i in range(n_seg)]
+        rng = torch.empty(2 * n_seg, dtype=torch.float32, device=dev)
+        _lib.per_tensor_batched_(mats, cfg, dev, rng, track_status=check)
+    else:
+        cfg = _lib.make_config(dt, _lib.SCHEME_INT, _lib.GROUP_PER_CHANNEL, bits=n_bits, symmetric=not zero_point)
+        _lib.fake_quant_(work, work, cfg, n_seg, seg_pad, track_status=check)
+    out.reshape(n_seg, seg).copy_(work[:, :seg])
 
 
 @torch.no_grad()

@@ -19,8 +19,8 @@ Also implemented: weight_format='bfp' (block floating point, :648-723); quant_di
 output dimension, :478-483, :640-647) for every scheme; the single aligned ("approximate") decode
 (_fp_decode_aligned, :237-285, driver :470-632) for both quant_dim; the double-approximate decode
 (fp_decode_aligned_double_approx, :288-363) for quant_dim=1 with (out_features / group) % 4 == 0 -- the
-configuration every script of the reference uses.
-Not implemented (raise NotImplementedError): double_approximate with quant_dim=0.
+configuration every script of the reference uses -- and for quant_dim=0 (:484-488) with group 32/64/128/256 and a
+number of segments that is a multiple of 4 (otherwise the reference's groups of four wrap around: NotImplementedError).
 """
 from __future__ import annotations
 

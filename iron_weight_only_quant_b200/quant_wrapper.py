@@ -61,7 +61,10 @@ class _Batcher:
             ql.quantize_weight()  # rare: strided / misaligned storage goes through the single-matrix call
             return
         rows, cols = w.shape
-        key = (w.device, w.dtype, cols if (ql.w_group_size == _lib.GROUP_PER_CHANNEL and cfg.quant_dim == 0) else 0)
+        # one launch = one configuration: the whole iwq_config is part of the key (quantize_linears_batched may be handed
+        # shells that differ in bits / group / format), plus cols for per-channel (a batched launch shares the row length)
+        cfg_key = tuple(getattr(cfg, f) for f, _ in cfg._fields_)
+        key = (w.device, w.dtype, cols if (ql.w_group_size == _lib.GROUP_PER_CHANNEL and cfg.quant_dim == 0) else 0, cfg_key, wants_zeros)
         self.groups[key].append((ql, cfg, w, rows, cols, G, wants_zeros))
         self.bytes[key] += w.numel() * 2
         if self.bytes[key] >= self.threshold[key]:
@@ -73,7 +76,7 @@ class _Batcher:
         self.bytes.pop(key, None)
         if not items:
             return
-        device, dtype, _ = key
+        device, dtype = key[0], key[1]
         cfg = items[0][1]
         # one allocation for all scales (and one for all zero points) of the launch, handed out as views
         n_seg = sum(it[5] for it in items)

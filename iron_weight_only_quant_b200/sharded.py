@@ -114,4 +114,10 @@ def pseudo_quantize_tensors_per_tensor_fused(shards: Sequence[torch.Tensor], n_b
         peers = _lib.Peers(world=st["world"], rank=st["rank"], slot_ptrs=ctypes.cast(st["slot_ptrs"], ctypes.POINTER(ctypes.c_void_p)),
                            flag_ptrs=ctypes.cast(st["flag_ptrs"], ctypes.POINTER(ctypes.c_void_p)), epoch=st["epoch"], spin_limit=0)
     _lib.per_tensor_fused_(mats, cfg, dev, peers, track_status=True)
+    # the exchange waits are bounded: a peer that never arrives raises IWQ_STATUS_TIMEOUT and the kernel goes on with
+    # whatever ranges it has -- never hand such weights back silently.  (One sync per call; this entry point is opt-in.)
+    st = _lib.read_and_clear_status(dev)
+    if st & _lib.STATUS_TIMEOUT:
+        raise RuntimeError("pseudo_quantize_tensors_per_tensor_fused: a peer's ranges did not arrive (IWQ_STATUS_TIMEOUT); the outputs are invalid")
+    assert st & _lib.STATUS_NAN == 0  # quant_funcs.py:40
     return outs

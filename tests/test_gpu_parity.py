@@ -685,9 +685,6 @@ def test_single_approximate_matches_reference_golden(golden, dt, case):
             _from_linear(w, dt, w_group_size=-1, weight_format=wf, approximate=True)  # quant_linear.py:475-476
         with pytest.raises(NotImplementedError):
             _from_linear(w, dt, w_group_size=32, weight_format="int", approximate=True)  # quant_linear.py:601
-        if not (wf == "fp4" and E == 1):
-            with pytest.raises(NotImplementedError):  # double-approximate exists for quant_dim = 1 only
-                _from_linear(w, dt, w_group_size=32, weight_format=wf, approximate=True, double_approximate=True, quant_dim=0, **kw)
     finally:
         quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
 
@@ -735,6 +732,18 @@ def test_double_approximate_matches_reference_golden(golden, dt, case):
         key = f"{dt}_approx_{name}_g128_d1"
         assert_bits(bits(ql.weight.data), g[key + "_out"], dt, key)
         assert np.array_equal(bits(ql.scales.reshape(-1)), g[key + "_scales"]), key + " scales"
+        # quant_dim = 0 (quant_linear.py:484-488): groups of four = the same offset of four consecutive segments
+        ql = _from_linear(w, dt, w_bit=4, w_group_size=32, symmetric=True, weight_format=wf, approximate=True, double_approximate=True, quant_dim=0, **kw)
+        key0 = f"{dt}_approx_{name}_g32_d0"
+        assert_bits(bits(ql.weight.data), g[key0 + "_out"], dt, key0)
+        assert np.array_equal(bits(ql.scales.reshape(-1)), g[key0 + "_scales"]), key0 + " scales"
+        for rows0, cols0, grp0 in [(96, 1024, 128), (33, 512, 64), (20, 768, 256), (64, 96, 32)]:  # ragged last unit, quads spanning rows
+            w0 = seeded(rows0, cols0, dt, 11 + E + grp0)
+            ref0 = O.fp_approx_fake_quant(bits(w0), dt, E, M, grp0, hs, hf, tp, True)
+            ql = _from_linear(w0.to(DEV), dt, w_bit=4, w_group_size=grp0, symmetric=True, weight_format=wf, approximate=True, double_approximate=True, quant_dim=0, **kw)
+            assert_bits(bits(ql.weight.data), ref0["out"], dt, f"{key0} [{rows0},{cols0}] g{grp0}")
+        with pytest.raises(NotImplementedError):  # 3 segments: the reference's groups of four would wrap around
+            _from_linear(seeded(3, 32, dt, 1).to(DEV), dt, w_bit=4, w_group_size=32, symmetric=True, weight_format=wf, approximate=True, double_approximate=True, quant_dim=0, **kw)
         # larger, against the oracle: 16 row blocks, ragged column tile
         wl = seeded(2048, 264, dt, 5 + E)
         ref = O.along_output_dim(O.fp_approx_fake_quant, bits(wl), dt, E, M, 128, hs, hf, tp, True)
