@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(built):
     assert set(built.EXPORTS) == declared
     assert L.iwq_abi_version() == 4
     L.iwq_workspace_bytes.restype = ctypes.c_size_t
-    assert L.iwq_workspace_bytes(10) == 640
+    assert L.iwq_workspace_bytes(10) == 640 + 10 * 256  # job table (64 B each, 128-aligned) + a load/store CUtensorMap pair per matrix
 
 
 def test_argument_validation_without_gpu(built):
