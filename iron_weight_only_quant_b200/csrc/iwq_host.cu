@@ -38,7 +38,7 @@ static int env_int(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 struct Knobs {
-  int seg_stages = env_int("IWQ_SEG_STAGES", 3);
+  int seg_stages = env_int("IWQ_SEG_STAGES", 4);
   int seg_ctas = env_int("IWQ_SEG_CTAS", 0);
   int row_ctas = env_int("IWQ_ROW_CTAS", 0);
   int row_smem_kb = env_int("IWQ_ROW_SMEM_KB", 0);  // per-CTA ring budget; 0 = automatic
@@ -58,7 +58,9 @@ struct Knobs {
                                                      // everything, then one apply pass
   int pt_reverse = env_int("IWQ_PT_REVERSE", 1);     // per-tensor apply pass walks its tiles from the end (most recently read first)
   int pt_hint = env_int("IWQ_PT_HINT", 0);           // LaunchParams::l2_hint bits of the per-tensor apply pass
-  int seg_hint = env_int("IWQ_SEG_HINT", 0);         // LaunchParams::l2_hint bits of the one-pass segment kernels
+  int seg_hint = env_int("IWQ_SEG_HINT", 2);         // LaunchParams::l2_hint bits of the one-pass segment kernels (2: bulk loads evict_last,
+                                                     // +1.3 % on the in-place stream: the bulk store then hits the line it was loaded into)
+  int seg_map = env_int("IWQ_SEG_MAP", 0);           // LaunchParams::tile_map of the seg4 kernels (1: contiguous run of tiles per CTA)
   int fp_mode = env_int("IWQ_FP_MODE", 2);           // seg4 minifloat kernel: 0 step table, 1 interleaved copies of it, 2 direct table
   int fp_rep = env_int("IWQ_FP_REP", 4);             // seg4 minifloat kernel: log2 of the interleaved copies of the step table
                                                      // in shared memory (4 = 16 copies: no bank conflicts); 0 = one copy
@@ -71,6 +73,15 @@ static Knobs& knobs_mut() {
   return k;
 }
 static const Knobs& knobs() { return knobs_mut(); }
+
+// Ring depth of the segment kernels: the wanted depth, clamped so that header + table + ring fit the 227 KB of one CTA (and the
+// per-stage range slots of seg4 fit the header).
+static int fit_seg_stages(int want, size_t lut_bytes, size_t extra_bytes = 0) {
+  int st = want < 2 ? 2 : want;
+  if (st > kSeg4MaxStages) st = kSeg4MaxStages;
+  while (st > 2 && kSmemHeader + lut_bytes + extra_bytes + (size_t)st * kTileBytes > 227u * 1024u) --st;
+  return st;
+}
 
 static int effective_variant(const iwq_config_t* cfg) { return knobs().variant >= 0 ? knobs().variant : cfg->variant; }
 
@@ -352,10 +363,7 @@ static int fill_params(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, c
   p->lps = pl.lps;
   p->vpl = pl.vpl;
   p->stage_bytes = pl.stage_bytes;
-  int st = knobs().seg_stages;
-  if (st < 2) st = 2;
-  if (st > kMaxStages) st = kMaxStages;
-  p->n_stages = pl.path == PATH_SEG ? st : pl.stages;
+  p->n_stages = pl.path == PATH_SEG ? fit_seg_stages(knobs().seg_stages, p->lut_smem_bytes, p->lut_extra_bytes) : pl.stages;
   // measured (profiles/README.md): bulk stores pay off for long rows (22 KB: +3.4 %, 32 KB: +2 %), not for 10..16 KB ones
   p->row_tma_out = (pl.path == PATH_ROW && pl.stages >= 3 && knobs().row_tma_out != 0 && (knobs().row_tma_out > 1 || pl.seg_elems * 2ull >= 20 * 1024)) ? 1u : 0u;
   return IWQ_OK;
@@ -502,7 +510,7 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
         rc = bind_lut();
         if (rc) return rc;
       }
-      if (knobs().fp_stages >= 2) tune.stages = p.n_stages = knobs().fp_stages > kMaxStages ? kMaxStages : knobs().fp_stages;
+      tune.stages = p.n_stages = fit_seg_stages(knobs().fp_stages >= 2 ? knobs().fp_stages : knobs().seg_stages, p.lut_smem_bytes, p.lut_extra_bytes);
     } else if (kind == KIND_FP && knobs().fp_mode == 1 && knobs().fp_rep > 0) {
       // seg4 minifloat kernel: interleaved copies of the step table (no shared-memory bank conflicts in the lookups)
       const QuantConsts base = p.qc;
@@ -518,7 +526,7 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
         rc = bind_lut();
         if (rc) return rc;
       }
-      if (knobs().fp_stages >= 2) tune.stages = p.n_stages = knobs().fp_stages > kMaxStages ? kMaxStages : knobs().fp_stages;
+      tune.stages = p.n_stages = fit_seg_stages(knobs().fp_stages >= 2 ? knobs().fp_stages : knobs().seg_stages, p.lut_smem_bytes, p.lut_extra_bytes);
     }
   }
   if (per_tensor) {
@@ -546,7 +554,7 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
         rc = run_minmax(cfg, p, range_ws, st, false, true);
         if (rc) return rc;
         p.reverse = 1;
-        p.l2_hint = (uint32_t)knobs().pt_hint & 7u;
+        p.l2_hint = (uint32_t)knobs().pt_hint & 23u;
         e = dispatch_seg(cfg->dtype, kind, p, sym, true, variant, tune, st);
         j0 = j1;
       }
@@ -559,12 +567,14 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
       if (minmax_only) return IWQ_OK;
       p.ranges = rng;
       p.reverse = (seg4 && knobs().pt_reverse != 0) ? 1u : 0u;
-      p.l2_hint = (uint32_t)knobs().pt_hint & 7u;
+      p.l2_hint = (uint32_t)knobs().pt_hint & 23u;
+      p.tile_map = (uint32_t)knobs().seg_map;
       e = dispatch_seg(cfg->dtype, kind, p, sym, true, variant, tune, st);
     }
   } else if (pl.path == PATH_SEG) {
     tune.ctas_per_sm = knobs().seg_ctas;
-    p.l2_hint = (uint32_t)knobs().seg_hint & 7u;
+    p.l2_hint = (uint32_t)knobs().seg_hint & 23u;
+    p.tile_map = (uint32_t)knobs().seg_map;
     e = dispatch_seg(cfg->dtype, kind, p, sym, false, variant, tune, st);
   } else {
     tune.ctas_per_sm = knobs().row_ctas;
@@ -840,9 +850,7 @@ int iwq_debug_plan(const iwq_config_t* cfg, int64_t rows, int64_t cols, int32_t*
     int variant = effective_variant(cfg);
     if (variant < 0 || variant > 2) variant = 0;
     if (variant == 0 && !per_tensor && pl.seg_elems < 32) variant = 2;
-    int st = knobs().seg_stages;
-    if (st < 2) st = 2;
-    if (st > kMaxStages) st = kMaxStages;
+    const int st = fit_seg_stages(knobs().seg_stages, lut_bytes);
     out[0] = 0;
     out[1] = variant;
     out[2] = variant == 0 ? (per_tensor ? 1 : (int32_t)(pl.seg_elems / 32)) : pl.lps;
@@ -873,7 +881,7 @@ int iwq_debug_set_knob(const char* name, int value) {
   IWQ_KNOB(seg_stages) IWQ_KNOB(seg_ctas) IWQ_KNOB(row_ctas) IWQ_KNOB(row_smem_kb) IWQ_KNOB(variant) IWQ_KNOB(row_warps) IWQ_KNOB(col_tile)
   IWQ_KNOB(col_ctas) IWQ_KNOB(fused_batch_mb) IWQ_KNOB(fused_lookahead) IWQ_KNOB(row_tma_out) IWQ_KNOB(wide_seg4) IWQ_KNOB(col_mode)
   IWQ_KNOB(col_stages) IWQ_KNOB(pt_slab_mb) IWQ_KNOB(pt_reverse) IWQ_KNOB(pt_hint) IWQ_KNOB(seg_hint) IWQ_KNOB(fp_mode) IWQ_KNOB(fp_rep) IWQ_KNOB(fp_rep_kb)
-  IWQ_KNOB(fp_stages) IWQ_KNOB(host_copy_only)
+  IWQ_KNOB(fp_stages) IWQ_KNOB(host_copy_only) IWQ_KNOB(seg_map)
 #undef IWQ_KNOB
   return fail(IWQ_ERR_INVALID, "unknown knob: " + n);
 }
@@ -958,7 +966,7 @@ int iwq_fake_quant_per_tensor_fused(const iwq_config_t* cfg, const iwq_matrix_t*
   std::vector<Job> jobs;
   rc = fill_params(cfg, ms, n, pl, &p, &jobs);
   if (rc) return rc;
-  if (p.n_stages < 3) p.n_stages = 3;  // the fused kernel parks one stage behind its bulk store across item changes
+  p.n_stages = 3;  // the fused kernel parks one stage behind its bulk store across item changes; its own ring stays at 3 tiles
   for (int i = 0; i < n; ++i)
     if (ms[i].codes) return fail(IWQ_ERR_UNSUPPORTED, "the fused per-tensor entry point does not emit codes");
   p.status = status;

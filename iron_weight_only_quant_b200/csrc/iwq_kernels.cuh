@@ -43,12 +43,24 @@ struct Job {               // one matrix (64 bytes)
   uint64_t pad;
 };
 
-constexpr int kConsumerWarps = 8;
+// Consumer warps per CTA of the segment kernels; a tile is kConsumerWarps x 2 KB.  Measured on the headline workload (one
+// B200, same box, interleaved rounds; tools/r2_exp9..11.sh, tools/tmabench.cu): 8 warps / 16 KB tiles x 3 stages x 3 CTAs per SM
+// 5.90-6.17 TB/s; 16 / 32 KB x 4 x 1: 6.09-6.38; 20 / 40 KB x 4 x 1: 6.15-6.51; 24 / 48 KB x 4 x 1: 6.05-6.52 -- the memory system
+// prefers ONE ring of large bulk copies per SM to three rings of small ones (the copy-only probe shows the same: 16 KB x 3 x 3
+// 6.19, 32 KB x 3 x 1 6.62 TB/s), and 24 warps are what the element stage needs to keep up.
+#ifndef IWQ_CW
+#define IWQ_CW 24
+#endif
+#ifndef IWQ_SEG4_MINB
+#define IWQ_SEG4_MINB 1   // __launch_bounds__ minimum CTAs per SM of seg4_tma_kernel
+#endif
+constexpr int kConsumerWarps = IWQ_CW;
 constexpr int kConsumers = kConsumerWarps * 32;
 constexpr int kVPT = 4;                                  // 128-bit vectors per thread per tile
 constexpr int kTileBytes = kConsumers * kVPT * 16;       // 16 KB
 constexpr int kMaxStages = 8;
-constexpr int kSmemHeader = 1024;                        // barriers + tile contexts + FP table
+constexpr int kSmemHeader = 1024;                        // barriers + tile contexts + range slots
+constexpr int kSeg4MaxStages = (kSmemHeader - 640) / (4 * kConsumerWarps) < kMaxStages ? (kSmemHeader - 640) / (4 * kConsumerWarps) : kMaxStages;  // range slots [stage][warp]
 
 struct LaunchParams {
   const Job* jobs;         // device array (n_jobs > 1) or nullptr -> `single`
@@ -73,7 +85,11 @@ struct LaunchParams {
   uint32_t reverse;        // seg4 / GIVEN: walk the slab's tiles from its end (per-tensor apply pass: the tiles the range pass
                            // read last are still in L2)
   uint32_t l2_hint;        // bit 0: bulk loads evict_first, bit 1: bulk loads evict_last, bit 2: bulk stores evict_first,
-                           // bit 3: minmax kernel walks tiles strided (blockIdx.x + k * gridDim.x) instead of in contiguous runs
+                           // bit 3: minmax kernel walks tiles strided (blockIdx.x + k * gridDim.x) instead of in contiguous runs,
+                           // bit 4: bulk stores evict_last
+  uint32_t tile_map;       // seg4: 0 = CTA b takes tiles b, b + grid, b + 2 grid, ... (a window of grid tiles slides over the work
+                           // list); 1 = CTA b takes the contiguous run [b n / grid, (b + 1) n / grid) -- measured faster for the
+                           // in-place read+write stream (tools/tmabench.cu)
   QuantConsts qc;
 };
 
@@ -384,6 +400,25 @@ struct TileCtx {
   uint32_t pad;
 };
 
+// The sequence of tile numbers one CTA visits (see LaunchParams::tile_map).
+struct TileWalk {
+  uint32_t cur, end, step;
+};
+__device__ __forceinline__ TileWalk make_walk(const LaunchParams& p) {
+  TileWalk w;
+  if (p.tile_map == 1u) {
+    const uint64_t n = p.total_units - p.unit_begin;
+    w.cur = p.unit_begin + (uint32_t)(n * blockIdx.x / gridDim.x);
+    w.end = p.unit_begin + (uint32_t)(n * (blockIdx.x + 1u) / gridDim.x);
+    w.step = 1u;
+  } else {
+    w.cur = p.unit_begin + blockIdx.x;
+    w.end = p.total_units;
+    w.step = gridDim.x;
+  }
+  return w;
+}
+
 __device__ __forceinline__ const Job* job_table(const LaunchParams& p) { return p.n_jobs == 1 ? &p.single : p.jobs; }
 
 // Track the job of `unit`, scanning forward from *cur (units are visited in increasing order).
@@ -501,7 +536,7 @@ __device__ __forceinline__ const FpStep* load_fp_lut(const LaunchParams& p, uint
 
 // ------------------------------------------------------------------------------------------------
 // seg_tma_kernel: TMA bulk-copy ring -> consumer warps
-// shared memory: [0,64) full barriers | [64,128) empty barriers | [128,640) TileCtx[8] | [640,896) seg4 range slots [stage][warp] | [1024,...) LUT, stages
+// shared memory: [0,64) full barriers | [64,128) empty barriers | [128,640) TileCtx[8] | [640,1024) seg4 range slots [stage][warp] | [1024,...) LUT, stages
 // ------------------------------------------------------------------------------------------------
 template <int DT, int KIND, bool SYM, bool GIVEN>
 __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_constant__ LaunchParams p) {
@@ -657,7 +692,7 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
 }
 
 template <int DT, int KIND, bool SYM, bool GIVEN, int LUT = LUT_STEP>
-__global__ void __launch_bounds__(kConsumers + 32, 3) seg4_tma_kernel(const __grid_constant__ LaunchParams p) {
+__global__ void __launch_bounds__(kConsumers + 32, IWQ_SEG4_MINB) seg4_tma_kernel(const __grid_constant__ LaunchParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kMaxStages;
@@ -684,7 +719,8 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) seg4_tma_kernel(const __gr
       Job jb;
       const uint32_t hint = p.l2_hint & 3u;
       const uint64_t pol = hint == 1u ? l2_policy_evict_first() : (hint == 2u ? l2_policy_evict_last() : 0ull);
-      for (uint32_t seq = p.unit_begin + blockIdx.x; seq < p.total_units; seq += gridDim.x) {
+      const TileWalk walk = make_walk(p);
+      for (uint32_t seq = walk.cur; seq < walk.end; seq += walk.step) {
         const uint32_t tile = p.reverse ? p.total_units - 1u - (seq - p.unit_begin) : seq;
         mbar_wait(&empty[stage], phase ^ 1u);
         advance_job(p, tile, &cur, &jb);
@@ -707,11 +743,12 @@ __global__ void __launch_bounds__(kConsumers + 32, 3) seg4_tma_kernel(const __gr
   const int lps = p.lps;                      // lanes per segment = group / 32 (1..32); unused when GIVEN
   const uint32_t lane_vec = (uint32_t)warp * 128u + (uint32_t)lane * 4u;  // first vector of this lane in the tile
   const uint32_t rot = (uint32_t)lane >> 1;
-  const bool store_hint = (p.l2_hint & 4u) != 0;
-  const uint64_t store_pol = l2_policy_evict_first();
+  const bool store_hint = (p.l2_hint & (4u | 16u)) != 0;
+  const uint64_t store_pol = (p.l2_hint & 16u) ? l2_policy_evict_last() : l2_policy_evict_first();
   int stage = 0, prev_stage = -1;
   uint32_t phase = 0;
-  for (uint32_t tile = p.unit_begin + blockIdx.x; tile < p.total_units; tile += gridDim.x) {
+  const TileWalk walk = make_walk(p);
+  for (uint32_t seq = walk.cur; seq < walk.end; seq += walk.step) {
     mbar_wait(&full[stage], phase);
     const TileCtx t = ctx[stage];
     uint8_t* lbase = data + (size_t)stage * kTileBytes + (size_t)lane_vec * 16;

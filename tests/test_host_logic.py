@@ -197,10 +197,10 @@ def test_dispatch_plan_for_the_baseline_shapes(built):
         return list(out)
 
     SEG, ROW, COL_ASYNC, COL_REG, COL_2SWEEP, COL_DOUBLE, COL_TMA = range(7)
-    # per-group: seg4 (variant 0), lanes per segment = group / 32, 3 stages
+    # per-group: seg4 (variant 0), lanes per segment = group / 32, 4 stages of 48 KB (one CTA per SM)
     for g, lps in [(32, 1), (64, 2), (128, 4), (256, 8), (1024, 32)]:
         p = plan(8192, 8192, group=g, bits=4)
-        assert p[0] == SEG and p[1] == 0 and p[2] == lps and p[3] == 3, (g, p)
+        assert p[0] == SEG and p[1] == 0 and p[2] == lps and p[3] == 4, (g, p)
     assert plan(64, 256, group=16, bits=4)[:2] == [SEG, 2]  # groups below 32 elements: one vector per lane-iteration
     assert plan(4096, 4096, group=-1, bits=4)[:3] == [SEG, 0, 1]  # per-tensor apply pass
     # per-channel: 2048 / 4096-wide rows through seg4 with 2 / 4 warps per row; others through the row kernel

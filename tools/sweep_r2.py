@@ -128,7 +128,7 @@ def main():
             else:
                 ts = sorted(times[ks])
                 med = ts[len(ts) // 2]
-                print(json.dumps({"config": name, "knobs": ks, "ms_median": med, "GBps": n * 4 / med / 1e6, "GBps_best": n * 4 / ts[0] / 1e6, "GBps_worst": n * 4 / ts[-1] / 1e6, "rounds": len(ts)}), flush=True)
+                print(json.dumps({"config": name, "knobs": ks, "ms_median": med, "GBps": n * 4 / med / 1e6, "GBps_best": n * 4 / ts[0] / 1e6, "GBps_worst": n * 4 / ts[-1] / 1e6, "rounds": len(ts), "GBps_all": [round(n * 4 / t / 1e6) for t in times[ks]]}), flush=True)
         for k_, v in defaults.items():
             L.iwq_debug_set_knob(k_.encode(), v)
 
