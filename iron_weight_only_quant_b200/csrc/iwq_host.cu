@@ -52,6 +52,8 @@ struct Knobs {
   int wide_seg4 = env_int("IWQ_WIDE_SEG4", 1);       // 1: segments of 2048/4096/8192 elements go through seg4_tma_kernel
   int col_mode = env_int("IWQ_COL_MODE", 2);         // 2: 2-D tensor-map boxes (col_tma_kernel), 0: warp-private cp.async ring
                                                      // (col_async_kernel), 1: register-resident (col_reg_kernel)
+  int col_box = env_int("IWQ_COL_BOX", 0);           // col_tma_kernel: columns per box (32 / 64 / 128 / 256); 0 = 4096 / group (8 KB boxes)
+  int col_hint = env_int("IWQ_COL_HINT", 0);         // col_tma_kernel: L2 policy of the tensor loads (1 evict_first, 2 evict_last)
   int col_stages = env_int("IWQ_COL_STAGES", 0);     // ring depth of col_async_kernel (1..4); 0 = automatic
   int pt_slab_mb = env_int("IWQ_PT_SLAB_MB", 0);     // per-tensor: range pass -> apply pass per slab of whole matrices of at most this
                                                      // many MB (the apply pass then finds the slab in L2); 0 = one range pass over
@@ -60,6 +62,9 @@ struct Knobs {
   int pt_hint = env_int("IWQ_PT_HINT", 0);           // LaunchParams::l2_hint bits of the per-tensor apply pass
   int seg_hint = env_int("IWQ_SEG_HINT", 2);         // LaunchParams::l2_hint bits of the one-pass segment kernels (2: bulk loads evict_last,
                                                      // +1.3 % on the in-place stream: the bulk store then hits the line it was loaded into)
+  int mm_tma = env_int("IWQ_MM_TMA", 1);             // per-tensor range pass: 1 = bulk-copy ring (minmax_tma_kernel), 0 = 128-bit global loads
+  int mm_stages = env_int("IWQ_MM_STAGES", 2);       // ... its ring depth (2 x 48 KB measured best: 7.26 TB/s vs 6.73 with 4, 6.9 for the global loads)
+  int mm_hint = env_int("IWQ_MM_HINT", 0);           // ... L2 policy of its bulk loads (1 evict_first, 2 evict_last)
   int seg_map = env_int("IWQ_SEG_MAP", 0);           // LaunchParams::tile_map of the seg4 kernels (1: contiguous run of tiles per CTA)
   int fp_mode = env_int("IWQ_FP_MODE", 2);           // seg4 minifloat kernel: 0 step table, 1 interleaved copies of it, 2 direct table
   int fp_rep = env_int("IWQ_FP_REP", 4);             // seg4 minifloat kernel: log2 of the interleaved copies of the step table
@@ -391,8 +396,24 @@ static int run_minmax(const iwq_config_t* cfg, const LaunchParams& base, float* 
   int grid = 0;
   cudaError_t e;
   const bool sym = p.qc.symmetric != 0;
+  const bool tma = knobs().mm_tma != 0;
+  if (tma) {
+    p.n_stages = fit_seg_stages(knobs().mm_stages, 0);
+    p.tile_map = strided ? 0u : 1u;
+    p.l2_hint = (uint32_t)knobs().mm_hint & 3u;
+  }
+  const size_t tma_smem = kSmemHeader + (size_t)p.n_stages * kTileBytes;
 #define IWQ_MM(DT, SYM)                                                                \
   do {                                                                                 \
+    if (tma) {                                                                         \
+      auto k = minmax_tma_kernel<DT, SYM>;                                             \
+      e = persistent_grid(k, kConsumers + 32, tma_smem, 0, p.total_units - p.unit_begin, &grid); \
+      if (e == cudaSuccess) {                                                          \
+        k<<<grid, kConsumers + 32, tma_smem, st>>>(p);                                 \
+        e = cudaGetLastError();                                                        \
+      }                                                                                \
+      break;                                                                           \
+    }                                                                                  \
     auto k = minmax_kernel<DT, SYM>;                                                   \
     e = persistent_grid(k, kConsumers, 0, 0, p.total_units - p.unit_begin, &grid);     \
     if (e == cudaSuccess) {                                                            \
@@ -661,6 +682,8 @@ static cudaError_t dispatch_col_tma(int dt, int kind, const LaunchParams& p, con
 static uint32_t col_tma_tile(int64_t g) {
   if (knobs().col_mode != 2) return 0;
   if (g != 32 && g != 64 && g != 128 && g != 256) return 0;
+  const int b = knobs().col_box;
+  if ((b == 32 || b == 64 || b == 128 || b == 256) && (int64_t)b * g * 2 <= 48 * 1024 && (int64_t)b * g >= 2048) return (uint32_t)b;
   return g == 32 ? 128u : g == 64 ? 64u : 32u;
 }
 
@@ -720,7 +743,8 @@ static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, Launc
     //      parameters for a single matrix ----
     p.stage_bytes = (uint32_t)cfg->group * tma_tile * 2u;
     p.n_stages = knobs().col_stages == 1 ? 1 : 2;
-    if (cfg->group == 256 && knobs().col_stages == 0) p.n_stages = 1;  // 16 KB boxes: one stage, more resident warps
+    if (p.stage_bytes >= 16384 && knobs().col_stages == 0) p.n_stages = 1;  // 16 KB boxes: one stage, more resident warps
+    p.l2_hint = (uint32_t)knobs().col_hint & 3u;
     std::vector<TensorMapPair> maps((size_t)n);
     for (int i = 0; i < n; ++i) {
       rc = encode_map(&maps[i].in, ms[i].w, ms[i].rows, ms[i].cols, (uint32_t)cfg->group, tma_tile);
@@ -881,7 +905,7 @@ int iwq_debug_set_knob(const char* name, int value) {
   IWQ_KNOB(seg_stages) IWQ_KNOB(seg_ctas) IWQ_KNOB(row_ctas) IWQ_KNOB(row_smem_kb) IWQ_KNOB(variant) IWQ_KNOB(row_warps) IWQ_KNOB(col_tile)
   IWQ_KNOB(col_ctas) IWQ_KNOB(fused_batch_mb) IWQ_KNOB(fused_lookahead) IWQ_KNOB(row_tma_out) IWQ_KNOB(wide_seg4) IWQ_KNOB(col_mode)
   IWQ_KNOB(col_stages) IWQ_KNOB(pt_slab_mb) IWQ_KNOB(pt_reverse) IWQ_KNOB(pt_hint) IWQ_KNOB(seg_hint) IWQ_KNOB(fp_mode) IWQ_KNOB(fp_rep) IWQ_KNOB(fp_rep_kb)
-  IWQ_KNOB(fp_stages) IWQ_KNOB(host_copy_only) IWQ_KNOB(seg_map)
+  IWQ_KNOB(fp_stages) IWQ_KNOB(host_copy_only) IWQ_KNOB(seg_map) IWQ_KNOB(mm_tma) IWQ_KNOB(mm_stages) IWQ_KNOB(mm_hint) IWQ_KNOB(col_box) IWQ_KNOB(col_hint)
 #undef IWQ_KNOB
   return fail(IWQ_ERR_INVALID, "unknown knob: " + n);
 }

@@ -1573,6 +1573,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const TensorMap2D* m
                "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const TensorMap2D* map, uint32_t c0, uint32_t c1, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(smem_dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const TensorMap2D* map, uint32_t c0, uint32_t c1, const void* smem_src) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(smem_src)) : "memory");
 }
@@ -1651,7 +1656,8 @@ __global__ void __launch_bounds__(kColTmaWarps * 32) col_tma_kernel(const __grid
       fenced = cur_l;
     }
     mbar_arrive_expect_tx(&bars[st], stage_bytes);
-    tma_load_2d(ring + (size_t)st * stage_bytes, &t.map->in, t.c0, t.c1, &bars[st]);
+    if (p.l2_hint & 3u) tma_load_2d_hint(ring + (size_t)st * stage_bytes, &t.map->in, t.c0, t.c1, &bars[st], (p.l2_hint & 1u) ? l2_policy_evict_first() : l2_policy_evict_last());
+    else tma_load_2d(ring + (size_t)st * stage_bytes, &t.map->in, t.c0, t.c1, &bars[st]);
   };
 
   const uint32_t first = blockIdx.x * (uint32_t)kColTmaWarps + (uint32_t)warp;
@@ -2099,6 +2105,112 @@ __global__ void __launch_bounds__(kConsumers) minmax_kernel(const __grid_constan
     }
 #pragma unroll
     for (int it = 0; it < kVPT; ++it) acc = range_max<DT>(acc, vec_range<DT, SYM>(v[it]));
+  }
+  if (acc_job >= 0) flush(acc_job);
+}
+
+// ------------------------------------------------------------------------------------------------
+// minmax_tma_kernel: the same range pass fed by the bulk-copy ring of seg4_tma_kernel (read only: a stage goes back to the
+// producer as soon as its vectors are in registers).  One CTA per SM, 48 KB tiles, contiguous run of tiles per CTA (so the block
+// reduction + atomics run once per (CTA, matrix)).  tools/tmabench.cu: a read-only ring of this shape streams at 7.1 TB/s, the
+// 128-bit global loads of minmax_kernel at 4.9-6 TB/s on the shard sizes of the 8-GPU per-tensor configuration.
+// shared memory: barriers and TileCtx as in seg4 (TileCtx::pad carries the job index) | [640, ...) per-warp partial ranges | ring
+// ------------------------------------------------------------------------------------------------
+template <int DT, bool SYM>
+__global__ void __launch_bounds__(kConsumers + 32, 1) minmax_tma_kernel(const __grid_constant__ LaunchParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + kMaxStages;
+  TileCtx* ctx = reinterpret_cast<TileCtx*>(smem + 128);
+  uint32_t* s_part = reinterpret_cast<uint32_t*>(smem + 640);
+  uint8_t* data = smem + kSmemHeader;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_stages = p.n_stages;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kConsumerWarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const TileWalk walk = make_walk(p);
+
+  if (warp == kConsumerWarps) {
+    if (lane == 0) {
+      int stage = 0, cur = -1;
+      uint32_t phase = 0;
+      Job jb;
+      const uint32_t hint = p.l2_hint & 3u;
+      const uint64_t pol = hint == 1u ? l2_policy_evict_first() : (hint == 2u ? l2_policy_evict_last() : 0ull);
+      for (uint32_t tile = walk.cur; tile < walk.end; tile += walk.step) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        advance_job(p, tile, &cur, &jb);
+        TileCtx t = make_tile_ctx(p, jb, cur, tile, false);
+        t.pad = (uint32_t)cur;
+        ctx[stage] = t;
+        const uint32_t bytes = t.n_vec * 16u;
+        mbar_arrive_expect_tx(&full[stage], bytes);
+        if (hint) tma_load_1d_hint(data + (size_t)stage * kTileBytes, jb.src + (t.vec0 << 4), bytes, &full[stage], pol);
+        else tma_load_1d(data + (size_t)stage * kTileBytes, jb.src + (t.vec0 << 4), bytes, &full[stage]);
+        if (++stage == n_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    return;
+  }
+
+  const uint32_t ident = SYM ? 0u : (DT == IWQ_F16 ? 0xFC00FC00u : 0xFF80FF80u);
+  uint32_t acc = ident;
+  int acc_job = -1;
+  auto flush = [&](int job) {  // all consumer warps (the tile sequence is CTA-uniform)
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) acc = range_max<DT>(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, o));
+    if (lane == 0) s_part[warp] = acc;
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+    if (threadIdx.x == 0) {
+      uint32_t all = s_part[0];
+      for (int w = 1; w < kConsumerWarps; ++w) all = range_max<DT>(all, s_part[w]);
+      float mx, mn;
+      range_unpack<DT>(all, &mx, &mn);
+      atomic_max_float(&p.ranges_out[2 * job], mx);
+      if (!SYM) atomic_max_float(&p.ranges_out[2 * job + 1], -mn);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+    acc = ident;
+  };
+  const uint32_t lane_vec = (uint32_t)warp * 128u + (uint32_t)lane * 4u;
+  const uint32_t rot = (uint32_t)lane >> 1;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (uint32_t tile = walk.cur; tile < walk.end; tile += walk.step) {
+    mbar_wait(&full[stage], phase);
+    const uint32_t n_vec = ctx[stage].n_vec;
+    const int job = (int)ctx[stage].pad;
+    if (job != acc_job) {
+      if (acc_job >= 0) flush(acc_job);
+      acc_job = job;
+    }
+    const uint8_t* lbase = data + (size_t)stage * kTileBytes + (size_t)lane_vec * 16;
+    uint4 v[4];
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t j = (k + rot) & 3u;
+      ok[k] = lane_vec + j < n_vec;
+      v[k] = ok[k] ? lds128(lbase + j * 16) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);  // the vectors are in registers: hand the stage back
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (ok[k]) acc = range_max<DT>(acc, vec_range<DT, SYM>(v[k]));
+    if (++stage == n_stages) {
+      stage = 0;
+      phase ^= 1u;
+    }
   }
   if (acc_job >= 0) flush(acc_job);
 }
