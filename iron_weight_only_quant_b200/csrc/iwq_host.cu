@@ -50,10 +50,11 @@ struct Knobs {
   int fused_lookahead = env_int("IWQ_FUSED_LOOKAHEAD", 2); // ... and how many batches the range pass runs ahead
   int row_tma_out = env_int("IWQ_ROW_TMA_OUT", 1);   // row kernel: bulk stores instead of STG.128 when the ring has >= 3 stages
   int wide_seg4 = env_int("IWQ_WIDE_SEG4", 1);       // 1: segments of 2048/4096/8192 elements go through seg4_tma_kernel
-  int col_mode = env_int("IWQ_COL_MODE", 2);         // 2: 2-D tensor-map boxes (col_tma_kernel), 0: warp-private cp.async ring
+  int col_mode = env_int("IWQ_COL_MODE", 3);         // 3: CTA-wide ring of 128 x 256 tensor-map tiles (col_wide_kernel; group 32 / 64 / 128),
+                                                     // 2: warp-private 2-D tensor-map boxes (col_tma_kernel), 0: warp-private cp.async ring
                                                      // (col_async_kernel), 1: register-resident (col_reg_kernel)
   int col_box = env_int("IWQ_COL_BOX", 0);           // col_tma_kernel: columns per box (32 / 64 / 128 / 256); 0 = 4096 / group (8 KB boxes)
-  int col_hint = env_int("IWQ_COL_HINT", 0);         // col_tma_kernel: L2 policy of the tensor loads (1 evict_first, 2 evict_last)
+  int col_hint = env_int("IWQ_COL_HINT", 2);         // col_tma_kernel: L2 policy of the tensor loads (1 evict_first, 2 evict_last)
   int col_stages = env_int("IWQ_COL_STAGES", 0);     // ring depth of col_async_kernel (1..4); 0 = automatic
   int pt_slab_mb = env_int("IWQ_PT_SLAB_MB", 0);     // per-tensor: range pass -> apply pass per slab of whole matrices of at most this
                                                      // many MB (the apply pass then finds the slab in L2); 0 = one range pass over
@@ -218,6 +219,17 @@ static cudaError_t dispatch_fused(int dt, int kind, const LaunchParams& p, const
 }
 
 // quant_dim = 1 (segments down the rows): one launch of col_kernel over all matrices
+// rows per tile of col_wide_kernel: 128 when three 64 KB stages fit next to the partial ranges, the published constants of both
+// consumer groups and the step table; else 64 (32 KB tiles)
+static size_t col_wide_fixed(int64_t g, int kind, uint32_t lut_bytes, uint32_t rows_per_tile) {
+  const size_t words = kind == KIND_INT_GENERIC ? 16 : (kind == KIND_BFP ? 4 : 8);  // PreparedPair<..>::kWords
+  return (size_t)kColWideHeader + lut_bytes + kColWidePart + (size_t)kColWideGroups * (rows_per_tile / (uint32_t)g) * 128 * words * 4;
+}
+static uint32_t col_wide_rows(int64_t g, int kind, uint32_t lut_bytes) {
+  if (g <= 64 && (col_wide_fixed(g, kind, lut_bytes, kColWideRows) + 3u * kColWideTile > 227u * 1024u || knobs().col_box == 64)) return 64;
+  return kColWideRows;
+}
+
 static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, LaunchParams& p, int kind, void* workspace, size_t ws_bytes, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
@@ -680,7 +692,7 @@ static cudaError_t dispatch_col_tma(int dt, int kind, const LaunchParams& p, con
 
 // tile shape of col_tma_kernel: 8 KB boxes (g rows x 4096 / g columns; 64-byte rows at least) -> columns per tile, 0 = not applicable
 static uint32_t col_tma_tile(int64_t g) {
-  if (knobs().col_mode != 2) return 0;
+  if (knobs().col_mode != 2 && knobs().col_mode != 3) return 0;
   if (g != 32 && g != 64 && g != 128 && g != 256) return 0;
   const int b = knobs().col_box;
   if ((b == 32 || b == 64 || b == 128 || b == 256) && (int64_t)b * g * 2 <= 48 * 1024 && (int64_t)b * g >= 2048) return (uint32_t)b;
@@ -693,7 +705,11 @@ static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, Launc
   int rpl = 0, stages = 0;
   const uint32_t tma_tile = (cfg->group > 0 && p.qc.approx != 2) ? col_tma_tile(cfg->group) : 0u;
   const uint32_t ctile = tma_tile ? tma_tile : ((cfg->group > 0 && p.qc.approx != 2) ? col_tile_for(cfg->group, &rpl, &stages) : 0u);
-  const uint32_t unit_cols = ctile ? ctile : (uint32_t)kColTile;
+  // col_wide_kernel: 128 x 256 tiles through a CTA-wide ring (every matrix must hold at least one full tile)
+  bool wide = tma_tile && knobs().col_mode == 3 && (cfg->group == 32 || cfg->group == 64 || cfg->group == 128);
+  for (int i = 0; i < n && wide; ++i) wide = ms[i].rows >= kColWideRows && ms[i].cols >= kColWideCols;
+  const int64_t wide_rows = wide ? (int64_t)col_wide_rows(cfg->group, kind, p.lut_smem_bytes) : 0;
+  const uint32_t unit_cols = wide ? (uint32_t)kColWideCols : (ctile ? ctile : (uint32_t)kColTile);
   for (int i = 0; i < n; ++i) {
     int rc = check_matrix(&ms[i]);
     if (rc) return rc;
@@ -718,6 +734,7 @@ static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, Launc
       if (row_blocks % 4 != 0) return fail(IWQ_ERR_UNSUPPORTED, "double-approximate decode needs (rows / group) % 4 == 0");
       row_blocks /= 4;
     }
+    if (wide) row_blocks = (uint64_t)((rows + wide_rows - 1) / wide_rows);
     units += row_blocks * (uint64_t)((cols + unit_cols - 1) / unit_cols);
     if (units >= 0xFFFFFFFFull) return fail(IWQ_ERR_INVALID, "too much work for one launch");
     jobs.push_back(j);
@@ -746,7 +763,27 @@ static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, Launc
     if (p.stage_bytes >= 16384 && knobs().col_stages == 0) p.n_stages = 1;  // 16 KB boxes: one stage, more resident warps
     p.l2_hint = (uint32_t)knobs().col_hint & 3u;
     std::vector<TensorMapPair> maps((size_t)n);
-    for (int i = 0; i < n; ++i) {
+    if (wide) {
+      // load boxes of TR rows x 256 columns, store boxes of TR / 8 rows x 256 columns (one per consumer warp).  TR = 128 when three
+      // 64 KB stages fit next to the partial ranges / published constants / step table, else 64 (32 KB tiles, up to 6 stages)
+      p.col_wide = 1;
+      p.col_tile = kColWideCols;
+      const uint32_t tr = (uint32_t)wide_rows;
+      auto fixed_for = [&](uint32_t rows_per_tile) { return col_wide_fixed(cfg->group, kind, p.lut_smem_bytes, rows_per_tile); };
+      p.col_rows = tr;
+      p.stage_bytes = tr * (uint32_t)(kColWideCols * 2);
+      int stg = knobs().col_stages > 0 ? knobs().col_stages : (tr == 128 ? 3 : 6);
+      if (stg > 8) stg = 8;  // ColWideCtx ctxs[8]
+      while (stg > 1 && fixed_for(tr) + (size_t)stg * p.stage_bytes > 227u * 1024u) --stg;
+      p.n_stages = stg;
+      for (int i = 0; i < n; ++i) {
+        rc = encode_map(&maps[i].in, ms[i].w, ms[i].rows, ms[i].cols, tr, kColWideCols);
+        if (rc) return rc;
+        rc = encode_map(&maps[i].out, ms[i].out, ms[i].rows, ms[i].cols, tr / kColWideWG, kColWideCols);
+        if (rc) return rc;
+      }
+    }
+    for (int i = 0; i < n && !wide; ++i) {
       rc = encode_map(&maps[i].in, ms[i].w, ms[i].rows, ms[i].cols, (uint32_t)cfg->group, tma_tile);
       if (rc) return rc;
       if (ms[i].out == ms[i].w) maps[i].out = maps[i].in;
@@ -852,6 +889,17 @@ int iwq_debug_plan(const iwq_config_t* cfg, int64_t rows, int64_t cols, int32_t*
       return IWQ_OK;
     }
     int rpl = 0, stages = 0;
+    if (cfg->group > 0 && col_tma_tile(cfg->group) && knobs().col_mode == 3 && (cfg->group == 32 || cfg->group == 64 || cfg->group == 128) && rows >= kColWideRows &&
+        cols >= kColWideCols) {
+      out[0] = 7;  // col_wide_kernel
+      const uint32_t tr = col_wide_rows(cfg->group, kind, lut_bytes);
+      int stg = tr == 128 ? 3 : 6;
+      while (stg > 1 && col_wide_fixed(cfg->group, kind, lut_bytes, tr) + (size_t)stg * tr * 512u > 227u * 1024u) --stg;
+      out[3] = stg;
+      out[5] = (int32_t)(tr * 512u);
+      out[7] = kColWideCols;
+      return IWQ_OK;
+    }
     if (cfg->group > 0 && col_tma_tile(cfg->group)) {
       out[0] = 6;  // col_tma_kernel
       out[3] = (knobs().col_stages == 1 || (cfg->group == 256 && knobs().col_stages == 0)) ? 1 : 2;

@@ -87,6 +87,8 @@ struct LaunchParams {
   uint32_t l2_hint;        // bit 0: bulk loads evict_first, bit 1: bulk loads evict_last, bit 2: bulk stores evict_first,
                            // bit 3: minmax kernel walks tiles strided (blockIdx.x + k * gridDim.x) instead of in contiguous runs,
                            // bit 4: bulk stores evict_last
+  uint32_t col_wide;       // quant_dim = 1: 1 = col_wide_kernel (128 x 256 tiles, CTA-wide ring) instead of col_tma_kernel
+  uint32_t col_rows;       // ... rows per tile (128 or 64)
   uint32_t tile_map;       // seg4: 0 = CTA b takes tiles b, b + grid, b + 2 grid, ... (a window of grid tiles slides over the work
                            // list); 1 = CTA b takes the contiguous run [b n / grid, (b + 1) n / grid) -- measured faster for the
                            // in-place read+write stream (tools/tmabench.cu)
@@ -997,6 +999,20 @@ struct PreparedPairInt {
     f.r.y = __shfl_sync(0xFFFFFFFFu, o.f.r.y, src);
     f.slow_div = __shfl_sync(0xFFFFFFFFu, (int)o.f.slow_div, src) != 0;
   }
+  // generic field exchange (col_wide_kernel hands the constants round through shared memory): x maps every per-pair word
+  static constexpr int kWords = 8;
+  template <class X>
+  __device__ __forceinline__ void map_from(const PreparedPairInt& o, X x) {
+    using T2 = typename DType<DT>::T2;
+    f.lo2 = from_u32<T2>(x(as_u32(o.f.lo2)));
+    f.hi2 = from_u32<T2>(x(as_u32(o.f.hi2)));
+    f.s2 = from_u32<T2>(x(as_u32(o.f.s2)));
+    f.s.x = __uint_as_float(x(__float_as_uint(o.f.s.x)));
+    f.s.y = __uint_as_float(x(__float_as_uint(o.f.s.y)));
+    f.r.x = __uint_as_float(x(__float_as_uint(o.f.r.x)));
+    f.r.y = __uint_as_float(x(__float_as_uint(o.f.r.y)));
+    f.slow_div = x((uint32_t)o.f.slow_div) != 0u;
+  }
   template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const {
     typename DType<DT>::T2 d;
@@ -1028,6 +1044,21 @@ struct PreparedPair<DT, KIND_INT_GENERIC> {
       d.hi = __shfl_sync(0xFFFFFFFFu, q.hi, src);
       d.bad = __shfl_sync(0xFFFFFFFFu, (int)q.bad, src) != 0;
       d.slow_div = __shfl_sync(0xFFFFFFFFu, (int)q.slow_div, src) != 0;
+    };
+    one(qa, o.qa);
+    one(qb, o.qb);
+  }
+  static constexpr int kWords = 16;
+  template <class X>
+  __device__ __forceinline__ void map_from(const PreparedPair& o, X x) {
+    auto one = [&](IntQ& d, const IntQ& q) {
+      d.s = __uint_as_float(x(__float_as_uint(q.s)));
+      d.r = __uint_as_float(x(__float_as_uint(q.r)));
+      d.z = __uint_as_float(x(__float_as_uint(q.z)));
+      d.lo = __uint_as_float(x(__float_as_uint(q.lo)));
+      d.hi = __uint_as_float(x(__float_as_uint(q.hi)));
+      d.bad = x((uint32_t)q.bad) != 0u;
+      d.slow_div = x((uint32_t)q.slow_div) != 0u;
     };
     one(qa, o.qa);
     one(qb, o.qb);
@@ -1064,6 +1095,20 @@ struct PreparedPair<DT, KIND_FP> {
     f.r.y = __shfl_sync(0xFFFFFFFFu, o.f.r.y, src);
     f.slow_div = __shfl_sync(0xFFFFFFFFu, (int)o.f.slow_div, src) != 0;
   }
+  static constexpr int kWords = 8;
+  template <class X>
+  __device__ __forceinline__ void map_from(const PreparedPair& o, X x) {
+    using T2 = typename DType<DT>::T2;
+    f = o.f;  // launch-uniform members
+    f.S2 = from_u32<T2>(x(as_u32(o.f.S2)));
+    f.mid2 = from_u32<T2>(x(as_u32(o.f.mid2)));
+    f.midh2 = from_u32<T2>(x(as_u32(o.f.midh2)));
+    f.S.x = __uint_as_float(x(__float_as_uint(o.f.S.x)));
+    f.S.y = __uint_as_float(x(__float_as_uint(o.f.S.y)));
+    f.r.x = __uint_as_float(x(__float_as_uint(o.f.r.x)));
+    f.r.y = __uint_as_float(x(__float_as_uint(o.f.r.y)));
+    f.slow_div = x((uint32_t)o.f.slow_div) != 0u;
+  }
   template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const {
     typename DType<DT>::T2 v;
@@ -1088,6 +1133,15 @@ struct PreparedPair<DT, KIND_BFP> {
     f.step.y = __shfl_sync(0xFFFFFFFFu, o.f.step.y, src);
     f.inv_step.x = __shfl_sync(0xFFFFFFFFu, o.f.inv_step.x, src);
     f.inv_step.y = __shfl_sync(0xFFFFFFFFu, o.f.inv_step.y, src);
+  }
+  static constexpr int kWords = 4;
+  template <class X>
+  __device__ __forceinline__ void map_from(const PreparedPair& o, X x) {
+    f = o.f;
+    f.step.x = __uint_as_float(x(__float_as_uint(o.f.step.x)));
+    f.step.y = __uint_as_float(x(__float_as_uint(o.f.step.y)));
+    f.inv_step.x = __uint_as_float(x(__float_as_uint(o.f.inv_step.x)));
+    f.inv_step.y = __uint_as_float(x(__float_as_uint(o.f.inv_step.y)));
   }
   template <bool SYM, int SLOW = -1>
   __device__ __forceinline__ uint32_t apply(uint32_t w2, const QuantConsts&) const { return f.apply(w2); }
@@ -1771,6 +1825,261 @@ __global__ void __launch_bounds__(kColTmaWarps * 32) col_tma_kernel(const __grid
       tma_store_commit();
     }
     if (n_stages == 2) st ^= 1;
+  }
+  if (lane == 0) tma_store_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------------
+// col_wide_kernel (quant_dim = 1, group 32 / 64 / 128): ONE CTA per SM streams [128 rows x 256 columns] tiles (64 KB) through a
+// ring fed by 2-D tensor-map loads with 512-byte rows -- the seg4 lesson applied to the column-grouped layout: one ring of large
+// bulk copies per SM instead of many warp-private 8 KB boxes with 64-byte rows.
+//   * producer warp: one cp.async.bulk.tensor.2d per tile (box 256 x 128);
+//   * 16 consumer warps, warp w owns rows 8w .. 8w+7 of the tile, lane L the 16-byte chunk L of a row (8 columns): a warp-wide
+//     LDS.128 / STS.128 covers one dense 512-byte row (conflict-free), and a lane's 8 columns never change;
+//   * sweep 1: per-lane column ranges over its 8 rows -> per-warp partials in shared memory -> barrier (consumers only);
+//   * parameters ONCE per column pair: thread t reduces the partials of the warps of its row block for pair t (128 pairs per
+//     row block, 128 / g row blocks per tile), runs setup2, writes the scales / zero points and publishes the packed constants
+//     in shared memory (transposed so that the readers' LDS.128 are conflict-free) -> barrier;
+//   * sweep 2: every lane fetches the constants of its 4 pairs and quantises its 8 rows in place in the stage;
+//   * each warp sends its 8 rows back with one cp.async.bulk.tensor.2d store (box 256 x 8) and releases the stage as in seg4.
+// Ragged edges: the hardware zero-fills loads and clips stores; parameters of non-existent columns / row blocks are not written.
+// ------------------------------------------------------------------------------------------------
+#ifndef IWQ_COLW_GROUPS
+#define IWQ_COLW_GROUPS 2
+#endif
+constexpr int kColWideWarps = 16;
+constexpr int kColWideGroups = IWQ_COLW_GROUPS;                 // independent consumer groups (alternate tiles)
+constexpr int kColWideWG = kColWideWarps / kColWideGroups;      // warps per group
+constexpr int kColWideRows = 128, kColWideCols = 256;           // largest tile; LaunchParams::col_rows = 128 or 64 rows per tile
+constexpr int kColWideTile = kColWideRows * kColWideCols * 2;  // 64 KB
+constexpr int kColWideHeader = 1024;                           // barriers, tile contexts [8], flags
+constexpr int kColWidePart = kColWideWarps * 2 * 32 * 16;      // per-warp partial ranges: [warp][max | min][lane] uint4 = 16 KB
+
+struct ColWideCtx {  // 64 bytes
+  const TensorMapPair* map;
+  uint8_t* scales;
+  uint8_t* zeros;
+  uint32_t c0, r0, n_rb, cols, job;
+  uint32_t pad[5];
+};
+
+template <int DT, int KIND, bool SYM>
+__global__ void __launch_bounds__(kColWideWarps * 32 + 32, 1) col_wide_kernel(const __grid_constant__ LaunchParams p, const __grid_constant__ TensorMapPair single_maps,
+                                                                                 const TensorMapPair* __restrict__ maps) {
+  using T2 = typename DType<DT>::T2;
+  using PP = PreparedPair<DT, KIND>;
+  constexpr int kU = PP::kWords / 4;  // 16-byte units of one pair's constants
+  constexpr int WG = kColWideWG, GT = WG * 32;  // warps / threads of a group
+  const uint32_t TR = p.col_rows, RW = TR / (uint32_t)WG;  // rows per tile (128 / 64) and per warp
+  const uint32_t tile_bytes = TR * (uint32_t)(kColWideCols * 2);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + kMaxStages;
+  ColWideCtx* ctxs = reinterpret_cast<ColWideCtx*>(smem + 128);       // [8]
+  uint32_t* flags_all = reinterpret_cast<uint32_t*>(smem + 128 + 8 * 64);  // [group][2] "a segment of this tile is suspect", by tile parity
+  const FpStep* s_tbl = nullptr;
+  if (KIND == KIND_FP) s_tbl = load_fp_lut(p, smem + kColWideHeader);
+  uint8_t* part_all = smem + kColWideHeader + p.lut_smem_bytes;
+  uint8_t* pars_all = part_all + kColWidePart;
+  const uint32_t g = p.col_group;
+  const uint32_t wpb = g / RW;                       // warps per row block
+  const uint32_t n_pairs = (TR / g) * 128u;
+  const uint32_t pars_bytes = n_pairs * PP::kWords * 4u;
+  uint8_t* ring = pars_all + (size_t)kColWideGroups * pars_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_stages = p.n_stages;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], WG);
+    }
+    for (int i = 0; i < 2 * kColWideGroups; ++i) flags_all[i] = 0u;
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == kColWideWarps) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      int stage = 0, cur = -1, fenced = -1;
+      uint32_t phase = 0;
+      Job jb;
+      const uint64_t pol = (p.l2_hint & 1u) ? l2_policy_evict_first() : l2_policy_evict_last();
+      for (uint32_t unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        advance_job(p, unit, &cur, &jb);
+        const uint32_t cols = jb.row_bytes >> 1;
+        const uint32_t rows = (uint32_t)(jb.bytes / jb.row_bytes);
+        const uint32_t n_ct = (cols + kColWideCols - 1) / kColWideCols;
+        const uint32_t local = unit - jb.first_unit;
+        const uint32_t rt = local / n_ct, ct = local - rt * n_ct;
+        ColWideCtx c;
+        c.map = maps ? &maps[cur] : &single_maps;
+        c.scales = jb.scales;
+        c.zeros = jb.zeros;
+        c.c0 = ct * kColWideCols;
+        c.r0 = rt * TR;
+        c.n_rb = rows / g;
+        c.cols = cols;
+        c.job = (uint32_t)cur;
+        ctxs[stage] = c;
+        if (maps && fenced != cur) {
+          tensormap_acquire(&c.map->in);
+          fenced = cur;
+        }
+        mbar_arrive_expect_tx(&full[stage], tile_bytes);
+        uint8_t* dst = ring + (size_t)stage * tile_bytes;
+        if (p.l2_hint & 3u) tma_load_2d_hint(dst, &c.map->in, c.c0, c.r0, &full[stage], pol);
+        else tma_load_2d(dst, &c.map->in, c.c0, c.r0, &full[stage]);
+        if (++stage == n_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers: group gi takes tiles gi, gi + groups, ... of this CTA's sequence ----------------
+  const uint32_t ident_max = SYM ? 0u : (DT == IWQ_F16 ? 0xFC00FC00u : 0xFF80FF80u);
+  const uint32_t ident_min = DT == IWQ_F16 ? 0x7C007C00u : 0x7F807F80u;
+  PP uni;  // launch-uniform members of the prepared constants (minifloat / BFP kinds): set once
+  {
+    float a, b, c, d;
+    bool bad;
+    uni.setup2(1.0f, -1.0f, 1.0f, -1.0f, p.qc, SYM, s_tbl, &a, &b, &c, &d, &bad);
+  }
+  const uint32_t gi = (uint32_t)warp / WG, wg = (uint32_t)warp % WG;
+  const uint32_t t_g = threadIdx.x - gi * GT;                   // thread within the group
+  const uint32_t my_blk = wg / wpb;                             // row block of this warp's rows within the tile
+  uint8_t* part = part_all + (size_t)gi * (kColWidePart / kColWideGroups);
+  uint8_t* pars = pars_all + (size_t)gi * pars_bytes;
+  uint32_t* flags = flags_all + 2u * gi;
+  uint4* part_mx = reinterpret_cast<uint4*>(part) + (size_t)wg * 64 + lane;     // [warp][0][lane]
+  uint4* part_mn = part_mx + 32;                                                 // [warp][1][lane]
+  const uint32_t* part_w = reinterpret_cast<const uint32_t*>(part);             // word view: [warp][max | min][128 pairs]
+  const uint32_t bar_id = 1u + gi;
+  int fenced = -1;
+  uint32_t parity = 0;
+  for (uint32_t i = gi;; i += kColWideGroups) {
+    const uint32_t unit = blockIdx.x + i * gridDim.x;
+    if (unit >= p.total_units) break;
+    const uint32_t stage = i % (uint32_t)n_stages, phase = (i / (uint32_t)n_stages) & 1u;
+    mbar_wait(&full[stage], phase);
+    const ColWideCtx c = ctxs[stage];
+    uint8_t* wbase = ring + (size_t)stage * tile_bytes + (size_t)wg * (RW * 512u);
+    uint8_t* sd = wbase + (size_t)lane * 16u;
+
+    // ---- sweep 1 ----
+    uint32_t mx[4] = {ident_max, ident_max, ident_max, ident_max};
+    uint32_t mn[4] = {ident_min, ident_min, ident_min, ident_min};
+#pragma unroll 1
+    for (uint32_t r0 = 0; r0 < RW; r0 += 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = lds128(sd + (r0 + r) * 512);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) col_range_update<DT, SYM>(mx, mn, v[r]);
+    }
+    *part_mx = make_uint4(mx[0], mx[1], mx[2], mx[3]);
+    if (!SYM) *part_mn = make_uint4(mn[0], mn[1], mn[2], mn[3]);
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(GT) : "memory");
+
+    // ---- parameters: one column pair per thread (while this group computes them the other group sweeps its own tile) ----
+    if (t_g == 0) flags[parity ^ 1u] = 0u;  // the other parity's flag: read by everybody before this tile's first barrier, set again after the next one
+    for (uint32_t pp = t_g; pp < n_pairs; pp += GT) {
+      const uint32_t b = pp >> 7, q = pp & 127u;
+      uint32_t mxs = ident_max, mns = ident_min;
+      for (uint32_t w = b * wpb; w < (b + 1u) * wpb; ++w) {
+        mxs = as_u32(__hmax2_nan(from_u32<T2>(mxs), from_u32<T2>(part_w[w * 256u + q])));
+        if (!SYM) mns = as_u32(__hmin2_nan(from_u32<T2>(mns), from_u32<T2>(part_w[w * 256u + 128u + q])));
+      }
+      const float mxa = DType<DT>::to_f32((uint16_t)(mxs & 0xFFFFu)), mxb = DType<DT>::to_f32((uint16_t)(mxs >> 16));
+      const float mna = DType<DT>::to_f32((uint16_t)(mns & 0xFFFFu)), mnb = DType<DT>::to_f32((uint16_t)(mns >> 16));
+      PP mine;
+      float sa, za, sb, zb;
+      bool bad;
+      mine.setup2(mxa, SYM ? -mxa : mna, mxb, SYM ? -mxb : mnb, p.qc, SYM, s_tbl, &sa, &za, &sb, &zb, &bad);
+      const uint32_t col = c.c0 + 2u * q, rb = c.r0 / g + b;
+      if (col < c.cols && rb < c.n_rb) {
+        // segment order of the reference for quant_dim = 1: column-major over (column, row block)
+        const size_t ga = (size_t)col * c.n_rb + rb, gb = ga + c.n_rb;
+        if (c.scales) {
+          reinterpret_cast<uint16_t*>(c.scales)[ga] = DType<DT>::from_f32(sa);
+          reinterpret_cast<uint16_t*>(c.scales)[gb] = DType<DT>::from_f32(sb);
+        }
+        if (c.zeros) {
+          reinterpret_cast<uint16_t*>(c.zeros)[ga] = DType<DT>::from_f32(za);
+          reinterpret_cast<uint16_t*>(c.zeros)[gb] = DType<DT>::from_f32(zb);
+        }
+        if (bad || mine.slow()) atomicOr(&flags[parity], 1u);
+      }
+      // publish: pair q of block b is pair j = q & 3 of chunk q >> 2; unit u of it lives at [(b * 4 + j) * kU + u][chunk] (16 B each)
+      uint32_t wds[PP::kWords];
+      int n = 0;
+      mine.map_from(mine, [&](uint32_t v) {
+        wds[n++] = v;
+        return v;
+      });
+      uint4* dst = reinterpret_cast<uint4*>(pars) + (size_t)((b * 4u + (q & 3u)) * kU) * 32u + (q >> 2);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) dst[u * 32] = make_uint4(wds[4 * u], wds[4 * u + 1], wds[4 * u + 2], wds[4 * u + 3]);
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(GT) : "memory");
+
+    // ---- sweep 2: the constants of this lane's 4 pairs, then quantise in place ----
+    PP prep[4];
+    const bool suspect = flags[parity] != 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4* src = reinterpret_cast<const uint4*>(pars) + (size_t)((my_blk * 4u + (uint32_t)j) * kU) * 32u + lane;
+      uint32_t wds[PP::kWords];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const uint4 x = src[u * 32];
+        wds[4 * u] = x.x; wds[4 * u + 1] = x.y; wds[4 * u + 2] = x.z; wds[4 * u + 3] = x.w;
+      }
+      int n = 0;
+      prep[j].map_from(uni, [&](uint32_t) { return wds[n++]; });
+    }
+    if (!suspect) {
+#pragma unroll 2
+      for (uint32_t r = 0; r < RW; ++r) {
+        const uint4 v = lds128(sd + r * 512);
+        uint4 o;
+        o.x = prep[0].template apply<SYM, 0>(v.x, p.qc); o.y = prep[1].template apply<SYM, 0>(v.y, p.qc);
+        o.z = prep[2].template apply<SYM, 0>(v.z, p.qc); o.w = prep[3].template apply<SYM, 0>(v.w, p.qc);
+        sts128(sd + r * 512, o);
+      }
+    } else {
+      const bool live = c.c0 + (uint32_t)lane * 8u < c.cols && c.r0 + wg * RW < c.n_rb * g;
+      bool nan_seen = false;
+#pragma unroll 1
+      for (uint32_t r = 0; r < RW; ++r) {
+        const uint4 v = lds128(sd + r * 512);
+        uint4 o;
+        o.x = prep[0].template apply<SYM>(v.x, p.qc); o.y = prep[1].template apply<SYM>(v.y, p.qc);
+        o.z = prep[2].template apply<SYM>(v.z, p.qc); o.w = prep[3].template apply<SYM>(v.w, p.qc);
+        sts128(sd + r * 512, o);
+        nan_seen |= vec_has_nan<DT>(o);
+      }
+      if (live && nan_seen && p.status) atomicOr(p.status, IWQ_STATUS_NAN);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (maps && fenced != (int)c.job) {
+        tensormap_acquire(&c.map->out);
+        fenced = (int)c.job;
+      }
+      tma_store_2d(&c.map->out, c.c0, c.r0 + wg * RW, wbase);
+      tma_store_commit();
+      // the stage goes back to the producer as soon as this warp's rows have been read out of shared memory (with two groups and
+      // three stages the other group is waiting for exactly this stage's next tile)
+      tma_store_wait_read<0>();
+      mbar_arrive(&empty[stage]);
+    }
+    parity ^= 1u;
   }
   if (lane == 0) tma_store_wait_all();
 }

@@ -84,6 +84,16 @@ cudaError_t launch_col_tma(const LaunchParams& p, const TensorMapPair& single, c
 
 template <int DT, int KIND, bool SYM>
 static cudaError_t launch_col_tma_one(const LaunchParams& p, const TensorMapPair& single, const TensorMapPair* maps, const LaunchTuning& tune, cudaStream_t st) {
+  if (p.col_wide) {
+    auto kw = col_wide_kernel<DT, KIND, SYM>;
+    const size_t n_pairs = (size_t)(p.col_rows / p.col_group) * 128;
+    const size_t smem = kColWideHeader + p.lut_smem_bytes + kColWidePart + kColWideGroups * n_pairs * PreparedPair<DT, KIND>::kWords * 4 + (size_t)p.n_stages * p.stage_bytes;
+    int grid = 0;
+    cudaError_t e = persistent_grid(kw, kColWideWarps * 32 + 32, smem, 1, p.total_units, &grid);
+    if (e != cudaSuccess) return e;
+    kw<<<grid, kColWideWarps * 32 + 32, smem, st>>>(p, single, maps);
+    return cudaGetLastError();
+  }
   auto k = col_tma_kernel<DT, KIND, SYM>;
   // [step table][mbarriers, 128 B][ring: warps x stages x stage]
   const size_t smem = p.lut_smem_bytes + 128 + (size_t)kColTmaWarps * p.n_stages * p.stage_bytes;

@@ -196,7 +196,7 @@ def test_dispatch_plan_for_the_baseline_shapes(built):
         built.check(L.iwq_debug_plan(ctypes.byref(cfg), rows, cols, out))
         return list(out)
 
-    SEG, ROW, COL_ASYNC, COL_REG, COL_2SWEEP, COL_DOUBLE, COL_TMA = range(7)
+    SEG, ROW, COL_ASYNC, COL_REG, COL_2SWEEP, COL_DOUBLE, COL_TMA, COL_WIDE = range(8)
     # per-group: seg4 (variant 0), lanes per segment = group / 32, 4 stages of 48 KB (one CTA per SM)
     for g, lps in [(32, 1), (64, 2), (128, 4), (256, 8), (1024, 32)]:
         p = plan(8192, 8192, group=g, bits=4)
@@ -217,9 +217,12 @@ def test_dispatch_plan_for_the_baseline_shapes(built):
     p = plan(8192, 28672, group=-2, scheme=built.SCHEME_FP_CODEC, exp_bits=2, mant_bits=1, symmetric=True)
     assert p[0] == ROW and p[4] == 16 and p[6] == 0, p
     # quant_dim = 1
-    p = plan(8192, 8192, group=128, bits=4, quant_dim=1)  # 2-D tensor-map boxes: 128 rows x 32 columns = 8 KB, two stages per warp
-    assert p[0] == COL_TMA and p[3] == 2 and p[5] == 8192 and p[7] == 32, p
-    assert plan(8192, 8192, group=32, bits=4, quant_dim=1)[7] == 128 and plan(8192, 8192, group=64, bits=4, quant_dim=1)[7] == 64
+    p = plan(8192, 8192, group=128, bits=4, quant_dim=1)  # CTA-wide ring of 128 x 256 tensor-map tiles (64 KB), three stages
+    assert p[0] == COL_WIDE and p[3] == 3 and p[5] == 65536 and p[7] == 256, p
+    assert plan(8192, 8192, group=32, bits=4, quant_dim=1)[0] == COL_WIDE and plan(8192, 8192, group=64, bits=4, quant_dim=1)[0] == COL_WIDE
+    p = plan(8192, 8192, group=256, bits=4, quant_dim=1)  # warp-private 2-D tensor-map boxes: 256 rows x 32 columns = 16 KB, one stage
+    assert p[0] == COL_TMA and p[3] == 1 and p[5] == 16384 and p[7] == 32, p
+    assert plan(64, 128, group=32, bits=4, quant_dim=1)[0] == COL_TMA  # smaller than one wide tile
     assert plan(8192, 8192, group=512, bits=4, quant_dim=1)[0] == COL_ASYNC  # boxes are at most 256 rows
     assert plan(8192, 8192, group=-2, bits=4, quant_dim=1)[0] == COL_2SWEEP
     assert plan(8192, 8192, group=96, bits=4, quant_dim=1)[0] == COL_2SWEEP
