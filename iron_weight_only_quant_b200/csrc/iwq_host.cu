@@ -66,6 +66,7 @@ struct Knobs {
   int mm_tma = env_int("IWQ_MM_TMA", 1);             // per-tensor range pass: 1 = bulk-copy ring (minmax_tma_kernel), 0 = 128-bit global loads
   int mm_stages = env_int("IWQ_MM_STAGES", 2);       // ... its ring depth (2 x 48 KB measured best: 7.26 TB/s vs 6.73 with 4, 6.9 for the global loads)
   int mm_hint = env_int("IWQ_MM_HINT", 0);           // ... L2 policy of its bulk loads (1 evict_first, 2 evict_last)
+  int seg_store = env_int("IWQ_SEG_STORE", 0);       // seg4: 1 = one bulk store per tile instead of one per warp
   int seg_map = env_int("IWQ_SEG_MAP", 0);           // LaunchParams::tile_map of the seg4 kernels (1: contiguous run of tiles per CTA)
   int fp_mode = env_int("IWQ_FP_MODE", 2);           // seg4 minifloat kernel: 0 step table, 1 interleaved copies of it, 2 direct table
   int fp_rep = env_int("IWQ_FP_REP", 4);             // seg4 minifloat kernel: log2 of the interleaved copies of the step table
@@ -602,12 +603,14 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
       p.reverse = (seg4 && knobs().pt_reverse != 0) ? 1u : 0u;
       p.l2_hint = (uint32_t)knobs().pt_hint & 23u;
       p.tile_map = (uint32_t)knobs().seg_map;
+      p.store_mode = (uint32_t)knobs().seg_store;
       e = dispatch_seg(cfg->dtype, kind, p, sym, true, variant, tune, st);
     }
   } else if (pl.path == PATH_SEG) {
     tune.ctas_per_sm = knobs().seg_ctas;
     p.l2_hint = (uint32_t)knobs().seg_hint & 23u;
     p.tile_map = (uint32_t)knobs().seg_map;
+    p.store_mode = (uint32_t)knobs().seg_store;
     e = dispatch_seg(cfg->dtype, kind, p, sym, false, variant, tune, st);
   } else {
     tune.ctas_per_sm = knobs().row_ctas;
@@ -953,7 +956,7 @@ int iwq_debug_set_knob(const char* name, int value) {
   IWQ_KNOB(seg_stages) IWQ_KNOB(seg_ctas) IWQ_KNOB(row_ctas) IWQ_KNOB(row_smem_kb) IWQ_KNOB(variant) IWQ_KNOB(row_warps) IWQ_KNOB(col_tile)
   IWQ_KNOB(col_ctas) IWQ_KNOB(fused_batch_mb) IWQ_KNOB(fused_lookahead) IWQ_KNOB(row_tma_out) IWQ_KNOB(wide_seg4) IWQ_KNOB(col_mode)
   IWQ_KNOB(col_stages) IWQ_KNOB(pt_slab_mb) IWQ_KNOB(pt_reverse) IWQ_KNOB(pt_hint) IWQ_KNOB(seg_hint) IWQ_KNOB(fp_mode) IWQ_KNOB(fp_rep) IWQ_KNOB(fp_rep_kb)
-  IWQ_KNOB(fp_stages) IWQ_KNOB(host_copy_only) IWQ_KNOB(seg_map) IWQ_KNOB(mm_tma) IWQ_KNOB(mm_stages) IWQ_KNOB(mm_hint) IWQ_KNOB(col_box) IWQ_KNOB(col_hint)
+  IWQ_KNOB(fp_stages) IWQ_KNOB(host_copy_only) IWQ_KNOB(seg_map) IWQ_KNOB(mm_tma) IWQ_KNOB(mm_stages) IWQ_KNOB(mm_hint) IWQ_KNOB(col_box) IWQ_KNOB(col_hint) IWQ_KNOB(seg_store)
 #undef IWQ_KNOB
   return fail(IWQ_ERR_INVALID, "unknown knob: " + n);
 }

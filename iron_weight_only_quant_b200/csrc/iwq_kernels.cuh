@@ -87,6 +87,7 @@ struct LaunchParams {
   uint32_t l2_hint;        // bit 0: bulk loads evict_first, bit 1: bulk loads evict_last, bit 2: bulk stores evict_first,
                            // bit 3: minmax kernel walks tiles strided (blockIdx.x + k * gridDim.x) instead of in contiguous runs,
                            // bit 4: bulk stores evict_last
+  uint32_t store_mode;     // seg4: 1 = one bulk store per tile (after a consumer-wide barrier) instead of one 2 KB store per warp
   uint32_t col_wide;       // quant_dim = 1: 1 = col_wide_kernel (128 x 256 tiles, CTA-wide ring) instead of col_tma_kernel
   uint32_t col_rows;       // ... rows per tile (128 or 64)
   uint32_t tile_map;       // seg4: 0 = CTA b takes tiles b, b + grid, b + 2 grid, ... (a window of grid tiles slides over the work
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(kConsumers + 32, IWQ_SEG4_MINB) seg4_tma_kerne
   if (threadIdx.x == 0) {
     for (int i = 0; i < n_stages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], kConsumerWarps);
+      mbar_init(&empty[i], p.store_mode ? 1u : (uint32_t)kConsumerWarps);
     }
     fence_mbar_init();
   }
@@ -760,6 +761,24 @@ __global__ void __launch_bounds__(kConsumers + 32, IWQ_SEG4_MINB) seg4_tma_kerne
     else
       seg4_consume<DT, KIND, SYM, GIVEN, false, LUT>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps, warp, xchg);
     fence_proxy_async_smem();
+    if (p.store_mode) {
+      // ONE bulk store per tile: the consumer warps meet at a named barrier, thread 0 sends the whole tile and releases the
+      // previous stage on behalf of everybody
+      asm volatile("bar.sync 15, %0;" ::"n"(kConsumers) : "memory");
+      if (threadIdx.x == 0) {
+        if (store_hint) tma_store_1d_hint(t.dst, data + (size_t)stage * kTileBytes, t.n_vec * 16u, store_pol);
+        else tma_store_1d(t.dst, data + (size_t)stage * kTileBytes, t.n_vec * 16u);
+        tma_store_commit();
+        tma_store_wait_read<1>();
+        if (prev_stage >= 0) mbar_arrive(&empty[prev_stage]);
+      }
+      prev_stage = stage;
+      if (++stage == n_stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+      continue;
+    }
     __syncwarp();
     if (lane == 0) {
       const uint32_t w0 = (uint32_t)warp * 128u;

@@ -229,3 +229,38 @@ def test_dispatch_plan_for_the_baseline_shapes(built):
     assert plan(8192, 8192, group=128, scheme=built.SCHEME_FP_CODEC, exp_bits=2, mant_bits=1, symmetric=True, quant_dim=1, approx=2, hi_align_start=0, hi_align_exp_field=2, tail_pad_bits=1)[0] == COL_DOUBLE
     with pytest.raises(AssertionError):
         plan(8192, 8200, group=128, bits=4)  # cols % group != 0 -> the reference's assert
+
+
+def test_dropin_shims_import_and_propagate_formats(built):
+    """with dropin/ in front on sys.path, `import quant_funcs / quant_wrapper / quant_linear /
+    fp4_quantize_cpu` (what main.py, eval_quant_lm_eval.py and visualize_utils.py do) binds to this package, and
+    configure_fp_formats called on the shim reaches the implementation module the kernels read (quant_linear.py:84-110)."""
+    import importlib
+    import subprocess
+    import sys
+
+    code = r"""
+import sys, os
+root = sys.argv[1]
+sys.path.insert(0, os.path.join(root, "dropin"))
+import quant_funcs, quant_wrapper, quant_linear, fp4_quantize_cpu
+import iron_weight_only_quant_b200.quant_linear as impl
+assert quant_funcs.pseudo_quantize_tensor.__module__ == "iron_weight_only_quant_b200.quant_funcs"
+assert quant_wrapper.quantize_model.__module__ == "iron_weight_only_quant_b200.quant_wrapper"
+assert quant_linear.QuantLinear is impl.QuantLinear and quant_linear.GPTQQuantLinear is impl.GPTQQuantLinear
+assert fp4_quantize_cpu.quantize_fp16_to_fp4_e1m2.__module__ == "iron_weight_only_quant_b200.fp4_quantize_cpu"
+for name in ("quantize_weight_per_channel_absmax", "quantize_activation_per_token_absmax", "quantize_weight_per_tensor_absmax", "quantize_activation_per_tensor_absmax"):
+    assert hasattr(quant_funcs, name), name
+# the names visualize_utils.py:6 imports by value
+for name in ("_fp_to_float", "_float_to_fp", "_count_fp4_values", "FP4_EXP_BITS", "FP8_MANTISSA_BITS", "MANTISSA_BITS"):
+    assert hasattr(quant_linear, name), name
+quant_linear.configure_fp_formats(fp4_exp_bits=1, fp4_mantissa_bits=2, fp6_exp_bits=2, fp6_mantissa_bits=3)
+assert (impl.FP4_EXP_BITS, impl.FP4_MANTISSA_BITS, impl.FP4_EXP_BIAS) == (1, 2, 0), "implementation globals"
+assert (quant_linear.FP4_EXP_BITS, quant_linear.FP4_MANTISSA_BITS, quant_linear.FP6_EXP_BITS, quant_linear.FP6_MANTISSA_BITS) == (1, 2, 2, 3), "shim globals"
+assert impl.fp_format_of("fp4") == (1, 2) and impl.fp_format_of("fp6") == (2, 3)
+quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
+assert impl.fp_format_of("fp4") == (2, 1) and quant_linear.FP6_EXP_BITS == 3
+print("dropin ok")
+"""
+    out = subprocess.run([sys.executable, "-c", code, ROOT], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "dropin ok" in out.stdout, out.stderr[-2000:]
