@@ -66,6 +66,7 @@ struct Knobs {
   int mm_tma = env_int("IWQ_MM_TMA", 1);             // per-tensor range pass: 1 = bulk-copy ring (minmax_tma_kernel), 0 = 128-bit global loads
   int mm_stages = env_int("IWQ_MM_STAGES", 2);       // ... its ring depth (2 x 48 KB measured best: 7.26 TB/s vs 6.73 with 4, 6.9 for the global loads)
   int mm_hint = env_int("IWQ_MM_HINT", 0);           // ... L2 policy of its bulk loads (1 evict_first, 2 evict_last)
+  int seg_vpl = env_int("IWQ_SEG_VPL", 0);           // seg4: 16-byte vectors per lane (4 / 8 / 16); 0 = automatic
   int seg_store = env_int("IWQ_SEG_STORE", 0);       // seg4: 1 = one bulk store per tile instead of one per warp
   int seg_map = env_int("IWQ_SEG_MAP", 0);           // LaunchParams::tile_map of the seg4 kernels (1: contiguous run of tiles per CTA)
   int fp_mode = env_int("IWQ_FP_MODE", 2);           // seg4 minifloat kernel: 0 step table, 1 interleaved copies of it, 2 direct table
@@ -89,6 +90,8 @@ static int fit_seg_stages(int want, size_t lut_bytes, size_t extra_bytes = 0) {
   while (st > 2 && kSmemHeader + lut_bytes + extra_bytes + (size_t)st * kTileBytes > 227u * 1024u) --st;
   return st;
 }
+
+constexpr int kSeg4AutoVpl = 4;  // default vectors per lane of seg4_tma_kernel (IWQ_SEG_VPL overrides)
 
 static int effective_variant(const iwq_config_t* cfg) { return knobs().variant >= 0 ? knobs().variant : cfg->variant; }
 
@@ -532,6 +535,7 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
   if (variant < 0 || variant > 2) variant = 0;
   if (variant == 0 && !per_tensor && pl.path == PATH_SEG && pl.seg_elems < 32) variant = 2;
   if (variant == 0 && pl.path == PATH_SEG) {
+    p.seg_vpl = 4;
     p.lps = per_tensor ? 1 : (int)(pl.seg_elems / 32);
     p.vpl = 1;
     if (kind == KIND_FP && knobs().fp_mode == 2 && p.qc.approx != 2) {
@@ -562,6 +566,28 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
       }
       tune.stages = p.n_stages = fit_seg_stages(knobs().fp_stages >= 2 ? knobs().fp_stages : knobs().seg_stages, p.lut_smem_bytes, p.lut_extra_bytes);
     }
+    // vectors per lane: more of a segment per lane = fewer lanes repeating the segment's parameter arithmetic.  Segments that span
+    // warps (2048+ elements) and the step-table minifloat forms stay at 4.
+    int vpl = 4;
+    {
+      // measured (tools/r2_exp16.sh / r2_exp17.sh, fresh data): the direct-table minifloat stage gains 5-13 % from 8 vectors per lane
+      // (FP4 E2M1 5.72 -> 6.39 TB/s, FP6 E3M2 5.60 -> 6.35, FP8 E4M3 5.45 -> 5.72); the INT / BFP stages are HBM-bound either way in
+      // bench-length runs (6.23-6.34 vs 6.17-6.32 TB/s) and keep 4 (in minute-long runs under the power cap 8 is ~7 % faster)
+      const int auto_vpl = kind == KIND_FP ? 8 : kSeg4AutoVpl;
+      const int want = knobs().seg_vpl == 8 || knobs().seg_vpl == 16 ? knobs().seg_vpl : (knobs().seg_vpl == 4 ? 4 : auto_vpl);
+      const bool fp_step = kind == KIND_FP && !p.qc.lut_direct;
+      if (kind != KIND_INT_GENERIC && !fp_step) {
+        for (int v = want; v > 4; v >>= 1) {
+          if (per_tensor || (pl.seg_elems % (8u * (uint32_t)v) == 0 && pl.seg_elems <= 1024u)) {
+            vpl = v;
+            break;
+          }
+        }
+      }
+    }
+    p.seg_vpl = (uint32_t)vpl;
+    p.lps = per_tensor ? 1 : (int)(pl.seg_elems / (8u * (uint32_t)vpl));
+
   }
   if (per_tensor) {
     const float* rng = given_range;
@@ -956,7 +982,7 @@ int iwq_debug_set_knob(const char* name, int value) {
   IWQ_KNOB(seg_stages) IWQ_KNOB(seg_ctas) IWQ_KNOB(row_ctas) IWQ_KNOB(row_smem_kb) IWQ_KNOB(variant) IWQ_KNOB(row_warps) IWQ_KNOB(col_tile)
   IWQ_KNOB(col_ctas) IWQ_KNOB(fused_batch_mb) IWQ_KNOB(fused_lookahead) IWQ_KNOB(row_tma_out) IWQ_KNOB(wide_seg4) IWQ_KNOB(col_mode)
   IWQ_KNOB(col_stages) IWQ_KNOB(pt_slab_mb) IWQ_KNOB(pt_reverse) IWQ_KNOB(pt_hint) IWQ_KNOB(seg_hint) IWQ_KNOB(fp_mode) IWQ_KNOB(fp_rep) IWQ_KNOB(fp_rep_kb)
-  IWQ_KNOB(fp_stages) IWQ_KNOB(host_copy_only) IWQ_KNOB(seg_map) IWQ_KNOB(mm_tma) IWQ_KNOB(mm_stages) IWQ_KNOB(mm_hint) IWQ_KNOB(col_box) IWQ_KNOB(col_hint) IWQ_KNOB(seg_store)
+  IWQ_KNOB(fp_stages) IWQ_KNOB(host_copy_only) IWQ_KNOB(seg_map) IWQ_KNOB(mm_tma) IWQ_KNOB(mm_stages) IWQ_KNOB(mm_hint) IWQ_KNOB(col_box) IWQ_KNOB(col_hint) IWQ_KNOB(seg_store) IWQ_KNOB(seg_vpl)
 #undef IWQ_KNOB
   return fail(IWQ_ERR_INVALID, "unknown knob: " + n);
 }

@@ -87,6 +87,7 @@ struct LaunchParams {
   uint32_t l2_hint;        // bit 0: bulk loads evict_first, bit 1: bulk loads evict_last, bit 2: bulk stores evict_first,
                            // bit 3: minmax kernel walks tiles strided (blockIdx.x + k * gridDim.x) instead of in contiguous runs,
                            // bit 4: bulk stores evict_last
+  uint32_t seg_vpl;        // seg4: 16-byte vectors per lane (4 / 8 / 16); lps = group / (8 * seg_vpl)
   uint32_t store_mode;     // seg4: 1 = one bulk store per tile (after a consumer-wide barrier) instead of one 2 KB store per warp
   uint32_t col_wide;       // quant_dim = 1: 1 = col_wide_kernel (128 x 256 tiles, CTA-wide ring) instead of col_tma_kernel
   uint32_t col_rows;       // ... rows per tile (128 or 64)
@@ -624,21 +625,30 @@ __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_c
 // ------------------------------------------------------------------------------------------------
 // One lane's share of a tile in seg4_tma_kernel: four vectors through registers, results back to the stage.
 // FAST = full 16 KB tile and no code emission: no per-vector predicates at all.
-template <int DT, int KIND, bool SYM, bool GIVEN, bool FAST, int LUT = LUT_STEP>
+template <int DT, int KIND, bool SYM, bool GIVEN, bool FAST, int LUT = LUT_STEP, int VPL = 4>
 __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParams& p, const FpStep* s_tbl, uint8_t* lbase, uint32_t lane_vec,
                                              uint32_t rot, int lane, int lps, int warp, uint32_t* xchg) {
-  uint4 v[4];
+  // VPL = vectors per lane (4, 8 or 16 consecutive 16-byte vectors): a lane that owns more of its segment needs fewer shuffle
+  // rounds and -- what counts -- fewer lanes repeat the same scale / zero-point arithmetic (group 128: 4 lanes per segment at
+  // VPL 4, one at VPL 16), and the per-tile bookkeeping is spread over more elements
+  uint4 v[VPL];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const uint32_t j = (k + rot) & 3u;
+  for (int k = 0; k < VPL; ++k) {
+    const uint32_t j = (k + rot) & (uint32_t)(VPL - 1);
     v[k] = (FAST || lane_vec + j < t.n_vec) ? lds128(lbase + j * 16) : make_uint4(0u, 0u, 0u, 0u);
   }
   typename std::conditional<LUT != LUT_STEP && KIND == KIND_FP, PreparedFp<DT, LUT>, Prepared<DT, KIND>>::type prep;
   if (GIVEN) {
     prep.setup(t.given_mx, t.given_mn, p.qc, SYM, s_tbl);
   } else {
-    uint32_t pk = range_max<DT>(range_max<DT>(vec_range<DT, SYM>(v[0]), vec_range<DT, SYM>(v[1])),
-                                range_max<DT>(vec_range<DT, SYM>(v[2]), vec_range<DT, SYM>(v[3])));
+    uint32_t pr[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) pr[k] = vec_range<DT, SYM>(v[k]);
+#pragma unroll
+    for (int w = VPL / 2; w > 0; w >>= 1)
+#pragma unroll
+      for (int k = 0; k < w; ++k) pr[k] = range_max<DT>(pr[k], pr[k + w]);
+    uint32_t pk = pr[0];
     // log2(lps) butterfly rounds; lps is launch-uniform, so this is a short uniform loop (no divergence handling)
 #pragma unroll 1
     for (int o = (lps > 32 ? 32 : lps) >> 1; o > 0; o >>= 1) pk = range_max<DT>(pk, __shfl_xor_sync(0xFFFFFFFFu, pk, o));
@@ -662,8 +672,8 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
     // the hot path: no code emission, reciprocal+FMA quotient; one segment-uniform branch per lane-tile keeps the
     // IEEE-division variant (degenerate scales only) out of the instruction stream
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t j = (k + rot) & 3u;
+    for (int k = 0; k < VPL; ++k) {
+      const uint32_t j = (k + rot) & (uint32_t)(VPL - 1);
       uint2 codes8;
       sts128(lbase + j * 16, prep.template apply<SYM, 0>(v[k], p.qc, s_tbl, false, &codes8));
     }
@@ -671,8 +681,8 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
     // rolled loop (code size): the inputs are re-read from the stage, which still holds them (each pass overwrites
     // only its own slot), so v[] is never indexed dynamically and stays in registers on the hot path
 #pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t j = (k + rot) & 3u;
+    for (int k = 0; k < VPL; ++k) {
+      const uint32_t j = (k + rot) & (uint32_t)(VPL - 1);
       uint2 codes8;
       const uint4 vv = (FAST || lane_vec + j < t.n_vec) ? lds128(lbase + j * 16) : make_uint4(0u, 0u, 0u, 0u);
       const uint4 o = prep.template apply<SYM>(vv, p.qc, s_tbl, want_codes, &codes8);
@@ -682,11 +692,11 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
     }
   }
   if (FAST || lane_vec < t.n_vec) {
-    const bool owner = GIVEN ? (t.vec0 + lane_vec == 0) : (lps > 32 ? ((lane_vec & (uint32_t)(4 * lps - 1)) == 0) : ((lane & (lps - 1)) == 0));
+    const bool owner = GIVEN ? (t.vec0 + lane_vec == 0) : (lps > 32 ? ((lane_vec & (uint32_t)(VPL * lps - 1)) == 0) : ((lane & (lps - 1)) == 0));
     if (owner) {
       // (a shift by log2(4 * lps) instead of this division was measured 0.7 % SLOWER on the same box -- A/B with two
       //  libraries, 3 runs each: 6176 vs 6130 GB/s -- so the division stays)
-      const uint64_t g = GIVEN ? 0 : (t.vec0 + lane_vec) / (uint32_t)(4 * lps);
+      const uint64_t g = GIVEN ? 0 : (t.vec0 + lane_vec) / (uint32_t)(VPL * lps);
       if (t.scales) reinterpret_cast<uint16_t*>(t.scales)[g] = DType<DT>::from_f32(prep.scale);
       if (t.zeros) reinterpret_cast<uint16_t*>(t.zeros)[g] = DType<DT>::from_f32(prep.zero);
     }
@@ -694,8 +704,8 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
   }
 }
 
-template <int DT, int KIND, bool SYM, bool GIVEN, int LUT = LUT_STEP>
-__global__ void __launch_bounds__(kConsumers + 32, IWQ_SEG4_MINB) seg4_tma_kernel(const __grid_constant__ LaunchParams p) {
+template <int DT, int KIND, bool SYM, bool GIVEN, int LUT = LUT_STEP, int VPL = 4>
+__global__ void __launch_bounds__(kConsumers * 4 / VPL + 32, IWQ_SEG4_MINB) seg4_tma_kernel(const __grid_constant__ LaunchParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kMaxStages;
@@ -703,19 +713,20 @@ __global__ void __launch_bounds__(kConsumers + 32, IWQ_SEG4_MINB) seg4_tma_kerne
   const FpStep* s_tbl = nullptr;
   uint8_t* data = smem + kSmemHeader + p.lut_smem_bytes;
 
+  constexpr int CWv = kConsumerWarps * 4 / VPL;  // consumer warps: a warp owns VPL x 512 bytes of the tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_stages = p.n_stages;
   if (threadIdx.x == 0) {
     for (int i = 0; i < n_stages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], p.store_mode ? 1u : (uint32_t)kConsumerWarps);
+      mbar_init(&empty[i], p.store_mode ? 1u : (uint32_t)CWv);
     }
     fence_mbar_init();
   }
   if (KIND == KIND_FP) s_tbl = load_fp_lut(p, smem + kSmemHeader);
   __syncthreads();
 
-  if (warp == kConsumerWarps) {
+  if (warp == CWv) {
     if (lane == 0) {
       int stage = 0, cur = -1;
       uint32_t phase = 0;
@@ -744,8 +755,8 @@ __global__ void __launch_bounds__(kConsumers + 32, IWQ_SEG4_MINB) seg4_tma_kerne
 
   // ---------------- consumers ----------------
   const int lps = p.lps;                      // lanes per segment = group / 32 (1..32); unused when GIVEN
-  const uint32_t lane_vec = (uint32_t)warp * 128u + (uint32_t)lane * 4u;  // first vector of this lane in the tile
-  const uint32_t rot = (uint32_t)lane >> 1;
+  const uint32_t lane_vec = (uint32_t)warp * (32u * VPL) + (uint32_t)lane * VPL;  // first vector of this lane in the tile
+  const uint32_t rot = VPL == 4 ? (uint32_t)lane >> 1 : (uint32_t)lane;       // rotated vector order: conflict-free LDS.128 / STS.128
   const bool store_hint = (p.l2_hint & (4u | 16u)) != 0;
   const uint64_t store_pol = (p.l2_hint & 16u) ? l2_policy_evict_last() : l2_policy_evict_first();
   int stage = 0, prev_stage = -1;
@@ -757,14 +768,14 @@ __global__ void __launch_bounds__(kConsumers + 32, IWQ_SEG4_MINB) seg4_tma_kerne
     uint8_t* lbase = data + (size_t)stage * kTileBytes + (size_t)lane_vec * 16;
     uint32_t* xchg = reinterpret_cast<uint32_t*>(smem + 640) + stage * kConsumerWarps;  // [stage][warp] range slots
     if (t.n_vec == (uint32_t)(kTileBytes / 16) && t.codes == nullptr)
-      seg4_consume<DT, KIND, SYM, GIVEN, true, LUT>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps, warp, xchg);
+      seg4_consume<DT, KIND, SYM, GIVEN, true, LUT, VPL>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps, warp, xchg);
     else
-      seg4_consume<DT, KIND, SYM, GIVEN, false, LUT>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps, warp, xchg);
+      seg4_consume<DT, KIND, SYM, GIVEN, false, LUT, VPL>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps, warp, xchg);
     fence_proxy_async_smem();
     if (p.store_mode) {
       // ONE bulk store per tile: the consumer warps meet at a named barrier, thread 0 sends the whole tile and releases the
       // previous stage on behalf of everybody
-      asm volatile("bar.sync 15, %0;" ::"n"(kConsumers) : "memory");
+      asm volatile("bar.sync 15, %0;" ::"n"(CWv * 32) : "memory");
       if (threadIdx.x == 0) {
         if (store_hint) tma_store_1d_hint(t.dst, data + (size_t)stage * kTileBytes, t.n_vec * 16u, store_pol);
         else tma_store_1d(t.dst, data + (size_t)stage * kTileBytes, t.n_vec * 16u);
@@ -781,9 +792,9 @@ __global__ void __launch_bounds__(kConsumers + 32, IWQ_SEG4_MINB) seg4_tma_kerne
     }
     __syncwarp();
     if (lane == 0) {
-      const uint32_t w0 = (uint32_t)warp * 128u;
+      const uint32_t w0 = (uint32_t)warp * (32u * VPL);
       if (w0 < t.n_vec) {
-        const uint32_t nv = t.n_vec - w0 < 128u ? t.n_vec - w0 : 128u;
+        const uint32_t nv = t.n_vec - w0 < 32u * VPL ? t.n_vec - w0 : 32u * VPL;
         if (store_hint) tma_store_1d_hint(t.dst + (size_t)w0 * 16, data + (size_t)stage * kTileBytes + (size_t)w0 * 16, nv * 16u, store_pol);
         else tma_store_1d(t.dst + (size_t)w0 * 16, data + (size_t)stage * kTileBytes + (size_t)w0 * 16, nv * 16u);
       }

@@ -203,24 +203,33 @@ static cudaError_t launch_seg_one(LaunchParams p, int variant, const LaunchTunin
     cudaError_t e = persistent_grid(k, kConsumers, smem, tune.ctas_per_sm, p.total_units - p.unit_begin, &grid);
     if (e != cudaSuccess) return e;
     k<<<grid, kConsumers, smem, st>>>(p);
-  } else if (variant == 0 && KIND == KIND_FP && p.qc.lut_direct) {
-    auto k = seg4_tma_kernel<DT, KIND, SYM, GIVEN, KIND == KIND_FP ? LUT_DIRECT : LUT_STEP>;  // one value per bit pattern
-    const size_t smem = kSmemHeader + p.lut_smem_bytes + (size_t)p.n_stages * kTileBytes;
-    cudaError_t e = persistent_grid(k, kConsumers + 32, smem, tune.ctas_per_sm, p.total_units - p.unit_begin, &grid);
-    if (e != cudaSuccess) return e;
-    k<<<grid, kConsumers + 32, smem, st>>>(p);
-  } else if (variant == 0 && KIND == KIND_FP && p.qc.lut_rep_shift > 0) {
-    auto k = seg4_tma_kernel<DT, KIND, SYM, GIVEN, KIND == KIND_FP ? LUT_REPL : LUT_STEP>;  // interleaved copies of the step table
-    const size_t smem = kSmemHeader + p.lut_smem_bytes + (size_t)p.n_stages * kTileBytes;
-    cudaError_t e = persistent_grid(k, kConsumers + 32, smem, tune.ctas_per_sm, p.total_units - p.unit_begin, &grid);
-    if (e != cudaSuccess) return e;
-    k<<<grid, kConsumers + 32, smem, st>>>(p);
   } else if (variant == 0) {
-    auto k = seg4_tma_kernel<DT, KIND, SYM, GIVEN>;
     const size_t smem = kSmemHeader + p.lut_smem_bytes + (size_t)p.n_stages * kTileBytes;
-    cudaError_t e = persistent_grid(k, kConsumers + 32, smem, tune.ctas_per_sm, p.total_units - p.unit_begin, &grid);
+    cudaError_t e = cudaSuccess;
+#define IWQ_SEG4(LUTV, VPLV)                                                                                        \
+  do {                                                                                                             \
+    auto k = seg4_tma_kernel<DT, KIND, SYM, GIVEN, LUTV, VPLV>;                                                    \
+    constexpr int threads = kConsumers * 4 / VPLV + 32;                                                            \
+    e = persistent_grid(k, threads, smem, tune.ctas_per_sm, p.total_units - p.unit_begin, &grid);                  \
+    if (e == cudaSuccess) k<<<grid, threads, smem, st>>>(p);                                                       \
+  } while (0)
+    constexpr bool kFp = KIND == KIND_FP;
+    const int vpl = (KIND == KIND_INT_GENERIC) ? 4 : (int)p.seg_vpl;
+    if (kFp && p.qc.lut_direct) {  // one value per bit pattern
+      if (vpl == 16) IWQ_SEG4((kFp ? LUT_DIRECT : LUT_STEP), (KIND == KIND_INT_GENERIC ? 4 : 16));
+      else if (vpl == 8) IWQ_SEG4((kFp ? LUT_DIRECT : LUT_STEP), (KIND == KIND_INT_GENERIC ? 4 : 8));
+      else IWQ_SEG4((kFp ? LUT_DIRECT : LUT_STEP), 4);
+    } else if (kFp && p.qc.lut_rep_shift > 0) {  // interleaved copies of the step table
+      IWQ_SEG4((kFp ? LUT_REPL : LUT_STEP), 4);
+    } else if (!kFp && vpl == 16) {
+      IWQ_SEG4(LUT_STEP, ((kFp || KIND == KIND_INT_GENERIC) ? 4 : 16));
+    } else if (!kFp && vpl == 8) {
+      IWQ_SEG4(LUT_STEP, ((kFp || KIND == KIND_INT_GENERIC) ? 4 : 8));
+    } else {
+      IWQ_SEG4(LUT_STEP, 4);
+    }
+#undef IWQ_SEG4
     if (e != cudaSuccess) return e;
-    k<<<grid, kConsumers + 32, smem, st>>>(p);
   } else {
     auto k = seg_tma_kernel<DT, KIND, SYM, GIVEN>;
     const size_t smem = kSmemHeader + p.lut_smem_bytes + (size_t)p.n_stages * kTileBytes;

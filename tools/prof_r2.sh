@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 B="python bench.py --steps 3 --warmup 3 --skip-e2e --skip-cpu --skip-configs"
 $B > gpurun_out/r2_bench_plain.log 2>&1 || { tail -5 gpurun_out/r2_bench_plain.log; exit 1; }
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_bench.csv $B > gpurun_out/r2_ncu_bench.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:seg4|row_tma|col_|minmax|range_init|seg_" -c 400 --csv --log-file gpurun_out/r2_launches_bench.csv $B > gpurun_out/r2_ncu_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:seg4 --launch-skip 4 -c 1 -f -o gpurun_out/r2_prof_bench $B > gpurun_out/r2_ncu_full_bench.log 2>&1
 python tools/ncu_summary.py gpurun_out/r2_prof_bench.ncu-rep > gpurun_out/r2_ncu_bench_kernel.txt 2>&1
 ncu -i gpurun_out/r2_prof_bench.ncu-rep --page raw --csv > gpurun_out/r2_ncu_bench_kernel.csv 2>/dev/null
