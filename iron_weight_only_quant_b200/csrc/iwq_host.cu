@@ -53,6 +53,8 @@ struct Knobs {
   int col_mode = env_int("IWQ_COL_MODE", 3);         // 3: CTA-wide ring of 128 x 256 tensor-map tiles (col_wide_kernel; group 32 / 64 / 128),
                                                      // 2: warp-private 2-D tensor-map boxes (col_tma_kernel), 0: warp-private cp.async ring
                                                      // (col_async_kernel), 1: register-resident (col_reg_kernel)
+  int col_dbl_tile = env_int("IWQ_COL_DBL_TILE", 256); // col_double_kernel: columns per tile (256; 64 = second sweep from L2, measured 35-48 % SLOWER:
+                                                     // the 16 per-lane scale computations per tile are then spread over 4x fewer elements)
   int col_box = env_int("IWQ_COL_BOX", 0);           // col_tma_kernel: columns per box (32 / 64 / 128 / 256); 0 = 4096 / group (8 KB boxes)
   int col_hint = env_int("IWQ_COL_HINT", 2);         // col_tma_kernel: L2 policy of the tensor loads (1 evict_first, 2 evict_last)
   int col_stages = env_int("IWQ_COL_STAGES", 0);     // ring depth of col_async_kernel (1..4); 0 = automatic
@@ -223,15 +225,36 @@ static cudaError_t dispatch_fused(int dt, int kind, const LaunchParams& p, const
 }
 
 // quant_dim = 1 (segments down the rows): one launch of col_kernel over all matrices
-// rows per tile of col_wide_kernel: 128 when three 64 KB stages fit next to the partial ranges, the published constants of both
-// consumer groups and the step table; else 64 (32 KB tiles)
-static size_t col_wide_fixed(int64_t g, int kind, uint32_t lut_bytes, uint32_t rows_per_tile) {
+// Tile shape of col_wide_kernel.  Shared memory = header + minifloat table + partial ranges + the published constants of both
+// consumer groups + the ring; candidates in order of preference (largest bulk copies first): 128 x 256 (64 KB), 64 x 256 (32 KB,
+// group <= 64), 128 x 128 and 64 x 128 (256-byte rows); the first one whose ring holds at least three stages wins.
+struct ColWideShape {
+  uint32_t rows, cols, stages;
+};
+static size_t col_wide_fixed(int64_t g, int kind, bool sym, uint32_t lut_bytes, uint32_t tr, uint32_t cc) {
   const size_t words = kind == KIND_INT_GENERIC ? 16 : (kind == KIND_BFP ? 4 : 8);  // PreparedPair<..>::kWords
-  return (size_t)kColWideHeader + lut_bytes + kColWidePart + (size_t)kColWideGroups * (rows_per_tile / (uint32_t)g) * 128 * words * 4;
+  return (size_t)kColWideHeader + lut_bytes + (sym ? kColWidePart / 2 : kColWidePart) + (size_t)kColWideGroups * (tr / (uint32_t)g) * (cc / 2) * words * 4;
 }
-static uint32_t col_wide_rows(int64_t g, int kind, uint32_t lut_bytes) {
-  if (g <= 64 && (col_wide_fixed(g, kind, lut_bytes, kColWideRows) + 3u * kColWideTile > 227u * 1024u || knobs().col_box == 64)) return 64;
-  return kColWideRows;
+static bool col_wide_shape(int64_t g, int kind, bool sym, uint32_t lut_bytes, ColWideShape* out, bool full_tile_only = false) {
+  const uint32_t cand[4][2] = {{128, 256}, {64, 256}, {128, 128}, {64, 128}};
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t tr = cand[i][0], cc = cand[i][1];
+    if (tr % (uint32_t)g != 0) continue;
+    if (knobs().col_box == 64 && tr != 64 && g <= 64) continue;   // experiments: force 64-row tiles
+    if (knobs().col_box == 128 && cc != 128) continue;            // experiments: force 128-column tiles
+    if (full_tile_only && (tr != 128 || cc != 256)) continue;
+    const size_t fixed = col_wide_fixed(g, kind, sym, lut_bytes, tr, cc), tile = (size_t)tr * cc * 2;
+    int stg = knobs().col_stages > 0 ? knobs().col_stages : (tile >= 65536 ? 3 : 6);
+    if (stg > 8) stg = 8;  // ColWideCtx ctxs[8]
+    while (stg > 1 && fixed + (size_t)stg * tile > 227u * 1024u) --stg;
+    if (stg >= 3 || (knobs().col_stages > 0 && stg >= knobs().col_stages)) {
+      out->rows = tr;
+      out->cols = cc;
+      out->stages = (uint32_t)stg;
+      return true;
+    }
+  }
+  return false;
 }
 
 static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, LaunchParams& p, int kind, void* workspace, size_t ws_bytes, cudaStream_t st);
@@ -737,8 +760,26 @@ static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, Launc
   // col_wide_kernel: 128 x 256 tiles through a CTA-wide ring (every matrix must hold at least one full tile)
   bool wide = tma_tile && knobs().col_mode == 3 && (cfg->group == 32 || cfg->group == 64 || cfg->group == 128);
   for (int i = 0; i < n && wide; ++i) wide = ms[i].rows >= kColWideRows && ms[i].cols >= kColWideCols;
-  const int64_t wide_rows = wide ? (int64_t)col_wide_rows(cfg->group, kind, p.lut_smem_bytes) : 0;
-  const uint32_t unit_cols = wide ? (uint32_t)kColWideCols : (ctile ? ctile : (uint32_t)kColTile);
+  ColWideShape shape = {0, 0, 0};
+  if (wide && kind == KIND_FP && knobs().fp_mode == 2 && p.qc.approx != 2) {
+    // DIRECT minifloat table (one 16-bit value per bit pattern: one 2-byte load per element instead of an 8-byte load, three
+    // byte permutes, a compare and a select) when a tile shape with at least three stages fits next to it
+    QuantConsts q = p.qc;
+    set_lut_direct(cfg->dtype, &q);
+    const uint32_t direct_bytes = (uint32_t)(((size_t)q.lut_n * 2 + 1023) & ~(size_t)1023);
+    // (measured: the direct table pays only with full 128 x 256 tiles -- FP4 at group 128, every format on bf16; with smaller
+    //  tiles the step table and full tiles win: profiles/r02_sweep_col18.jsonl)
+    if (col_wide_shape(cfg->group, kind, p.qc.symmetric != 0, direct_bytes, &shape, true)) {
+      p.qc = q;
+      int rc = get_fp_lut(cfg, p.qc, st, &p.lut);
+      if (rc) return rc;
+      p.lut_smem_bytes = direct_bytes;
+    }
+  }
+  if (wide && shape.rows == 0) wide = col_wide_shape(cfg->group, kind, p.qc.symmetric != 0, p.lut_smem_bytes, &shape);
+  const int64_t wide_rows = wide ? (int64_t)shape.rows : 0;
+  const uint32_t dbl_tile = knobs().col_dbl_tile == 64 ? 64u : 256u;
+  const uint32_t unit_cols = wide ? shape.cols : (ctile ? ctile : (p.qc.approx == 2 ? dbl_tile : (uint32_t)kColTile));
   for (int i = 0; i < n; ++i) {
     int rc = check_matrix(&ms[i]);
     if (rc) return rc;
@@ -773,7 +814,7 @@ static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, Launc
   p.single = jobs[0];
   p.jobs = nullptr;
   p.col_group = cfg->group > 0 ? (uint32_t)cfg->group : 0u;
-  p.col_tile = ctile;
+  p.col_tile = p.qc.approx == 2 ? dbl_tile : ctile;
   p.col_rpl = (uint32_t)rpl;
   if (ctile && rpl == 0) {
     p.stage_bytes = (uint32_t)cfg->group * (ctile / 2);  // g rows x 16 * lpr bytes, lpr = ctile / 32
@@ -793,22 +834,16 @@ static int run_col(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, Launc
     p.l2_hint = (uint32_t)knobs().col_hint & 3u;
     std::vector<TensorMapPair> maps((size_t)n);
     if (wide) {
-      // load boxes of TR rows x 256 columns, store boxes of TR / 8 rows x 256 columns (one per consumer warp).  TR = 128 when three
-      // 64 KB stages fit next to the partial ranges / published constants / step table, else 64 (32 KB tiles, up to 6 stages)
+      // load boxes of TR rows x CC columns, store boxes of TR / 8 rows x CC columns (one per consumer warp)
       p.col_wide = 1;
-      p.col_tile = kColWideCols;
-      const uint32_t tr = (uint32_t)wide_rows;
-      auto fixed_for = [&](uint32_t rows_per_tile) { return col_wide_fixed(cfg->group, kind, p.lut_smem_bytes, rows_per_tile); };
-      p.col_rows = tr;
-      p.stage_bytes = tr * (uint32_t)(kColWideCols * 2);
-      int stg = knobs().col_stages > 0 ? knobs().col_stages : (tr == 128 ? 3 : 6);
-      if (stg > 8) stg = 8;  // ColWideCtx ctxs[8]
-      while (stg > 1 && fixed_for(tr) + (size_t)stg * p.stage_bytes > 227u * 1024u) --stg;
-      p.n_stages = stg;
+      p.col_tile = shape.cols;
+      p.col_rows = shape.rows;
+      p.stage_bytes = shape.rows * shape.cols * 2u;
+      p.n_stages = (int)shape.stages;
       for (int i = 0; i < n; ++i) {
-        rc = encode_map(&maps[i].in, ms[i].w, ms[i].rows, ms[i].cols, tr, kColWideCols);
+        rc = encode_map(&maps[i].in, ms[i].w, ms[i].rows, ms[i].cols, shape.rows, shape.cols);
         if (rc) return rc;
-        rc = encode_map(&maps[i].out, ms[i].out, ms[i].rows, ms[i].cols, tr / kColWideWG, kColWideCols);
+        rc = encode_map(&maps[i].out, ms[i].out, ms[i].rows, ms[i].cols, shape.rows / kColWideWG, shape.cols);
         if (rc) return rc;
       }
     }
@@ -914,20 +949,29 @@ int iwq_debug_plan(const iwq_config_t* cfg, int64_t rows, int64_t cols, int32_t*
   if (cfg->quant_dim == 1 && cfg->group != IWQ_GROUP_PER_TENSOR) {
     if (qc.approx == 2) {
       out[0] = 5;
-      out[7] = kColTile;
+      out[7] = knobs().col_dbl_tile == 64 ? 64 : 256;
       return IWQ_OK;
     }
     int rpl = 0, stages = 0;
     if (cfg->group > 0 && col_tma_tile(cfg->group) && knobs().col_mode == 3 && (cfg->group == 32 || cfg->group == 64 || cfg->group == 128) && rows >= kColWideRows &&
         cols >= kColWideCols) {
-      out[0] = 7;  // col_wide_kernel
-      const uint32_t tr = col_wide_rows(cfg->group, kind, lut_bytes);
-      int stg = tr == 128 ? 3 : 6;
-      while (stg > 1 && col_wide_fixed(cfg->group, kind, lut_bytes, tr) + (size_t)stg * tr * 512u > 227u * 1024u) --stg;
-      out[3] = stg;
-      out[5] = (int32_t)(tr * 512u);
-      out[7] = kColWideCols;
-      return IWQ_OK;
+      ColWideShape shape = {0, 0, 0};
+      uint32_t lb = lut_bytes;
+      if (kind == KIND_FP && knobs().fp_mode == 2 && qc.approx != 2) {
+        QuantConsts q = qc;
+        set_lut_direct(cfg->dtype, &q);
+        const uint32_t direct_bytes = (uint32_t)(((size_t)q.lut_n * 2 + 1023) & ~(size_t)1023);
+        if (col_wide_shape(cfg->group, kind, qc.symmetric != 0, direct_bytes, &shape, true)) lb = direct_bytes;
+      }
+      if (shape.rows != 0 || col_wide_shape(cfg->group, kind, qc.symmetric != 0, lb, &shape)) {
+        out[0] = 7;  // col_wide_kernel
+        out[3] = (int32_t)shape.stages;
+        out[4] = (int32_t)shape.rows;
+        out[5] = (int32_t)(shape.rows * shape.cols * 2u);
+        out[6] = lb != lut_bytes ? 1 : 0;  // direct minifloat table
+        out[7] = (int32_t)shape.cols;
+        return IWQ_OK;
+      }
     }
     if (cfg->group > 0 && col_tma_tile(cfg->group)) {
       out[0] = 6;  // col_tma_kernel
@@ -982,7 +1026,7 @@ int iwq_debug_set_knob(const char* name, int value) {
   IWQ_KNOB(seg_stages) IWQ_KNOB(seg_ctas) IWQ_KNOB(row_ctas) IWQ_KNOB(row_smem_kb) IWQ_KNOB(variant) IWQ_KNOB(row_warps) IWQ_KNOB(col_tile)
   IWQ_KNOB(col_ctas) IWQ_KNOB(fused_batch_mb) IWQ_KNOB(fused_lookahead) IWQ_KNOB(row_tma_out) IWQ_KNOB(wide_seg4) IWQ_KNOB(col_mode)
   IWQ_KNOB(col_stages) IWQ_KNOB(pt_slab_mb) IWQ_KNOB(pt_reverse) IWQ_KNOB(pt_hint) IWQ_KNOB(seg_hint) IWQ_KNOB(fp_mode) IWQ_KNOB(fp_rep) IWQ_KNOB(fp_rep_kb)
-  IWQ_KNOB(fp_stages) IWQ_KNOB(host_copy_only) IWQ_KNOB(seg_map) IWQ_KNOB(mm_tma) IWQ_KNOB(mm_stages) IWQ_KNOB(mm_hint) IWQ_KNOB(col_box) IWQ_KNOB(col_hint) IWQ_KNOB(seg_store) IWQ_KNOB(seg_vpl)
+  IWQ_KNOB(fp_stages) IWQ_KNOB(host_copy_only) IWQ_KNOB(seg_map) IWQ_KNOB(mm_tma) IWQ_KNOB(mm_stages) IWQ_KNOB(mm_hint) IWQ_KNOB(col_box) IWQ_KNOB(col_hint) IWQ_KNOB(seg_store) IWQ_KNOB(seg_vpl) IWQ_KNOB(col_dbl_tile)
 #undef IWQ_KNOB
   return fail(IWQ_ERR_INVALID, "unknown knob: " + n);
 }

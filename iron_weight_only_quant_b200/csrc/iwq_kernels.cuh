@@ -1102,9 +1102,9 @@ struct PreparedPair<DT, KIND_INT_GENERIC> {
   }
 };
 
-template <int DT>
-struct PreparedPair<DT, KIND_FP> {
-  FpTable<DT, true> f;
+template <int DT, int LUT>
+struct PreparedPairFp {
+  FpTable<DT, true, LUT> f;
   __device__ __forceinline__ void setup2(float mxa, float mna, float mxb, float mnb, const QuantConsts& c, bool, const FpStep* steps, float* sa, float* za, float* sb,
                                          float* zb, bool* bad) {
     FpQ qa = fp_segment_params<DT>(mxa, mna, c), qb = fp_segment_params<DT>(mxb, mnb, c);
@@ -1113,7 +1113,7 @@ struct PreparedPair<DT, KIND_FP> {
     *bad = qa.bad || qb.bad;
   }
   __device__ __forceinline__ bool slow() const { return f.slow_div; }
-  __device__ __forceinline__ void shfl_from(const PreparedPair& o, int src) {
+  __device__ __forceinline__ void shfl_from(const PreparedPairFp& o, int src) {
     using T2 = typename DType<DT>::T2;
     f = o.f;  // launch-uniform members (clamp bounds, table address, flags)
     f.S2 = from_u32<T2>(__shfl_sync(0xFFFFFFFFu, as_u32(o.f.S2), src));
@@ -1127,7 +1127,7 @@ struct PreparedPair<DT, KIND_FP> {
   }
   static constexpr int kWords = 8;
   template <class X>
-  __device__ __forceinline__ void map_from(const PreparedPair& o, X x) {
+  __device__ __forceinline__ void map_from(const PreparedPairFp& o, X x) {
     using T2 = typename DType<DT>::T2;
     f = o.f;  // launch-uniform members
     f.S2 = from_u32<T2>(x(as_u32(o.f.S2)));
@@ -1146,6 +1146,8 @@ struct PreparedPair<DT, KIND_FP> {
     return f.slow_div ? f.template apply<true, SYM ? 0 : 1>(w2, &v) : f.template apply<false, SYM ? 0 : 1>(w2, &v);
   }
 };
+template <int DT>
+struct PreparedPair<DT, KIND_FP> : PreparedPairFp<DT, LUT_STEP> {};
 
 template <int DT>
 struct PreparedPair<DT, KIND_BFP> {
@@ -1893,15 +1895,19 @@ struct ColWideCtx {  // 64 bytes
   uint32_t pad[5];
 };
 
-template <int DT, int KIND, bool SYM>
+template <int DT, int KIND, bool SYM, int LUT = LUT_STEP>
 __global__ void __launch_bounds__(kColWideWarps * 32 + 32, 1) col_wide_kernel(const __grid_constant__ LaunchParams p, const __grid_constant__ TensorMapPair single_maps,
                                                                                  const TensorMapPair* __restrict__ maps) {
   using T2 = typename DType<DT>::T2;
-  using PP = PreparedPair<DT, KIND>;
+  using PP = typename std::conditional<KIND == KIND_FP && LUT != LUT_STEP, PreparedPairFp<DT, LUT>, PreparedPair<DT, KIND>>::type;
   constexpr int kU = PP::kWords / 4;  // 16-byte units of one pair's constants
   constexpr int WG = kColWideWG, GT = WG * 32;  // warps / threads of a group
   const uint32_t TR = p.col_rows, RW = TR / (uint32_t)WG;  // rows per tile (128 / 64) and per warp
-  const uint32_t tile_bytes = TR * (uint32_t)(kColWideCols * 2);
+  const uint32_t CC = p.col_tile;                          // columns per tile (256 / 128): lpr = CC / 8 lanes cover a row, a warp-wide
+  const uint32_t lpr = CC >> 3;                            // 16-byte access 32 / lpr consecutive (dense) rows
+  const uint32_t tile_bytes = TR * CC * 2u;
+  const uint32_t n_acc = RW * lpr / 32u;                   // warp-wide accesses per warp and sweep (a multiple of 4)
+  const uint32_t half_cc = CC >> 1;                        // column pairs per row block
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + kMaxStages;
@@ -1910,10 +1916,12 @@ __global__ void __launch_bounds__(kColWideWarps * 32 + 32, 1) col_wide_kernel(co
   const FpStep* s_tbl = nullptr;
   if (KIND == KIND_FP) s_tbl = load_fp_lut(p, smem + kColWideHeader);
   uint8_t* part_all = smem + kColWideHeader + p.lut_smem_bytes;
-  uint8_t* pars_all = part_all + kColWidePart;
+  constexpr uint32_t kPartBytes = SYM ? kColWidePart / 2 : kColWidePart;  // symmetric forms keep no minima
+  constexpr uint32_t kPW = SYM ? 128u : 256u;                              // words of partials per warp
+  uint8_t* pars_all = part_all + kPartBytes;
   const uint32_t g = p.col_group;
   const uint32_t wpb = g / RW;                       // warps per row block
-  const uint32_t n_pairs = (TR / g) * 128u;
+  const uint32_t n_pairs = (TR / g) * half_cc;
   const uint32_t pars_bytes = n_pairs * PP::kWords * 4u;
   uint8_t* ring = pars_all + (size_t)kColWideGroups * pars_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1940,14 +1948,14 @@ __global__ void __launch_bounds__(kColWideWarps * 32 + 32, 1) col_wide_kernel(co
         advance_job(p, unit, &cur, &jb);
         const uint32_t cols = jb.row_bytes >> 1;
         const uint32_t rows = (uint32_t)(jb.bytes / jb.row_bytes);
-        const uint32_t n_ct = (cols + kColWideCols - 1) / kColWideCols;
+        const uint32_t n_ct = (cols + CC - 1) / CC;
         const uint32_t local = unit - jb.first_unit;
         const uint32_t rt = local / n_ct, ct = local - rt * n_ct;
         ColWideCtx c;
         c.map = maps ? &maps[cur] : &single_maps;
         c.scales = jb.scales;
         c.zeros = jb.zeros;
-        c.c0 = ct * kColWideCols;
+        c.c0 = ct * CC;
         c.r0 = rt * TR;
         c.n_rb = rows / g;
         c.cols = cols;
@@ -1982,10 +1990,10 @@ __global__ void __launch_bounds__(kColWideWarps * 32 + 32, 1) col_wide_kernel(co
   const uint32_t gi = (uint32_t)warp / WG, wg = (uint32_t)warp % WG;
   const uint32_t t_g = threadIdx.x - gi * GT;                   // thread within the group
   const uint32_t my_blk = wg / wpb;                             // row block of this warp's rows within the tile
-  uint8_t* part = part_all + (size_t)gi * (kColWidePart / kColWideGroups);
+  uint8_t* part = part_all + (size_t)gi * (kPartBytes / kColWideGroups);
   uint8_t* pars = pars_all + (size_t)gi * pars_bytes;
   uint32_t* flags = flags_all + 2u * gi;
-  uint4* part_mx = reinterpret_cast<uint4*>(part) + (size_t)wg * 64 + lane;     // [warp][0][lane]
+  uint4* part_mx = reinterpret_cast<uint4*>(part) + (size_t)wg * (kPW / 4) + lane;  // [warp][0][lane]
   uint4* part_mn = part_mx + 32;                                                 // [warp][1][lane]
   const uint32_t* part_w = reinterpret_cast<const uint32_t*>(part);             // word view: [warp][max | min][128 pairs]
   const uint32_t bar_id = 1u + gi;
@@ -1997,19 +2005,26 @@ __global__ void __launch_bounds__(kColWideWarps * 32 + 32, 1) col_wide_kernel(co
     const uint32_t stage = i % (uint32_t)n_stages, phase = (i / (uint32_t)n_stages) & 1u;
     mbar_wait(&full[stage], phase);
     const ColWideCtx c = ctxs[stage];
-    uint8_t* wbase = ring + (size_t)stage * tile_bytes + (size_t)wg * (RW * 512u);
+    uint8_t* wbase = ring + (size_t)stage * tile_bytes + (size_t)wg * (RW * CC * 2u);
     uint8_t* sd = wbase + (size_t)lane * 16u;
 
     // ---- sweep 1 ----
     uint32_t mx[4] = {ident_max, ident_max, ident_max, ident_max};
     uint32_t mn[4] = {ident_min, ident_min, ident_min, ident_min};
 #pragma unroll 1
-    for (uint32_t r0 = 0; r0 < RW; r0 += 8) {
-      uint4 v[8];
+    for (uint32_t r0 = 0; r0 < n_acc; r0 += 4) {
+      uint4 v[4];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) v[r] = lds128(sd + (r0 + r) * 512);
+      for (int r = 0; r < 4; ++r) v[r] = lds128(sd + (r0 + r) * 512);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) col_range_update<DT, SYM>(mx, mn, v[r]);
+      for (int r = 0; r < 4; ++r) col_range_update<DT, SYM>(mx, mn, v[r]);
+    }
+    if (lpr == 16u) {  // 256-byte rows: lanes L and L ^ 16 hold the two rows of an access, same columns
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mx[j] = as_u32(__hmax2_nan(from_u32<T2>(mx[j]), from_u32<T2>(__shfl_xor_sync(0xFFFFFFFFu, mx[j], 16))));
+        if (!SYM) mn[j] = as_u32(__hmin2_nan(from_u32<T2>(mn[j]), from_u32<T2>(__shfl_xor_sync(0xFFFFFFFFu, mn[j], 16))));
+      }
     }
     *part_mx = make_uint4(mx[0], mx[1], mx[2], mx[3]);
     if (!SYM) *part_mn = make_uint4(mn[0], mn[1], mn[2], mn[3]);
@@ -2018,11 +2033,11 @@ __global__ void __launch_bounds__(kColWideWarps * 32 + 32, 1) col_wide_kernel(co
     // ---- parameters: one column pair per thread (while this group computes them the other group sweeps its own tile) ----
     if (t_g == 0) flags[parity ^ 1u] = 0u;  // the other parity's flag: read by everybody before this tile's first barrier, set again after the next one
     for (uint32_t pp = t_g; pp < n_pairs; pp += GT) {
-      const uint32_t b = pp >> 7, q = pp & 127u;
+      const uint32_t b = pp / half_cc, q = pp - b * half_cc;
       uint32_t mxs = ident_max, mns = ident_min;
       for (uint32_t w = b * wpb; w < (b + 1u) * wpb; ++w) {
-        mxs = as_u32(__hmax2_nan(from_u32<T2>(mxs), from_u32<T2>(part_w[w * 256u + q])));
-        if (!SYM) mns = as_u32(__hmin2_nan(from_u32<T2>(mns), from_u32<T2>(part_w[w * 256u + 128u + q])));
+        mxs = as_u32(__hmax2_nan(from_u32<T2>(mxs), from_u32<T2>(part_w[w * kPW + q])));
+        if (!SYM) mns = as_u32(__hmin2_nan(from_u32<T2>(mns), from_u32<T2>(part_w[w * kPW + 128u + q])));
       }
       const float mxa = DType<DT>::to_f32((uint16_t)(mxs & 0xFFFFu)), mxb = DType<DT>::to_f32((uint16_t)(mxs >> 16));
       const float mna = DType<DT>::to_f32((uint16_t)(mns & 0xFFFFu)), mnb = DType<DT>::to_f32((uint16_t)(mns >> 16));
@@ -2062,7 +2077,7 @@ __global__ void __launch_bounds__(kColWideWarps * 32 + 32, 1) col_wide_kernel(co
     const bool suspect = flags[parity] != 0u;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint4* src = reinterpret_cast<const uint4*>(pars) + (size_t)((my_blk * 4u + (uint32_t)j) * kU) * 32u + lane;
+      const uint4* src = reinterpret_cast<const uint4*>(pars) + (size_t)((my_blk * 4u + (uint32_t)j) * kU) * 32u + (lane & (lpr - 1u));
       uint32_t wds[PP::kWords];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
@@ -2074,7 +2089,7 @@ __global__ void __launch_bounds__(kColWideWarps * 32 + 32, 1) col_wide_kernel(co
     }
     if (!suspect) {
 #pragma unroll 2
-      for (uint32_t r = 0; r < RW; ++r) {
+      for (uint32_t r = 0; r < n_acc; ++r) {
         const uint4 v = lds128(sd + r * 512);
         uint4 o;
         o.x = prep[0].template apply<SYM, 0>(v.x, p.qc); o.y = prep[1].template apply<SYM, 0>(v.y, p.qc);
@@ -2082,10 +2097,10 @@ __global__ void __launch_bounds__(kColWideWarps * 32 + 32, 1) col_wide_kernel(co
         sts128(sd + r * 512, o);
       }
     } else {
-      const bool live = c.c0 + (uint32_t)lane * 8u < c.cols && c.r0 + wg * RW < c.n_rb * g;
+      const bool live = c.c0 + ((uint32_t)lane & (lpr - 1u)) * 8u < c.cols && c.r0 + wg * RW < c.n_rb * g;
       bool nan_seen = false;
 #pragma unroll 1
-      for (uint32_t r = 0; r < RW; ++r) {
+      for (uint32_t r = 0; r < n_acc; ++r) {
         const uint4 v = lds128(sd + r * 512);
         uint4 o;
         o.x = prep[0].template apply<SYM>(v.x, p.qc); o.y = prep[1].template apply<SYM>(v.y, p.qc);
@@ -2135,6 +2150,12 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile = 4 row blocks x C columns.  C = 256 (default): a lane owns 8 columns of a full-width access.  C = 64 (IWQ_COL_DBL_TILE): 8
+  // lanes cover a 128-byte row piece and a warp-wide access takes 4 consecutive rows, so that the second sweep finds the tile in L2
+  // (with C = 256 the 296 resident tiles are 76 MB: 1.68 x read traffic) -- measured 35-48 % SLOWER (profiles/r02_sweep_col19.jsonl):
+  // the 16 scale computations per lane and tile are then spread over 4 x fewer elements; the kernel is instruction-bound, not HBM-bound
+  const uint32_t C = p.col_tile, lpr = C >> 3, rps = 32u / lpr;
+  const uint32_t sub = (uint32_t)lane & (lpr - 1u), rph = (uint32_t)lane / lpr;
   int cur = -1;
   Job jb;
   uint32_t par = 0;
@@ -2147,10 +2168,10 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
     const uint32_t cols = jb.row_bytes >> 1;
     const uint32_t rows = (uint32_t)(jb.bytes / jb.row_bytes);
     const uint32_t g = p.col_group;
-    const uint32_t n_ct = (cols + kColTile - 1) / kColTile;
+    const uint32_t n_ct = (cols + C - 1) / C;
     const uint32_t local = tile - jb.first_unit;
     const uint32_t rb4 = local / n_ct, ct = local - rb4 * n_ct;  // rb4 counts groups of 4 row blocks
-    const uint32_t col = ct * kColTile + (uint32_t)lane * 8u;
+    const uint32_t col = ct * C + sub * 8u;
     const bool live = col < cols;
     const size_t off = (size_t)rb4 * 4 * g * jb.row_bytes + (size_t)col * 2;
     const uint8_t* src = jb.src + off;
@@ -2164,7 +2185,7 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
 #pragma unroll
       for (int j = 0; j < 4; ++j) mx[b][j] = 0u;
     if (live) {
-      for (uint32_t k = (uint32_t)warp; k < g; k += 8) {
+      for (uint32_t k = (uint32_t)warp * rps + rph; k < g; k += 8u * rps) {
         uint4 v[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) v[b] = ldg128(src + b * blk + (size_t)k * jb.row_bytes);
@@ -2175,6 +2196,12 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
           for (int j = 0; j < 4; ++j) mx[b][j] = as_u32(__hmax2_nan(from_u32<T2>(mx[b][j]), from_u32<T2>(w4[j] & 0x7FFF7FFFu)));
         }
       }
+    }
+    for (uint32_t o = lpr; o < 32u; o <<= 1) {  // the row phases of a warp-wide access hold the same columns
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mx[b][j] = as_u32(__hmax2_nan(from_u32<T2>(mx[b][j]), from_u32<T2>(__shfl_xor_sync(0xFFFFFFFFu, mx[b][j], o))));
     }
 #pragma unroll
     for (int b = 0; b < 4; ++b) part[((par * 8 + warp) * 4 + b) * 32 + lane] = make_uint4(mx[b][0], mx[b][1], mx[b][2], mx[b][3]);
@@ -2206,7 +2233,7 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
         S2[b][j] = as_u32(D::from_f32x2(qa.S, qb.S));
         any_bad |= qa.bad || qb.bad;
         slow |= qa.slow_div || qb.slow_div;
-        if (live && warp == 0 && jb.scales) {
+        if (live && warp == 0 && rph == 0u && jb.scales) {
           const size_t n_rb = rows / g;
           const size_t ga = (size_t)(col + 2 * j) * n_rb + (size_t)rb4 * 4 + b;
           reinterpret_cast<uint16_t*>(jb.scales)[ga] = D::from_f32(qa.S);
@@ -2223,7 +2250,7 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
       const uint32_t val_saddr = smem_u32(smem + 32768 + p.lut_smem_bytes);
       auto sweep2 = [&](auto slow_c) {
       constexpr bool kSlow = decltype(slow_c)::value;  // IEEE division only for degenerate scales: chosen once per tile
-      for (uint32_t k = (uint32_t)warp; k < g; k += 8) {
+      for (uint32_t k = (uint32_t)warp * rps + rph; k < g; k += 8u * rps) {
         uint4 v[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) v[b] = ldg128(src + b * blk + (size_t)k * jb.row_bytes);

@@ -85,13 +85,21 @@ cudaError_t launch_col_tma(const LaunchParams& p, const TensorMapPair& single, c
 template <int DT, int KIND, bool SYM>
 static cudaError_t launch_col_tma_one(const LaunchParams& p, const TensorMapPair& single, const TensorMapPair* maps, const LaunchTuning& tune, cudaStream_t st) {
   if (p.col_wide) {
-    auto kw = col_wide_kernel<DT, KIND, SYM>;
-    const size_t n_pairs = (size_t)(p.col_rows / p.col_group) * 128;
-    const size_t smem = kColWideHeader + p.lut_smem_bytes + kColWidePart + kColWideGroups * n_pairs * PreparedPair<DT, KIND>::kWords * 4 + (size_t)p.n_stages * p.stage_bytes;
+    const size_t n_pairs = (size_t)(p.col_rows / p.col_group) * (p.col_tile / 2);
+    const size_t smem = kColWideHeader + p.lut_smem_bytes + (SYM ? kColWidePart / 2 : kColWidePart) + kColWideGroups * n_pairs * PreparedPair<DT, KIND>::kWords * 4 + (size_t)p.n_stages * p.stage_bytes;
     int grid = 0;
-    cudaError_t e = persistent_grid(kw, kColWideWarps * 32 + 32, smem, 1, p.total_units, &grid);
-    if (e != cudaSuccess) return e;
-    kw<<<grid, kColWideWarps * 32 + 32, smem, st>>>(p, single, maps);
+    cudaError_t e;
+    if (KIND == KIND_FP && p.qc.lut_direct) {
+      auto kw = col_wide_kernel<DT, KIND, SYM, KIND == KIND_FP ? LUT_DIRECT : LUT_STEP>;
+      e = persistent_grid(kw, kColWideWarps * 32 + 32, smem, 1, p.total_units, &grid);
+      if (e != cudaSuccess) return e;
+      kw<<<grid, kColWideWarps * 32 + 32, smem, st>>>(p, single, maps);
+    } else {
+      auto kw = col_wide_kernel<DT, KIND, SYM>;
+      e = persistent_grid(kw, kColWideWarps * 32 + 32, smem, 1, p.total_units, &grid);
+      if (e != cudaSuccess) return e;
+      kw<<<grid, kColWideWarps * 32 + 32, smem, st>>>(p, single, maps);
+    }
     return cudaGetLastError();
   }
   auto k = col_tma_kernel<DT, KIND, SYM>;

@@ -43,8 +43,12 @@ CONFIGS = {
     "fp4e2m1g128_d1": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=2, mant_bits=1, symmetric=True, quant_dim=1),
     "fp4e2m1g64_d1": dict(scheme=_lib.SCHEME_FP_CODEC, group=64, exp_bits=2, mant_bits=1, symmetric=True, quant_dim=1),
     "fp8e4m3g128_d1": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=4, mant_bits=3, symmetric=True, quant_dim=1),
+    "fp6e3m2g128_d1": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=3, mant_bits=2, symmetric=True, quant_dim=1),
+    "fp8e4m3g64_d1": dict(scheme=_lib.SCHEME_FP_CODEC, group=64, exp_bits=4, mant_bits=3, symmetric=True, quant_dim=1),
+    "fp6e3m2g64_d1": dict(scheme=_lib.SCHEME_FP_CODEC, group=64, exp_bits=3, mant_bits=2, symmetric=True, quant_dim=1),
     "fp4e2m1g128_d1_approx": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=2, mant_bits=1, symmetric=True, quant_dim=1, approx=1, hi_align_start=1, hi_align_exp_field=1, tail_pad_bits=0),
     "fp4e2m1g128_d1_double": dict(scheme=_lib.SCHEME_FP_CODEC, group=128, exp_bits=2, mant_bits=1, symmetric=True, quant_dim=1, approx=2, hi_align_start=0, hi_align_exp_field=2, tail_pad_bits=1),
+    "fp8e4m3g64_d1_double": dict(scheme=_lib.SCHEME_FP_CODEC, group=64, exp_bits=4, mant_bits=3, symmetric=True, quant_dim=1, approx=2, hi_align_start=13, hi_align_exp_field=15, tail_pad_bits=-1),
     "int4pc_sym": dict(scheme=_lib.SCHEME_INT, group=-2, bits=4, symmetric=True),
     "fp4e2m1pc": dict(scheme=_lib.SCHEME_FP_CODEC, group=-2, exp_bits=2, mant_bits=1, symmetric=True),
     "int4pt_sym": dict(scheme=_lib.SCHEME_INT, group=-1, bits=4, symmetric=True),
