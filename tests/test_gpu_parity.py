@@ -751,3 +751,63 @@ def test_double_approximate_matches_reference_golden(golden, dt, case):
         assert_bits(bits(ql.weight.data), ref["out"], dt, key + " large")
     finally:
         quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: shapes the vectorised kernels do not take directly, and full-size properties of the column path
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_odd_shapes_match_oracle(dt):
+    """The reference takes ANY shape (quant_funcs.py:10-15): tensors whose numel / rows / groups are not whole 16-byte
+    vectors ([3,5], [7,129] per tensor and per channel, group 12), 1-D and 3-D inputs, and the in-place contract on a
+    non-contiguous view (the caller's storage is mutated, quant_funcs.py:44-46)."""
+    cases = [((3, 5), dict(per_tensor=True), -1), ((7, 129), dict(per_tensor=True), -1), ((7, 129), dict(), -2), ((5, 36), dict(q_group_size=12), 12),
+             ((1, 8), dict(per_tensor=True), -1), ((2, 3, 40), dict(q_group_size=20), 20), ((6, 1000), dict(), -2), ((1, 3), dict(), -2)]
+    for shape, kw, grp in cases:
+        for zp in (True, False):
+            n = int(np.prod(shape))
+            w = seeded(n, 1, dt, 7 + n).reshape(shape)
+            ref = O.int_fake_quant(bits(w).reshape(-1, shape[-1]), dt, 4, zp, grp)["out"].reshape(shape)
+            out = quant_funcs.pseudo_quantize_tensor(w.to(DEV), n_bits=4, zero_point=zp, **kw)
+            assert out.shape == w.shape
+            assert_bits(bits(out), ref, dt, f"{dt} {shape} {kw} zp={zp}")
+    # non-contiguous in place: every second column of a wider buffer
+    base = seeded(16, 512, dt, 99).to(DEV)
+    view = base[:, ::2]
+    want = O.int_fake_quant(bits(view), dt, 4, True, 128)["out"]
+    untouched = bits(base[:, 1::2])
+    ret = quant_funcs.pseudo_quantize_tensor(view, n_bits=4, zero_point=True, q_group_size=128, inplace=True)
+    assert ret.data_ptr() == view.data_ptr()
+    assert_bits(bits(base[:, ::2]), want, dt, "strided in place")
+    assert np.array_equal(bits(base[:, 1::2]), untouched)
+    # the wrappers on odd shapes (quant_funcs.py:49-77)
+    t = seeded(5, 77, dt, 3).to(DEV)
+    assert_bits(bits(quant_funcs.quantize_weight_per_tensor_absmax(t, n_bits=8)), O.int_fake_quant(bits(t), dt, 8, False, -1)["out"], dt, "per-tensor absmax odd")
+    assert_bits(bits(quant_funcs.quantize_activation_per_token_absmax(t.reshape(5, 7, 11), n_bits=8)), O.int_fake_quant(bits(t).reshape(35, 11), dt, 8, True, -2)["out"].reshape(5, 7, 11), dt, "per-token odd")
+
+
+@pytest.mark.parametrize("shape", [(8192, 8192), (11008, 4096), (4096, 11008)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_quant_dim1_equals_transposed_quant_dim0_full_size(shape):
+    """Size-independent property of the column-grouped path at LLaMA sizes (quant_linear.py:478-483 transposes, quantises along
+    the last dim and transposes back): quant_dim = 1 on W == (quant_dim = 0 on W^T)^T, bit for bit, including the order of
+    the emitted scales and zero points -- col_wide_kernel against seg4_tma_kernel, two kernels that share no code path but
+    the element stage."""
+    rows, cols = shape
+    g = torch.Generator(device=DEV).manual_seed(4321)
+    w = (torch.randn(rows, cols, generator=g, device=DEV) * 0.02).half()
+    wt = w.t().contiguous()
+    for name, mk in [("int4 g128 asym", lambda qd: _lib.make_config(torch.float16, _lib.SCHEME_INT, 128, bits=4, symmetric=False, quant_dim=qd)),
+                     ("int3 g64 sym", lambda qd: _lib.make_config(torch.float16, _lib.SCHEME_INT, 64, bits=3, symmetric=True, quant_dim=qd)),
+                     ("fp4 e2m1 g128", lambda qd: _lib.make_config(torch.float16, _lib.SCHEME_FP_CODEC, 128, exp_bits=2, mant_bits=1, symmetric=True, quant_dim=qd)),
+                     ("fp8 e4m3 g64 approx", lambda qd: _lib.make_config(torch.float16, _lib.SCHEME_FP_CODEC, 64, exp_bits=4, mant_bits=3, symmetric=True, quant_dim=qd, approx=1, hi_align_start=12, hi_align_exp_field=15, tail_pad_bits=1))]:
+        grp = 64 if "g64" in name else 128
+        G = rows * cols // grp
+        o1, s1, z1 = torch.empty_like(w), torch.empty(G, dtype=w.dtype, device=DEV), torch.zeros(G, dtype=w.dtype, device=DEV)
+        o0, s0, z0 = torch.empty_like(wt), torch.empty(G, dtype=w.dtype, device=DEV), torch.zeros(G, dtype=w.dtype, device=DEV)
+        asym = "asym" in name
+        _lib.fake_quant_(w, o1, mk(1), rows, cols, scales=s1, zeros=z1 if asym else None)
+        _lib.fake_quant_(wt, o0, mk(0), cols, rows, scales=s0, zeros=z0 if asym else None)
+        assert torch.equal(o1.view(torch.int16), o0.t().contiguous().view(torch.int16)), name
+        assert torch.equal(s1.view(torch.int16), s0.view(torch.int16)), name + " scales"
+        assert torch.equal(z1.view(torch.int16), z0.view(torch.int16)), name + " zeros"
+    assert _lib.read_and_clear_status(torch.device(DEV)) & _lib.STATUS_NAN == 0
