@@ -596,7 +596,11 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
       // measured (tools/r2_exp16.sh / r2_exp17.sh, fresh data): the direct-table minifloat stage gains 5-13 % from 8 vectors per lane
       // (FP4 E2M1 5.72 -> 6.39 TB/s, FP6 E3M2 5.60 -> 6.35, FP8 E4M3 5.45 -> 5.72); the INT / BFP stages are HBM-bound either way in
       // bench-length runs (6.23-6.34 vs 6.17-6.32 TB/s) and keep 4 (in minute-long runs under the power cap 8 is ~7 % faster)
-      const int auto_vpl = kind == KIND_FP ? 8 : kSeg4AutoVpl;
+      // INT stage, bench regime, fresh process per measurement, alternating (profiles/r02_bench20_vpl.txt): group 128 -- 16 vectors
+      // per lane (a lane owns a whole segment: no shuffle, no repeated parameters) 6327-6382 vs 6270-6280 GB/s at 4; group 256 -- 8:
+      // 6270-6298 vs 6041-6068; group 64 -- 4: 6350-6386 vs 6063-6089 at 8; BFP and the per-tensor apply pass: no gain, 4
+      int auto_vpl = kind == KIND_FP ? 8 : kSeg4AutoVpl;
+      if ((kind == KIND_INT_FAST || kind == KIND_INT_WIDE) && !per_tensor) auto_vpl = pl.seg_elems == 128 ? 16 : (pl.seg_elems >= 256 ? 8 : 4);
       const int want = knobs().seg_vpl == 8 || knobs().seg_vpl == 16 ? knobs().seg_vpl : (knobs().seg_vpl == 4 ? 4 : auto_vpl);
       const bool fp_step = kind == KIND_FP && !p.qc.lut_direct;
       if (kind != KIND_INT_GENERIC && !fp_step) {
