@@ -2147,6 +2147,9 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
   // [2 parities][8 warps][4 blocks][32 lanes] uint4 = 32 KB, then the step table
   uint4* part = reinterpret_cast<uint4*>(smem);
   const FpStep* s_tbl = load_fp_lut(p, smem + 32768);
+  // behind the step table and the value table: the published scales [16 (block, pair)][32 lanes] float4 + flags
+  float4* exch = reinterpret_cast<float4*>(smem + 32768 + p.lut_smem_bytes + p.lut_extra_bytes);
+  uint32_t* exch_flags = reinterpret_cast<uint32_t*>(exch + 16 * 32);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -2218,7 +2221,34 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
     }
     par ^= 1u;
 
-    // ---- scales per (block, column pair) ----
+    // ---- scales per (block, column pair): warp w computes pairs 2w and 2w + 1 of the 16 (block, pair) combinations of every lane's
+    //      columns and publishes {S, 1/S} through shared memory (round 1: all 8 warps computed all 16 -- 2000 of the 10 000
+    //      instructions a lane spends on a tile) ----
+    {
+      uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (warp == i) {
+          m0 = mx[(2 * i) >> 2][(2 * i) & 3];
+          m1 = mx[(2 * i + 1) >> 2][(2 * i + 1) & 3];
+        }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t m = h ? m1 : m0;
+        const int idx = 2 * warp + h, b = idx >> 2, j = idx & 3;
+        const float mxa = D::to_f32((uint16_t)(m & 0xFFFFu)), mxb = D::to_f32((uint16_t)(m >> 16));
+        const FpQ qa = fp_segment_params<DT>(mxa, -mxa, p.qc), qb = fp_segment_params<DT>(mxb, -mxb, p.qc);
+        exch[idx * 32 + lane] = make_float4(qa.S, qb.S, qa.r, qb.r);
+        exch_flags[idx * 32 + lane] = ((qa.bad || qb.bad) ? 1u : 0u) | ((qa.slow_div || qb.slow_div) ? 2u : 0u);
+        if (live && rph == 0u && jb.scales) {
+          const size_t n_rb = rows / g;
+          const size_t ga = (size_t)(col + 2 * j) * n_rb + (size_t)rb4 * 4 + b;
+          reinterpret_cast<uint16_t*>(jb.scales)[ga] = D::from_f32(qa.S);
+          reinterpret_cast<uint16_t*>(jb.scales)[ga + n_rb] = D::from_f32(qb.S);
+        }
+      }
+    }
+    __syncthreads();
     float2 S[4][4], R[4][4];
     uint32_t S2[4][4];
     bool any_bad = false, slow = false;
@@ -2226,19 +2256,13 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
     for (int b = 0; b < 4; ++b) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float mxa = D::to_f32((uint16_t)(mx[b][j] & 0xFFFFu)), mxb = D::to_f32((uint16_t)(mx[b][j] >> 16));
-        const FpQ qa = fp_segment_params<DT>(mxa, -mxa, p.qc), qb = fp_segment_params<DT>(mxb, -mxb, p.qc);
-        S[b][j] = make_float2(qa.S, qb.S);
-        R[b][j] = make_float2(qa.r, qb.r);
-        S2[b][j] = as_u32(D::from_f32x2(qa.S, qb.S));
-        any_bad |= qa.bad || qb.bad;
-        slow |= qa.slow_div || qb.slow_div;
-        if (live && warp == 0 && rph == 0u && jb.scales) {
-          const size_t n_rb = rows / g;
-          const size_t ga = (size_t)(col + 2 * j) * n_rb + (size_t)rb4 * 4 + b;
-          reinterpret_cast<uint16_t*>(jb.scales)[ga] = D::from_f32(qa.S);
-          reinterpret_cast<uint16_t*>(jb.scales)[ga + n_rb] = D::from_f32(qb.S);
-        }
+        const float4 e = exch[(b * 4 + j) * 32 + lane];
+        const uint32_t f = exch_flags[(b * 4 + j) * 32 + lane];
+        S[b][j] = make_float2(e.x, e.y);
+        R[b][j] = make_float2(e.z, e.w);
+        S2[b][j] = as_u32(D::from_f32x2(e.x, e.y));
+        any_bad |= (f & 1u) != 0u;
+        slow |= (f & 2u) != 0u;
       }
     }
     if (live && any_bad && p.status) atomicOr(p.status, IWQ_STATUS_NAN);

@@ -149,7 +149,7 @@ cudaError_t launch_fused(const LaunchParams& p, const FusedParams& f, bool sym, 
 template <int DT>
 cudaError_t launch_col_double(const LaunchParams& p, cudaStream_t st) {
   auto k = col_double_kernel<DT>;
-  const size_t smem = 32768 + p.lut_smem_bytes + p.lut_extra_bytes;
+  const size_t smem = 32768 + p.lut_smem_bytes + p.lut_extra_bytes + 16 * 32 * (16 + 4);  // partials | step table | value table | published scales + flags
   int grid = 0;
   cudaError_t e = persistent_grid(k, 256, smem, 0, p.total_units, &grid);
   if (e != cudaSuccess) return e;
