@@ -101,6 +101,12 @@ int iwq_abi_version(void);
 const char* iwq_last_error(void);
 /* bytes of device workspace `iwq_fake_quant_batched` needs for `n` matrices */
 size_t iwq_workspace_bytes(int n);
+/* Job-table cache.  A batched entry point copies its job table (64 bytes per matrix) into `workspace` on the caller's stream; that
+ * copy has to wait for the previous kernel of the stream (~35 us of idle GPU between back-to-back launches).  enable = 1 declares
+ * that the workspaces handed to this library are written by nobody else between calls: a table identical to the one last uploaded
+ * to the same workspace on the same stream is then not uploaded again.  Off by default; the Python layer (which owns its
+ * workspaces) turns it on.  No counterpart in the reference (quant_wrapper.py:52-82 launches per module). */
+int iwq_workspace_cache(int enable);
 
 /* ---- the hot path ----------------------------------------------------------------------------- */
 /* One fused pass over one matrix.  Replaces pseudo_quantize_tensor (quant_funcs.py:4-46), the INT

@@ -28,6 +28,7 @@ EXPORTS = (
     "iwq_abi_version",
     "iwq_last_error",
     "iwq_workspace_bytes",
+    "iwq_workspace_cache",
     "iwq_fake_quant",
     "iwq_fake_quant_batched",
     "iwq_fake_quant_per_tensor_batched",
@@ -101,6 +102,8 @@ def lib() -> ctypes.CDLL:
         L.iwq_last_error.restype = ctypes.c_char_p
         L.iwq_workspace_bytes.restype = ctypes.c_size_t
         L.iwq_workspace_bytes.argtypes = [ctypes.c_int]
+        L.iwq_workspace_cache.restype = ctypes.c_int
+        L.iwq_workspace_cache.argtypes = [ctypes.c_int]
         L.iwq_fake_quant.restype = ctypes.c_int
         L.iwq_fake_quant.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(Matrix), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.iwq_fake_quant_batched.restype = ctypes.c_int
@@ -129,6 +132,8 @@ def lib() -> ctypes.CDLL:
         L.iwq_fake_quant_per_tensor_fused.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(Matrix), ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(Peers), ctypes.c_void_p, ctypes.c_void_p]
         if L.iwq_abi_version() != 4:
             raise RuntimeError("libiwq_b200.so ABI version mismatch")
+        # the job-table workspaces handed to the library are the tensors of scratch() below: nobody else writes them
+        L.iwq_workspace_cache(1)
         _lib = L
     return _lib
 
@@ -200,6 +205,8 @@ def scratch(device: torch.device, n_jobs: int = 1):
         status = st[0] if st is not None else torch.zeros(1, dtype=torch.int32, device=device)
         rng = torch.empty(max(2 * n_jobs, 2), dtype=torch.float32, device=device)
         ws = torch.empty(max(need_ws, 64), dtype=torch.uint8, device=device)
+        if st is not None:
+            lib().iwq_workspace_cache(1)  # the old workspace goes back to the allocator: forget what was uploaded to it
         st = (status, rng, ws)
         _scratch[key] = st
     return st

@@ -88,7 +88,6 @@ struct LaunchParams {
                            // bit 3: minmax kernel walks tiles strided (blockIdx.x + k * gridDim.x) instead of in contiguous runs,
                            // bit 4: bulk stores evict_last
   uint32_t seg_vpl;        // seg4: 16-byte vectors per lane (4 / 8 / 16); lps = group / (8 * seg_vpl)
-  uint32_t store_mode;     // seg4: 1 = one bulk store per tile (after a consumer-wide barrier) instead of one 2 KB store per warp
   uint32_t col_wide;       // quant_dim = 1: 1 = col_wide_kernel (128 x 256 tiles, CTA-wide ring) instead of col_tma_kernel
   uint32_t col_rows;       // ... rows per tile (128 or 64)
   uint32_t tile_map;       // seg4: 0 = CTA b takes tiles b, b + grid, b + 2 grid, ... (a window of grid tiles slides over the work
@@ -641,14 +640,19 @@ __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParam
   if (GIVEN) {
     prep.setup(t.given_mx, t.given_mn, p.qc, SYM, s_tbl);
   } else {
-    uint32_t pr[VPL];
+    uint32_t pk;
+    if (VPL == 4) {
+      pk = range_max<DT>(range_max<DT>(vec_range<DT, SYM>(v[0]), vec_range<DT, SYM>(v[1])), range_max<DT>(vec_range<DT, SYM>(v[2]), vec_range<DT, SYM>(v[3])));
+    } else {
+      uint32_t pr[VPL];
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) pr[k] = vec_range<DT, SYM>(v[k]);
+      for (int k = 0; k < VPL; ++k) pr[k] = vec_range<DT, SYM>(v[k]);
 #pragma unroll
-    for (int w = VPL / 2; w > 0; w >>= 1)
+      for (int w = VPL / 2; w > 0; w >>= 1)
 #pragma unroll
-      for (int k = 0; k < w; ++k) pr[k] = range_max<DT>(pr[k], pr[k + w]);
-    uint32_t pk = pr[0];
+        for (int k = 0; k < w; ++k) pr[k] = range_max<DT>(pr[k], pr[k + w]);
+      pk = pr[0];
+    }
     // log2(lps) butterfly rounds; lps is launch-uniform, so this is a short uniform loop (no divergence handling)
 #pragma unroll 1
     for (int o = (lps > 32 ? 32 : lps) >> 1; o > 0; o >>= 1) pk = range_max<DT>(pk, __shfl_xor_sync(0xFFFFFFFFu, pk, o));
@@ -719,7 +723,7 @@ __global__ void __launch_bounds__(kConsumers * 4 / VPL + 32, IWQ_SEG4_MINB) seg4
   if (threadIdx.x == 0) {
     for (int i = 0; i < n_stages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], p.store_mode ? 1u : (uint32_t)CWv);
+      mbar_init(&empty[i], (uint32_t)CWv);
     }
     fence_mbar_init();
   }
@@ -757,8 +761,6 @@ __global__ void __launch_bounds__(kConsumers * 4 / VPL + 32, IWQ_SEG4_MINB) seg4
   const int lps = p.lps;                      // lanes per segment = group / 32 (1..32); unused when GIVEN
   const uint32_t lane_vec = (uint32_t)warp * (32u * VPL) + (uint32_t)lane * VPL;  // first vector of this lane in the tile
   const uint32_t rot = VPL == 4 ? (uint32_t)lane >> 1 : (uint32_t)lane;       // rotated vector order: conflict-free LDS.128 / STS.128
-  const bool store_hint = (p.l2_hint & (4u | 16u)) != 0;
-  const uint64_t store_pol = (p.l2_hint & 16u) ? l2_policy_evict_last() : l2_policy_evict_first();
   int stage = 0, prev_stage = -1;
   uint32_t phase = 0;
   const TileWalk walk = make_walk(p);
@@ -772,30 +774,13 @@ __global__ void __launch_bounds__(kConsumers * 4 / VPL + 32, IWQ_SEG4_MINB) seg4
     else
       seg4_consume<DT, KIND, SYM, GIVEN, false, LUT, VPL>(t, p, s_tbl, lbase, lane_vec, rot, lane, lps, warp, xchg);
     fence_proxy_async_smem();
-    if (p.store_mode) {
-      // ONE bulk store per tile: the consumer warps meet at a named barrier, thread 0 sends the whole tile and releases the
-      // previous stage on behalf of everybody
-      asm volatile("bar.sync 15, %0;" ::"n"(CWv * 32) : "memory");
-      if (threadIdx.x == 0) {
-        if (store_hint) tma_store_1d_hint(t.dst, data + (size_t)stage * kTileBytes, t.n_vec * 16u, store_pol);
-        else tma_store_1d(t.dst, data + (size_t)stage * kTileBytes, t.n_vec * 16u);
-        tma_store_commit();
-        tma_store_wait_read<1>();
-        if (prev_stage >= 0) mbar_arrive(&empty[prev_stage]);
-      }
-      prev_stage = stage;
-      if (++stage == n_stages) {
-        stage = 0;
-        phase ^= 1u;
-      }
-      continue;
-    }
     __syncwarp();
     if (lane == 0) {
       const uint32_t w0 = (uint32_t)warp * (32u * VPL);
       if (w0 < t.n_vec) {
         const uint32_t nv = t.n_vec - w0 < 32u * VPL ? t.n_vec - w0 : 32u * VPL;
-        if (store_hint) tma_store_1d_hint(t.dst + (size_t)w0 * 16, data + (size_t)stage * kTileBytes + (size_t)w0 * 16, nv * 16u, store_pol);
+        if (p.l2_hint & (4u | 16u))  // (experiments only; the policy is built here so that it costs the hot path no registers)
+          tma_store_1d_hint(t.dst + (size_t)w0 * 16, data + (size_t)stage * kTileBytes + (size_t)w0 * 16, nv * 16u, (p.l2_hint & 16u) ? l2_policy_evict_last() : l2_policy_evict_first());
         else tma_store_1d(t.dst + (size_t)w0 * 16, data + (size_t)stage * kTileBytes + (size_t)w0 * 16, nv * 16u);
       }
       tma_store_commit();
