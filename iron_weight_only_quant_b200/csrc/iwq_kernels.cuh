@@ -2173,6 +2173,7 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
 #pragma unroll
       for (int j = 0; j < 4; ++j) mx[b][j] = 0u;
     if (live) {
+#pragma unroll 2
       for (uint32_t k = (uint32_t)warp * rps + rph; k < g; k += 8u * rps) {
         uint4 v[4];
 #pragma unroll
@@ -2235,7 +2236,6 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
     }
     __syncthreads();
     float2 S[4][4], R[4][4];
-    uint32_t S2[4][4];
     bool any_bad = false, slow = false;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
@@ -2245,7 +2245,6 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
         const uint32_t f = exch_flags[(b * 4 + j) * 32 + lane];
         S[b][j] = make_float2(e.x, e.y);
         R[b][j] = make_float2(e.z, e.w);
-        S2[b][j] = as_u32(D::from_f32x2(e.x, e.y));
         any_bad |= (f & 1u) != 0u;
         slow |= (f & 2u) != 0u;
       }
@@ -2259,10 +2258,21 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
       const uint32_t val_saddr = smem_u32(smem + 32768 + p.lut_smem_bytes);
       auto sweep2 = [&](auto slow_c) {
       constexpr bool kSlow = decltype(slow_c)::value;  // IEEE division only for degenerate scales: chosen once per tile
-      for (uint32_t k = (uint32_t)warp * rps + rph; k < g; k += 8u * rps) {
+      // the four vectors of the NEXT row offset are requested before the ~550 instructions of the current one run (the loop used
+      // to stall on its own loads: long scoreboard 41 % of the stall samples, profiles/r02_ncu_col_double.txt)
+      const uint32_t k_step = 8u * rps;
+      uint32_t k = (uint32_t)warp * rps + rph;
+      uint4 nv[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) nv[b] = k < g ? ldg128(src + b * blk + (size_t)k * jb.row_bytes) : make_uint4(0u, 0u, 0u, 0u);
+      for (; k < g; k += k_step) {
         uint4 v[4];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) v[b] = ldg128(src + b * blk + (size_t)k * jb.row_bytes);
+        for (int b = 0; b < 4; ++b) v[b] = nv[b];
+        if (k + k_step < g) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) nv[b] = ldg128(src + b * blk + (size_t)(k + k_step) * jb.row_bytes);
+        }
         uint32_t o[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -2286,7 +2296,7 @@ __global__ void __launch_bounds__(256, 2) col_double_kernel(const __grid_constan
             asm("ld.shared.u16 %0, [%1];" : "=h"(lo) : "r"(val_saddr + (idx & 0xFFFFu) * 2u));
             asm("ld.shared.u16 %0, [%1];" : "=h"(hi) : "r"(val_saddr + (idx >> 16) * 2u));
             const T2 dec = from_u32<T2>((uint32_t)lo | ((uint32_t)hi << 16));
-            o[b][j] = as_u32(__hmul2(dec, from_u32<T2>(S2[b][j])));  // decoded * scales   quant_linear.py:606
+            o[b][j] = as_u32(__hmul2(dec, D::from_f32x2(S[b][j].x, S[b][j].y)));  // decoded * scales   quant_linear.py:606
           }
         }
 #pragma unroll
