@@ -223,6 +223,19 @@ def test_dispatch_plan_for_the_baseline_shapes(built):
     p = plan(8192, 8192, group=256, bits=4, quant_dim=1)  # warp-private 2-D tensor-map boxes: 256 rows x 32 columns = 16 KB, one stage
     assert p[0] == COL_TMA and p[3] == 1 and p[5] == 16384 and p[7] == 32, p
     assert plan(64, 128, group=32, bits=4, quant_dim=1)[0] == COL_TMA  # smaller than one wide tile
+    # minifloats with quant_dim = 1 (what the reference's scripts run): full 128 x 256 tiles always; the direct table only when it
+    # fits next to three of them (FP4 on fp16; every format on bf16), else the step table
+    fp = dict(scheme=built.SCHEME_FP_CODEC, symmetric=True, quant_dim=1)
+    p = plan(8192, 8192, group=128, exp_bits=2, mant_bits=1, **fp)
+    assert p[0] == COL_WIDE and p[3] == 3 and p[4] == 128 and p[6] == 1 and p[7] == 256, p
+    p = plan(8192, 8192, group=128, exp_bits=4, mant_bits=3, **fp)
+    assert p[0] == COL_WIDE and p[3] == 3 and p[4] == 128 and p[6] == 0 and p[7] == 256, p
+    p = plan(8192, 8192, group=64, exp_bits=3, mant_bits=2, approx=1, hi_align_start=4, hi_align_exp_field=6, tail_pad_bits=0, **fp)
+    assert p[0] == COL_WIDE and p[3] == 3 and p[4] == 128 and p[6] == 0 and p[7] == 256, p
+    cfg16 = built.make_config(torch.bfloat16, built.SCHEME_FP_CODEC, 128, exp_bits=4, mant_bits=3, symmetric=True, quant_dim=1)
+    out16 = (ctypes.c_int32 * 8)()
+    built.check(L.iwq_debug_plan(ctypes.byref(cfg16), 8192, 8192, out16))
+    assert out16[0] == COL_WIDE and out16[6] == 1 and out16[7] == 256, list(out16)
     assert plan(8192, 8192, group=512, bits=4, quant_dim=1)[0] == COL_ASYNC  # boxes are at most 256 rows
     assert plan(8192, 8192, group=-2, bits=4, quant_dim=1)[0] == COL_2SWEEP
     assert plan(8192, 8192, group=96, bits=4, quant_dim=1)[0] == COL_2SWEEP
