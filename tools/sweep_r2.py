@@ -87,7 +87,11 @@ def main():
             keep.append((s, z))
             descs.append(_lib.matrix_desc(w, w, o, k, s, z))
         rng = torch.empty(2 * len(descs), dtype=torch.float32, device=dev)
-        if c["group"] == -1:
+        if c["group"] == -1 and c.get("fused"):
+
+            def fn():
+                _lib.per_tensor_fused_(descs, cfg, dev, None, track_status=False)
+        elif c["group"] == -1:
             # single-GPU per-tensor: the library orders range / apply passes itself (iwq_fake_quant_batched is not for
             # per-tensor; go through minmax + with_range for the classic order, or the per-tensor batched entry)
             def fn():
