@@ -1916,7 +1916,7 @@ __global__ void __launch_bounds__(kColWideWarps * 32 + 32, 1) col_wide_kernel(co
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], WG);
     }
-    for (int i = 0; i < 2 * kColWideGroups; ++i) flags_all[i] = 0u;
+    for (int i = 0; i < 2 * 4 * kColWideGroups; ++i) flags_all[i] = 0u;
     fence_mbar_init();
   }
   __syncthreads();
@@ -1973,15 +1973,18 @@ __global__ void __launch_bounds__(kColWideWarps * 32 + 32, 1) col_wide_kernel(co
     uni.setup2(1.0f, -1.0f, 1.0f, -1.0f, p.qc, SYM, s_tbl, &a, &b, &c, &d, &bad);
   }
   const uint32_t gi = (uint32_t)warp / WG, wg = (uint32_t)warp % WG;
-  const uint32_t t_g = threadIdx.x - gi * GT;                   // thread within the group
   const uint32_t my_blk = wg / wpb;                             // row block of this warp's rows within the tile
+  // the warps of a ROW BLOCK synchronise among themselves only (group 64: 4 warps, group 32: 2): the row blocks of a tile are
+  // independent, so a block's parameter phase overlaps the sweeps of the others
+  const uint32_t blk_threads = wpb * 32u;
+  const uint32_t t_b = threadIdx.x - gi * GT - my_blk * blk_threads;  // thread within the row block's warps
   uint8_t* part = part_all + (size_t)gi * (kPartBytes / kColWideGroups);
   uint8_t* pars = pars_all + (size_t)gi * pars_bytes;
-  uint32_t* flags = flags_all + 2u * gi;
+  uint32_t* flags = flags_all + 2u * (gi * 4u + my_blk);
   uint4* part_mx = reinterpret_cast<uint4*>(part) + (size_t)wg * (kPW / 4) + lane;  // [warp][0][lane]
   uint4* part_mn = part_mx + 32;                                                 // [warp][1][lane]
   const uint32_t* part_w = reinterpret_cast<const uint32_t*>(part);             // word view: [warp][max | min][128 pairs]
-  const uint32_t bar_id = 1u + gi;
+  const uint32_t bar_id = 1u + gi * ((uint32_t)WG / wpb) + my_blk;  // <= 8 named barriers
   int fenced = -1;
   uint32_t parity = 0;
   for (uint32_t i = gi;; i += kColWideGroups) {
@@ -2013,12 +2016,12 @@ __global__ void __launch_bounds__(kColWideWarps * 32 + 32, 1) col_wide_kernel(co
     }
     *part_mx = make_uint4(mx[0], mx[1], mx[2], mx[3]);
     if (!SYM) *part_mn = make_uint4(mn[0], mn[1], mn[2], mn[3]);
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(GT) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(blk_threads) : "memory");
 
-    // ---- parameters: one column pair per thread (while this group computes them the other group sweeps its own tile) ----
-    if (t_g == 0) flags[parity ^ 1u] = 0u;  // the other parity's flag: read by everybody before this tile's first barrier, set again after the next one
-    for (uint32_t pp = t_g; pp < n_pairs; pp += GT) {
-      const uint32_t b = pp / half_cc, q = pp - b * half_cc;
+    // ---- parameters of this row block: one column pair per thread (the other row blocks / the other group keep sweeping) ----
+    if (t_b == 0) flags[parity ^ 1u] = 0u;  // the other parity's flag: read by everybody before this tile's first barrier, set again after the next one
+    for (uint32_t q = t_b; q < half_cc; q += blk_threads) {
+      const uint32_t b = my_blk;
       uint32_t mxs = ident_max, mns = ident_min;
       for (uint32_t w = b * wpb; w < (b + 1u) * wpb; ++w) {
         mxs = as_u32(__hmax2_nan(from_u32<T2>(mxs), from_u32<T2>(part_w[w * kPW + q])));
@@ -2055,7 +2058,7 @@ __global__ void __launch_bounds__(kColWideWarps * 32 + 32, 1) col_wide_kernel(co
 #pragma unroll
       for (int u = 0; u < kU; ++u) dst[u * 32] = make_uint4(wds[4 * u], wds[4 * u + 1], wds[4 * u + 2], wds[4 * u + 3]);
     }
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(GT) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(blk_threads) : "memory");
 
     // ---- sweep 2: the constants of this lane's 4 pairs, then quantise in place ----
     PP prep[4];
