@@ -644,7 +644,8 @@ static int run_batched(const iwq_config_t* cfg, const iwq_matrix_t* ms, int n, v
       const bool fp_step = kind == KIND_FP && !p.qc.lut_direct;
       if (kind != KIND_INT_GENERIC && !fp_step) {
         for (int v = want; v > 4; v >>= 1) {
-          if (per_tensor || (pl.seg_elems % (8u * (uint32_t)v) == 0 && pl.seg_elems <= 1024u)) {
+          // (lanes per segment = seg / (8 v) must stay within one warp: 2048 / 4096-element per-channel rows qualify at v = 16)
+          if (per_tensor || (pl.seg_elems % (8u * (uint32_t)v) == 0 && pl.seg_elems / (8u * (uint32_t)v) <= 32u)) {
             vpl = v;
             break;
           }
