@@ -363,6 +363,13 @@ static int make_plan(const iwq_config_t* cfg, int64_t cols, uint32_t lut_bytes, 
   if (st > 4 && knobs().row_smem_kb <= 0) st = 4;
   if (st > kMaxStages) st = kMaxStages;
   pl->stages = st;
+  // rings of which exactly two fit an SM (24-36 KB rows, e.g. the 13824-wide rows of LLaMA-2-13B): 8 consumer warps per CTA instead of
+  // 4 -- 6039 against 5654 GB/s (profiles/r02_sweep_row24.jsonl); with three or more resident CTAs (11008-wide rows) and with a single one
+  // (28672-wide rows) 4 warps stay ahead
+  if (!minifloat && knobs().row_warps <= 0 && warps == 4) {
+    const uint64_t cta_smem = kSmemHeader + (uint64_t)lut_bytes + (uint64_t)st * stage;
+    if ((227ull * 1024) / cta_smem == 2) pl->consumers = 32 * 8;
+  }
   return IWQ_OK;
 }
 

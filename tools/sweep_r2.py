@@ -26,12 +26,16 @@ def main():
     ap.add_argument("--rounds", type=int, default=3)
     ap.add_argument("--fresh", action="store_true", help="restore pristine weights before every timed pass (data-dependent kernels)")
     ap.add_argument("--knobs", default="", help="';'-separated knob sets, each 'name=value,name=value'")
+    ap.add_argument("--shape", default="", help="rows,cols[,count]: `count` matrices of this shape instead of a model's layers")
     ap.add_argument("--shards", type=int, default=0, help="row-split every matrix this many ways and keep shard 0 (config 4 per-rank sizes)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     dt = torch.float16 if args.dtype == "f16" else torch.bfloat16
     m = shapes.MODELS[args.model]
     mats = m.matrices(range(args.layers if args.layers > 0 else m.n_layers))
+    if args.shape:
+        f = [int(x) for x in args.shape.split(",")]
+        mats = [(f[0], f[1])] * (f[2] if len(f) > 2 else 1)
     if args.shards:
         mats = [(o // args.shards, k) for o, k in mats]
     ws = [(torch.randn(o, k, device=dev, dtype=torch.float32) * 0.02).to(dt) for o, k in mats]
