@@ -223,3 +223,52 @@ def test_alternate_kernel_variants_match_oracle(knobs, tmp_path):
         env[k] = v
     out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300, env=env)
     assert "ALT_OK" in out.stdout, knobs + ": " + out.stdout[-1500:] + out.stderr[-1500:]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_column_configurations_wide_tiles(seed):
+    """quant_dim = 1 on shapes that reach col_wide_kernel (rows >= 128, cols >= 256): several 128-row tiles, ragged last
+    column tile, row counts that are not a multiple of the tile (rows = group x odd), every scheme / dtype, adversarial
+    values; scales and zero points in the reference's column-major segment order."""
+    rng = np.random.default_rng([2000 + seed])
+    for case in range(8):
+        dt = ["f16", "bf16"][int(rng.integers(0, 2))]
+        scheme = ["int", "fp", "bfp", "int"][int(rng.integers(0, 4))]
+        grp = int(rng.choice([32, 64, 128]))
+        rows = grp * int(rng.integers(max(1, 128 // grp), 40 if grp == 32 else 13))
+        rows = max(rows, 128)
+        cols = 8 * int(rng.integers(32, 170))
+        w = adversarial(rng, rows, cols, dt)
+        sym = bool(rng.integers(0, 2))
+        if scheme == "int":
+            nb = int(rng.choice([2, 3, 4, 5, 8]))
+            kw = dict(bits=nb, symmetric=sym)
+            sid, fn, args = _lib.SCHEME_INT, O.int_fake_quant, (dt, nb, not sym, grp)
+        elif scheme == "fp":
+            E, M = FP_FORMATS[int(rng.integers(0, len(FP_FORMATS)))]
+            kw = dict(exp_bits=E, mant_bits=M, symmetric=sym)
+            sid, fn, args = _lib.SCHEME_FP_CODEC, O.fp_codec_fake_quant, (dt, E, M, sym, grp)
+        else:
+            nb = int(rng.choice([4, 6, 8]))
+            kw = dict(bits=nb, symmetric=True)
+            sid, fn, args = _lib.SCHEME_BFP, O.bfp_fake_quant, (dt, nb, grp)
+        tag = f"seed{seed}/{case} {dt} {scheme} {kw} g{grp} d1 [{rows},{cols}]"
+        ref = O.along_output_dim(fn, bits(w), *args)
+        G = _lib.num_segments(rows, cols, grp, 1)
+        scales = torch.zeros(G, dtype=TDT[dt], device=DEV)
+        zeros = torch.zeros(G, dtype=TDT[dt], device=DEV)
+        emit_z = scheme != "bfp" and not sym
+        # in place and batched with a second matrix of another shape (tensor maps per matrix behind the job table)
+        wd = w.to(DEV)
+        w2 = adversarial(rng, 256, 264, dt)
+        ref2 = O.along_output_dim(fn, bits(w2), *args)
+        w2d = w2.to(DEV)
+        cfg = _lib.make_config(TDT[dt], sid, grp, quant_dim=1, **kw)
+        mats = [_lib.matrix_desc(wd, wd, rows, cols, None if scheme == "bfp" else scales, zeros if emit_z else None), _lib.matrix_desc(w2d, w2d, 256, 264)]
+        _lib.fake_quant_batched_(mats, cfg, torch.device(DEV), track_status=False)
+        same(bits(wd), ref["out"], dt, tag)
+        same(bits(w2d), ref2["out"], dt, tag + " (second matrix of the batch)")
+        if scheme != "bfp":
+            same(bits(scales), ref["scales"], dt, tag + " scales")
+        if emit_z and "zeros" in ref:
+            same(bits(zeros), ref["zeros"], dt, tag + " zeros")
