@@ -250,9 +250,32 @@ def gen_dim1_approx(out: dict):
             quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
 
 
+ODD_CASES = [  # (shape, kwargs of pseudo_quantize_tensor): segments that are not whole 16-byte vectors, 1-row / 3-D inputs
+    ((3, 5), dict(per_tensor=True)), ((7, 129), dict(per_tensor=True)), ((7, 129), dict()), ((5, 36), dict(q_group_size=12)),
+    ((1, 8), dict(per_tensor=True)), ((2, 3, 40), dict(q_group_size=20)), ((6, 1000), dict()), ((1, 3), dict()), ((3, 51216), dict()),
+]
+
+
+def gen_odd(out: dict):
+    """quant_funcs.pseudo_quantize_tensor (quant_funcs.py:4-46) on shapes outside the vectorised kernels' direct reach (round 2:
+    the advisor's [3,5] / [7,129] per-tensor cases and friends; the last one is a per-channel row longer than any ring stage)."""
+    for dn, dt in TORCH_DT.items():
+        for ci, (shape, kw) in enumerate(ODD_CASES):
+            g = torch.Generator().manual_seed(500 + ci)
+            n = int(np.prod(shape))
+            w = (torch.randn(n, generator=g) * 0.02).reshape(shape).to(dt)
+            out[f"w_{dn}_{ci}"] = bits_of(w)
+            for bits, zp in ((4, True), (4, False), (8, True), (3, False)):
+                y = quant_funcs.pseudo_quantize_tensor(w.clone(), n_bits=bits, zero_point=zp, **kw)
+                out[f"{dn}_{ci}_b{bits}_{'asym' if zp else 'sym'}"] = bits_of(y)
+
+
 def main():
     torch.set_num_threads(8)
-    for name, fn in (("golden_int", gen_int), ("golden_fp_chain", gen_fp_chain), ("golden_fp_tables", gen_fp_tables), ("golden_fp_rne", gen_fp_rne), ("golden_bfp", gen_bfp), ("golden_dim1_approx", gen_dim1_approx)):
+    only = sys.argv[1:]
+    for name, fn in (("golden_odd", gen_odd), ("golden_int", gen_int), ("golden_fp_chain", gen_fp_chain), ("golden_fp_tables", gen_fp_tables), ("golden_fp_rne", gen_fp_rne), ("golden_bfp", gen_bfp), ("golden_dim1_approx", gen_dim1_approx)):
+        if only and name not in only:
+            continue
         d = {}
         fn(d)
         d["_meta"] = np.array([f"torch {torch.__version__}; reference at {REF}; cpu"], dtype="U")

@@ -811,3 +811,21 @@ def test_quant_dim1_equals_transposed_quant_dim0_full_size(shape):
         assert torch.equal(s1.view(torch.int16), s0.view(torch.int16)), name + " scales"
         assert torch.equal(z1.view(torch.int16), z0.view(torch.int16)), name + " zeros"
     assert _lib.read_and_clear_status(torch.device(DEV)) & _lib.STATUS_NAN == 0
+
+
+ODD_GOLDEN = [((3, 5), dict(per_tensor=True)), ((7, 129), dict(per_tensor=True)), ((7, 129), dict()), ((5, 36), dict(q_group_size=12)),
+              ((1, 8), dict(per_tensor=True)), ((2, 3, 40), dict(q_group_size=20)), ((6, 1000), dict()), ((1, 3), dict()), ((3, 51216), dict())]
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_odd_shapes_match_reference_golden(golden, dt):
+    """pseudo_quantize_tensor on the shapes of tests/golden/golden_odd.npz against the reference's own outputs: numel not a multiple of 8
+    per tensor, 129- and 1000-wide rows per channel, group 12 / 20, a 3-D input, and a per-channel row of 51216 elements (longer than
+    any ring stage: it goes through the two-pass kernels, one job per row)."""
+    g = golden("golden_odd")
+    for ci, (shape, kw) in enumerate(ODD_GOLDEN):
+        w = tensor_of(g[f"w_{dt}_{ci}"], dt)
+        assert tuple(w.shape) == shape
+        for nb, zp in ((4, True), (4, False), (8, True), (3, False)):
+            out = quant_funcs.pseudo_quantize_tensor(w, n_bits=nb, zero_point=zp, **kw)
+            assert_bits(bits(out), g[f"{dt}_{ci}_b{nb}_{'asym' if zp else 'sym'}"], dt, f"{dt} {shape} {kw} b{nb} zp={zp}")

@@ -241,3 +241,21 @@ def test_approximate_decode_matches_reference(golden, dtype, case):
     r = O.along_output_dim(O.fp_approx_fake_quant, w, dtype, E, M, 128, hs, hf, tp, dbl)
     assert _nan_equal_bits(r["out"], g[f"{dtype}_approx_{name}_g128_d1_out"], dtype), "quant_dim 1"
     assert np.array_equal(r["scales_half"], g[f"{dtype}_approx_{name}_g128_d1_scales"])
+
+
+ODD_CASES = [((3, 5), dict(per_tensor=True), -1), ((7, 129), dict(per_tensor=True), -1), ((7, 129), dict(), -2), ((5, 36), dict(q_group_size=12), 12),
+             ((1, 8), dict(per_tensor=True), -1), ((2, 3, 40), dict(q_group_size=20), 20), ((6, 1000), dict(), -2), ((1, 3), dict(), -2), ((3, 51216), dict(), -2)]
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+def test_int_odd_shapes_match_reference(golden, dtype):
+    """The oracle on shapes whose segments are not whole 16-byte vectors, against what the reference itself returns
+    (quant_funcs.py:10-15 takes any shape; tests/golden/golden_odd.npz)."""
+    g = golden("golden_odd")
+    for ci, (shape, _kw, grp) in enumerate(ODD_CASES):
+        wb = g[f"w_{dtype}_{ci}"]
+        assert wb.shape == shape
+        for bits, zp in ((4, True), (4, False), (8, True), (3, False)):
+            ref = g[f"{dtype}_{ci}_b{bits}_{'asym' if zp else 'sym'}"]
+            got = O.int_fake_quant(wb.reshape(-1, shape[-1]), dtype, bits, zp, grp)["out"].reshape(shape)
+            assert _nan_equal_bits(got, ref, dtype), (shape, bits, zp)
