@@ -250,6 +250,48 @@ def gen_dim1_approx(out: dict):
             quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
 
 
+def gen_dim1_wide(out: dict):
+    """quant_dim = 1 on a [256, 264] matrix -- two 128-row tiles and a ragged second column tile of col_wide_kernel (round 2) --
+    through QuantLinear.from_linear exactly as main.py builds it: INT, BFP, exact and single-approximate FP at group 64 / 128."""
+    g = torch.Generator().manual_seed(11)
+    master = torch.randn(256, 264, generator=g) * 0.02
+    master[:, 200] = 0.0113
+    master[:, 201] = 0.0
+    master[:, 202] = torch.randn(256, generator=g).abs() * 0.05 + 0.01
+    master[:, 203] = torch.randn(256, generator=g) * 1e-6
+    master[::3, 260] = 0.0
+    master[1::6, 260] = -0.0
+    master[100, 261] = 2.0
+    for dn, dt in TORCH_DT.items():
+        w = master.to(dt)
+        out[f"w_{dn}"] = bits_of(w)
+
+        def run(key, **kw):
+            lin = torch.nn.Linear(w.shape[1], w.shape[0], bias=False)
+            lin.weight.data = w.clone()
+            ql = quant_linear.QuantLinear.from_linear(lin, **kw)
+            out[f"{dn}_{key}_out"] = bits_of(ql.weight.data)
+            if ql.scales is not None:
+                out[f"{dn}_{key}_scales"] = bits_of(ql.scales.reshape(-1))
+            if ql.zeros is not None:
+                out[f"{dn}_{key}_zeros"] = bits_of(ql.zeros.reshape(-1))
+
+        quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
+        run("int4_asym_g128", w_bit=4, w_group_size=128, symmetric=False, weight_format="int", quant_dim=1)
+        run("int3_sym_g64", w_bit=3, w_group_size=64, symmetric=True, weight_format="int", quant_dim=1)
+        run("bfp4_g128", w_bit=4, w_group_size=128, symmetric=True, weight_format="bfp", quant_dim=1)
+        run("fp4_sym_g128", w_bit=4, w_group_size=128, symmetric=True, weight_format="fp4", quant_dim=1)
+        run("fp8_asym_g64", w_bit=8, w_group_size=64, symmetric=False, weight_format="fp8", quant_dim=1)
+        for name, wf, E, M, hs, hf, tp, dbl in APPROX_CASES:
+            if dbl or name in ("e1m2_s", "e2m3_s"):
+                continue
+            quant_linear.configure_fp_formats(**{f"{wf}_exp_bits": E, f"{wf}_mantissa_bits": M})
+            kw = {f"{wf}_hi_align_start": hs, f"{wf}_hi_align_exp_field": hf, f"{wf}_tail_pad_bits": tp}
+            for grp in (64, 128):
+                run(f"approx_{name}_g{grp}", w_bit=4, w_group_size=grp, symmetric=True, weight_format=wf, approximate=True, double_approximate=False, quant_dim=1, **kw)
+            quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
+
+
 ODD_CASES = [  # (shape, kwargs of pseudo_quantize_tensor): segments that are not whole 16-byte vectors, 1-row / 3-D inputs
     ((3, 5), dict(per_tensor=True)), ((7, 129), dict(per_tensor=True)), ((7, 129), dict()), ((5, 36), dict(q_group_size=12)),
     ((1, 8), dict(per_tensor=True)), ((2, 3, 40), dict(q_group_size=20)), ((6, 1000), dict()), ((1, 3), dict()), ((3, 51216), dict()),
@@ -273,7 +315,7 @@ def gen_odd(out: dict):
 def main():
     torch.set_num_threads(8)
     only = sys.argv[1:]
-    for name, fn in (("golden_odd", gen_odd), ("golden_int", gen_int), ("golden_fp_chain", gen_fp_chain), ("golden_fp_tables", gen_fp_tables), ("golden_fp_rne", gen_fp_rne), ("golden_bfp", gen_bfp), ("golden_dim1_approx", gen_dim1_approx)):
+    for name, fn in (("golden_dim1_wide", gen_dim1_wide), ("golden_odd", gen_odd), ("golden_int", gen_int), ("golden_fp_chain", gen_fp_chain), ("golden_fp_tables", gen_fp_tables), ("golden_fp_rne", gen_fp_rne), ("golden_bfp", gen_bfp), ("golden_dim1_approx", gen_dim1_approx)):
         if only and name not in only:
             continue
         d = {}

@@ -829,3 +829,38 @@ def test_odd_shapes_match_reference_golden(golden, dt):
         for nb, zp in ((4, True), (4, False), (8, True), (3, False)):
             out = quant_funcs.pseudo_quantize_tensor(w, n_bits=nb, zero_point=zp, **kw)
             assert_bits(bits(out), g[f"{dt}_{ci}_b{nb}_{'asym' if zp else 'sym'}"], dt, f"{dt} {shape} {kw} b{nb} zp={zp}")
+
+
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+def test_quant_dim1_wide_tiles_match_reference_golden(golden, dt):
+    """QuantLinear.from_linear(..., quant_dim=1) on the [256, 264] fixture minted from the reference (golden_dim1_wide.npz): two 128-row
+    tiles and a ragged second column tile of col_wide_kernel -- INT (scales and zero points in the reference's order), BFP, exact FP4 /
+    asymmetric FP8, and the single-approximate decode of FP4 / FP6 / FP8 at group 64 and 128 (scripts/*/scripts_*.sh)."""
+    g = golden("golden_dim1_wide")
+    w = tensor_of(g[f"w_{dt}"], dt)
+    quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
+
+    def check(key, **kw):
+        ql = _from_linear(w, dt, quant_dim=1, **kw)
+        assert_bits(bits(ql.weight.data), g[f"{dt}_{key}_out"], dt, f"{dt} {key}")
+        if f"{dt}_{key}_scales" in g.files:
+            assert np.array_equal(bits(ql.scales.reshape(-1)), g[f"{dt}_{key}_scales"]), f"{dt} {key} scales"
+        if f"{dt}_{key}_zeros" in g.files:
+            assert np.array_equal(bits(ql.zeros.reshape(-1)), g[f"{dt}_{key}_zeros"]), f"{dt} {key} zeros"
+
+    check("int4_asym_g128", w_bit=4, w_group_size=128, symmetric=False, weight_format="int")
+    check("int3_sym_g64", w_bit=3, w_group_size=64, symmetric=True, weight_format="int")
+    check("bfp4_g128", w_bit=4, w_group_size=128, symmetric=True, weight_format="bfp")
+    check("fp4_sym_g128", w_bit=4, w_group_size=128, symmetric=True, weight_format="fp4")
+    check("fp8_asym_g64", w_bit=8, w_group_size=64, symmetric=False, weight_format="fp8")
+    try:
+        for name, wf, E, M, hs, hf, tp in SINGLE_APPROX:
+            if name in ("e1m2_s", "e2m3_s"):
+                continue
+            quant_linear.configure_fp_formats(**{f"{wf}_exp_bits": E, f"{wf}_mantissa_bits": M})
+            kw = {f"{wf}_hi_align_start": hs, f"{wf}_hi_align_exp_field": hf, f"{wf}_tail_pad_bits": tp}
+            for grp in (64, 128):
+                check(f"approx_{name}_g{grp}", w_bit=4, w_group_size=grp, symmetric=True, weight_format=wf, approximate=True, **kw)
+            quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)
+    finally:
+        quant_linear.configure_fp_formats(2, 1, 3, 2, 4, 3)

@@ -259,3 +259,30 @@ def test_int_odd_shapes_match_reference(golden, dtype):
             ref = g[f"{dtype}_{ci}_b{bits}_{'asym' if zp else 'sym'}"]
             got = O.int_fake_quant(wb.reshape(-1, shape[-1]), dtype, bits, zp, grp)["out"].reshape(shape)
             assert _nan_equal_bits(got, ref, dtype), (shape, bits, zp)
+
+
+WIDE_APPROX = [c for c in APPROX_CASES if not c[6] and c[0] not in ("e1m2_s", "e2m3_s")]
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+def test_quant_dim1_wide_matches_reference(golden, dtype):
+    """quant_dim = 1 on the [256, 264] fixture (the shape class col_wide_kernel serves): oracle == reference."""
+    g = golden("golden_dim1_wide")
+    w = g[f"w_{dtype}"]
+    r = O.along_output_dim(O.int_fake_quant, w, dtype, 4, True, 128)
+    assert _nan_equal_bits(r["out"], g[f"{dtype}_int4_asym_g128_out"], dtype)
+    assert _nan_equal_bits(r["scales"], g[f"{dtype}_int4_asym_g128_scales"], dtype)
+    assert np.array_equal(r["zeros"], g[f"{dtype}_int4_asym_g128_zeros"])
+    r = O.along_output_dim(O.int_fake_quant, w, dtype, 3, False, 64)
+    assert _nan_equal_bits(r["out"], g[f"{dtype}_int3_sym_g64_out"], dtype)
+    r = O.along_output_dim(O.bfp_fake_quant, w, dtype, 4, 128)
+    assert _nan_equal_bits(r["out"], g[f"{dtype}_bfp4_g128_out"], dtype)
+    r = O.along_output_dim(O.fp_codec_fake_quant, w, dtype, 2, 1, True, 128)
+    assert _nan_equal_bits(r["out"], g[f"{dtype}_fp4_sym_g128_out"], dtype)
+    r = O.along_output_dim(O.fp_codec_fake_quant, w, dtype, 4, 3, False, 64)
+    assert _nan_equal_bits(r["out"], g[f"{dtype}_fp8_asym_g64_out"], dtype)
+    for name, E, M, hs, hf, tp, _ in WIDE_APPROX:
+        for grp in (64, 128):
+            r = O.along_output_dim(O.fp_approx_fake_quant, w, dtype, E, M, grp, hs, hf, tp, False)
+            assert _nan_equal_bits(r["out"], g[f"{dtype}_approx_{name}_g{grp}_out"], dtype), (name, grp)
+            assert np.array_equal(r["scales_half"], g[f"{dtype}_approx_{name}_g{grp}_scales"]), (name, grp)
