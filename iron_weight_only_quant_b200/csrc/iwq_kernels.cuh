@@ -612,18 +612,20 @@ __global__ void __launch_bounds__(kConsumers + 32) seg_tma_kernel(const __grid_c
 //
 //   global --TMA bulk load--> shared stage --LDS.128--> registers --STS.128--> same stage --TMA bulk store--> global
 //
-// Each lane owns FOUR consecutive 16-byte vectors (32 elements) of its warp's 2 KB slice of the tile, so a
-// segment of `group` elements is held by group/32 lanes: the min/max reduction needs log2(group/32) shuffle
-// rounds and the scale / zero-point arithmetic is done once per 32 elements instead of once per 8.
-// Lane L touches its vectors in the rotated order (k + L/2) mod 4, which makes every LDS.128 / STS.128
-// quarter-warp hit 8 distinct 16-byte bank groups (conflict-free) although lanes are 64 bytes apart.
-// Results go back into the lane's own 64 bytes of the stage; one elected lane per warp issues a 2 KB bulk
-// store, and hands the stage back to the producer once the PREVIOUS tile's store has finished reading
-// shared memory (cp.async.bulk.wait_group.read 1), so the store latency is never exposed.
+// One CTA per SM: a producer lane streams 48 KB tiles (one cp.async.bulk each) into a ring of 4 stages; 96 / VPL consumer warps.
+// Each lane owns VPL consecutive 16-byte vectors (VPL = 4: 32 elements, 64 bytes; 8; 16: a whole group of 128) of its warp's
+// VPL x 512-byte slice of the tile, so a segment of `group` elements is held by group / (8 VPL) lanes: the min/max reduction
+// needs log2 of that many shuffle rounds and the scale / zero-point arithmetic is done once per lane.
+// Lane L touches its vectors in a rotated order -- (k + L/2) mod 4 at VPL 4, (k + L) mod VPL otherwise -- which makes every
+// LDS.128 / STS.128 quarter-warp hit 8 distinct 16-byte bank groups (conflict-free) although lanes are 64 / 128 / 256 bytes apart.
+// Results go back into the lane's own bytes of the stage; one elected lane per warp issues one bulk store for the warp's slice,
+// and hands the stage back to the producer once the PREVIOUS tile's store has finished reading shared memory
+// (cp.async.bulk.wait_group.read 1), so the store latency is never exposed.
 // No per-element global store instructions, no per-vector address arithmetic.
+// (25 warps per CTA: one SM sub-partition holds 7 of them, so the VPL = 4 form must fit 72 registers per thread.)
 // ------------------------------------------------------------------------------------------------
-// One lane's share of a tile in seg4_tma_kernel: four vectors through registers, results back to the stage.
-// FAST = full 16 KB tile and no code emission: no per-vector predicates at all.
+// One lane's share of a tile in seg4_tma_kernel: VPL vectors through registers, results back to the stage.
+// FAST = full tile and no code emission: no per-vector predicates at all.
 template <int DT, int KIND, bool SYM, bool GIVEN, bool FAST, int LUT = LUT_STEP, int VPL = 4>
 __device__ __forceinline__ void seg4_consume(const TileCtx& t, const LaunchParams& p, const FpStep* s_tbl, uint8_t* lbase, uint32_t lane_vec,
                                              uint32_t rot, int lane, int lps, int warp, uint32_t* xchg) {
