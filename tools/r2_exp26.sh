@@ -1,5 +1,6 @@
 #!/bin/bash
-# round 2, experiment 26: FP8 E4M3 on fp16 (38 KB direct table): 40 KB tiles x 4 stages vs 48 KB tiles x 3 stages
+# round 2, experiment 26: FP8 E4M3 on fp16 (38 KB direct table): 40 KB tiles x 4 stages vs 48 KB tiles x 3 stages.  The IWQ_FP_TILE40 knob and the
+# 40 KB-tile instantiation this script drove were measured slower and removed again (profiles/r02_sweep_fp26_tile40.jsonl); kept for the record.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q -k "fp_chain or fp_codec or fp_rne or fuzz or variants or approx or smoke or hf_arch" > gpurun_out/r2_tests26.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2_tests26.log
