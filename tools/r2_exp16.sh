@@ -1,5 +1,6 @@
 #!/bin/bash
 # round 2, experiment 16: seg4 with 8 / 16 vectors per lane (fewer lanes repeat the segment parameters), one bulk store per tile
+# (the seg_store knob of this script -- one bulk store per tile -- was measured 1-2 % slower and removed again; those knob sets now report "unknown knob")
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 for v in 8 16; do
